@@ -1,0 +1,177 @@
+/*
+ * libknockoffs_b200 -- C ABI of the B200-native (sm_100a) model-X Gaussian knockoff hot path.
+ *
+ * Drop-in boundary for biona001/Knockoffs.jl v2.0.2 (paths below are relative to that repo):
+ * Julia keeps argument handling and struct construction; everything from `solve_s(...)`
+ * (src/modelX.jl:62) through `condition(...)` (src/modelX.jl:64) is one of the calls below.
+ * INTEGRATION.md shows the `ccall` stubs a maintainer would add.
+ *
+ * Conventions
+ *   - all matrices are column-major FP64 with leading dimension = number of rows
+ *     (Julia `Matrix{Float64}`); sizes are int64_t; `groups` are 1-based int64 ids.
+ *   - Sigma is read from its UPPER triangle only (`Symmetric(Sigma)`, default uplo = :U) and
+ *     no input is ever written (reference guarantee: test/runtests.jl:582-583).
+ *   - host entry points take HOST pointers, copy in/out and hold no pointer after return;
+ *     `_dev` variants take DEVICE pointers on the context's device and run on ctx's stream.
+ *   - every function returns an int status (below); kb_last_error() gives the message.
+ *     Nothing aborts, nothing prints unless opts->verbose.
+ *   - one kb_ctx per host thread; distinct contexts may be used concurrently.
+ */
+#ifndef KNOCKOFFS_B200_H
+#define KNOCKOFFS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (map to the reference's exceptions) ------------------------------------ */
+#define KB_OK 0
+#define KB_ERR_INVALID (-1) /* error("m should be 1 or larger ...") modelX.jl:105, utilities.jl:28,46,301-302 */
+#define KB_ERR_NOT_PD (-2)  /* PosDefException: initial cholesky utilities.jl:140,237,309; downdate :591-593 */
+#define KB_ERR_NAN (-3)     /* "δj is Inf/NaN, aborting" utilities.jl:195-196 */
+#define KB_ERR_CUDA (-4)    /* CUDA / NCCL / out-of-memory */
+
+/* ---- methods ----------------------------------------------------------------------------- */
+#define KB_METHOD_MVR 0     /* :mvr     -> solve_MVR          utilities.jl:124-175 */
+#define KB_METHOD_MAXENT 1  /* :maxent  -> solve_max_entropy  utilities.jl:221-280 */
+#define KB_METHOD_SDP_CCD 2 /* :sdp_ccd -> solve_sdp_ccd      utilities.jl:291-343 (group :sdp likewise is CCD) */
+#define KB_METHOD_EQUI 3    /* :equi    -> solve_equi         utilities.jl:104-111 */
+
+/* solver execution modes (same mathematics, different kernels) */
+#define KB_MODE_AUTO 0
+#define KB_MODE_STREAM 1  /* persistent kernel, one rank-1 streaming pass over the resident triangle per coordinate */
+
+#define KB_MAX_TRACE 128
+
+typedef struct kb_ctx kb_ctx;
+
+/* Options of solve_s's keyword arguments (utilities.jl:124-133, 221-230, 291-300).
+ * kb_default_solve_opts() fills the reference defaults. */
+typedef struct {
+    int32_t niter;       /* 100 */
+    double tol;          /* 1e-6 */
+    double lambda_min;   /* λmin = 1e-6 (MVR / maxent) */
+    double sdp_lambda;   /* λ = 0.5 (sdp_ccd barrier) */
+    double sdp_mu;       /* μ = 0.8 (sdp_ccd decay) */
+    int32_t robust;      /* accepted, no effect on results beyond rounding */
+    int32_t verbose;     /* per-sweep trace is always returned in kb_solve_info */
+    int32_t mode;        /* KB_MODE_* */
+    int32_t refresh_every; /* rebuild the device-resident inverse from the current diagonal every k sweeps
+                              (1 = default; 0 = never: the whole solve is ONE kernel launch) */
+} kb_solve_opts;
+
+typedef struct {
+    int32_t sweeps;               /* sweeps executed */
+    int32_t status;               /* same as the return code */
+    int32_t mode;                 /* mode that actually ran */
+    int32_t launches;             /* kernels launched by the call */
+    double trace[KB_MAX_TRACE];   /* per sweep: max|δ| (MVR, maxent) or sum(s) (sdp_ccd) -- what verbose prints */
+    double solve_ms;              /* device time of the CCD kernel(s), CUDA events */
+    double init_ms;               /* device time of the initial factorisation */
+    double ref_bytes;             /* algorithmic bytes of the reference's steps actually taken */
+    double touched_bytes;         /* bytes this implementation's update passes read + wrote */
+    double flops;                 /* FP64 flops of tensor-core stages */
+    double updates;               /* coordinates whose |δ| >= 1e-15 (factor updates performed) */
+    double objective;             /* MVR trace / ME logdet / SDP sum(s) of the returned s (on the correlation scale) */
+} kb_solve_info;
+
+/* ---- context ----------------------------------------------------------------------------- */
+int kb_create(kb_ctx** ctx, int device);
+void kb_destroy(kb_ctx* ctx);
+const char* kb_last_error(const kb_ctx* ctx);
+const char* kb_version(void);
+void kb_default_solve_opts(kb_solve_opts* opts);
+/* kernels launched by this library on ctx since creation (bench.py's gpu_launches) */
+uint64_t kb_launch_count(const kb_ctx* ctx);
+/* the cudaStream_t all of ctx's kernels are launched on (for CUDA-event timing by the caller) */
+void* kb_stream(const kb_ctx* ctx);
+int kb_synchronize(kb_ctx* ctx);
+/* rows per chunk of the sampling pipeline (0 = default 4096) */
+int kb_set_sample_chunk_rows(kb_ctx* ctx, int64_t rows);
+
+/* ---- (1) s-solvers ------------------------------------------------------------------------
+ * kb_solve_s replaces `solve_s(Σ::Symmetric, method; m, kwargs...)` (utilities.jl:27-51):
+ * cov->cor, dispatch to MVR / maxent / sdp_ccd / equi, rescale by σ².  `s_init` (length p, on the
+ * correlation scale) replaces the `s_init` kwarg; NULL = `solve_equi` (utilities.jl:130,227).
+ */
+int kb_solve_s(kb_ctx* ctx, const double* Sigma, int64_t p, int32_t method, double m,
+               const kb_solve_opts* opts, const double* s_init, double* s_out, kb_solve_info* info);
+int kb_solve_s_dev(kb_ctx* ctx, const double* dSigma, int64_t p, int32_t method, double m,
+                   const kb_solve_opts* opts, const double* d_s_init, double* d_s_out, kb_solve_info* info);
+
+/* λmin(Symmetric(Sigma)) -- the `eigvals(Σ) |> minimum` of solve_equi (utilities.jl:108). */
+int kb_eigmin(kb_ctx* ctx, const double* Sigma, int64_t p, double* lambda_min_out);
+
+/* ---- (2) Gram / covariance ------------------------------------------------------------------
+ * G = (Xc' Xc) / denom with Xc = X - colmean if center != 0.  Replaces the Gram inside
+ * `cov(covariance_approximator, X)` and `mean(X, dims=1)` (modelX.jl:47-49).
+ * colmean_out may be NULL.  denom <= 0 means n.
+ */
+int kb_gram(kb_ctx* ctx, const double* X, int64_t n, int64_t p, int32_t center, double denom,
+            double* G_out, double* colmean_out);
+/* row-shard building block for multi-GPU: raw sums over the local rows, no centring:
+ * dG (p x p, full symmetric) = X' X, dcolsum (p) = 1' X.  The caller all-reduces both (NCCL)
+ * and calls kb_gram_finish_dev on every rank. */
+int kb_gram_partial_dev(kb_ctx* ctx, const double* dX, int64_t n_local, int64_t ldx, int64_t p,
+                        double* dG, double* dcolsum);
+int kb_gram_finish_dev(kb_ctx* ctx, double* dG, double* dcolsum, int64_t n_total, int64_t p,
+                       int32_t center, double denom);
+
+/* ---- (3) conditional-covariance factor ------------------------------------------------------
+ * Replaces modelX.jl:106-120: ΣinvS = inv(Symmetric Σ)·S, C = 2S − S·ΣinvS and the Cholesky factor
+ * used for the noise.  S is a length-p vector (Diagonal(s)) if s_is_diag, else dense p x p.
+ * The pm x pm factor of modelX.jl:116-120 has exact block structure (all sub-diagonal blocks of
+ * a block column are equal); it is returned as Lblocks = [L_11 | M_1 | L_22 | M_2 | ... | L_mm]
+ * (2m-1 column-major p x p blocks): block row i, block col k of the dense factor is L_kk if
+ * i == k, M_k if i > k.  For m == 1 Lblocks is just the lower factor L of C.
+ */
+int kb_cond_factor(kb_ctx* ctx, const double* Sigma, int64_t p, const double* S, int32_t s_is_diag,
+                   int32_t m, double* SigmaInvS_out, double* Lblocks_out);
+
+/* ---- (4) sampling -----------------------------------------------------------------------------
+ * Xko (n x m·p) = repeat(X − (X .− μ')·ΣinvS, 1, m) + Z·L   (modelX.jl:112, 118-121; the noise
+ * multiplies the LOWER factor exactly as the reference does).
+ * Z (n x m·p, column-major) is the injected `randn(n, m·p)`; Z == NULL draws it on the device from
+ * Philox4x32-10 keyed by (seed, row, column) so any row shard reproduces the same numbers.
+ * row_offset = global index of X's first row (for row-sharded multi-GPU sampling).
+ */
+int kb_sample(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* mu,
+              const double* SigmaInvS, const double* Lblocks, int32_t m, const double* Z,
+              uint64_t seed, int64_t row_offset, double* Xko_out);
+
+/* ---- one-shot entry points ----------------------------------------------------------------------
+ * kb_modelx_gaussian_knockoffs replaces `modelX_gaussian_knockoffs(X, method, μ, Σ; m, kwargs...)`
+ * (modelX.jl:53-66): s = solve_s(...), Xko = condition(X, μ, Σ, Diagonal(s); m); all
+ * intermediates stay on the device.  row_offset / n as in kb_sample.
+ */
+int kb_modelx_gaussian_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* mu,
+                                 const double* Sigma, int32_t method, int32_t m,
+                                 const kb_solve_opts* opts, const double* s_init, const double* Z,
+                                 uint64_t seed, int64_t row_offset, double* Xko_out, double* s_out,
+                                 kb_solve_info* info);
+
+/* device-resident pieces of the same pipeline (used by the multi-GPU driver and bench.py) */
+int kb_cond_factor_dev(kb_ctx* ctx, const double* dSigma, int64_t p, const double* dS, int32_t s_is_diag,
+                       int32_t m, double* dSigmaInvS, double* dLblocks);
+int kb_sample_dev(kb_ctx* ctx, const double* dX, int64_t n, int64_t ldx, int64_t p, const double* dmu,
+                  const double* dSigmaInvS, const double* dLblocks, int32_t m, const double* dZ, int64_t ldz,
+                  uint64_t seed, int64_t row_offset, double* dXko, int64_t ldxko);
+
+/* ---- test hooks (exercised by tests/, not part of the reference interface) -------------------- */
+/* C (M x N, col-major) = alpha * op(A) * op(B) + beta * C on the hand-written DMMA kernel.
+ * transa / transb: 0 = 'N', 1 = 'T' (BLAS dgemm semantics, host pointers). */
+int kb_test_dgemm(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_t N, int64_t K,
+                  double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
+                  double* C, int64_t ldc);
+/* lower Cholesky factor (potrf) and inverse of an SPD matrix on the device kernels. */
+int kb_test_potrf(kb_ctx* ctx, const double* A, int64_t p, double* L_out);
+int kb_test_spd_inverse(kb_ctx* ctx, const double* A, int64_t p, double* Ainv_out);
+/* n x ncols block of the device Gaussian stream (what kb_sample uses when Z == NULL). */
+int kb_test_randn(kb_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n, int64_t ncols, double* Z_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KNOCKOFFS_B200_H */

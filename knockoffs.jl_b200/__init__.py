@@ -1,0 +1,13 @@
+"""knockoffs_b200 -- B200-native (sm_100a) model-X Gaussian knockoff hot path behind the Knockoffs.jl API.
+
+The directory is named ``knockoffs.jl_b200`` (not importable by name because of the dot); import it as
+``knockoffs_b200`` through the loader module at the repo root.
+"""
+from ._lib import KnockoffsError, PosDefException, LIB_PATH, SIGNATURES, load  # noqa: F401
+from .api import (Context, GaussianKnockoff, cond_factor, condition, default_context, dense_factor_from_blocks,  # noqa: F401
+                  eigmin, gram, hook_dgemm, hook_potrf, hook_randn, hook_spd_inverse, make_opts,
+                  modelX_gaussian_knockoffs, sample, solve_equi, solve_s)
+from . import harness  # noqa: F401
+
+__all__ = ["Context", "GaussianKnockoff", "KnockoffsError", "PosDefException", "cond_factor", "condition", "eigmin",
+           "gram", "modelX_gaussian_knockoffs", "sample", "solve_equi", "solve_s", "harness"]

@@ -1,0 +1,102 @@
+"""ctypes binding of libknockoffs_b200.so -- exactly the symbols include/knockoffs_b200.h declares.
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is present,
+every entry point raises.  (The CPU oracle lives in oracle/ and is test infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libknockoffs_b200.so")
+
+KB_OK, KB_ERR_INVALID, KB_ERR_NOT_PD, KB_ERR_NAN, KB_ERR_CUDA = 0, -1, -2, -3, -4
+KB_MAX_TRACE = 128
+METHODS = {"mvr": 0, "maxent": 1, "sdp_ccd": 2, "equi": 3}
+
+c_double_p = C.POINTER(C.c_double)
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("niter", C.c_int32), ("tol", C.c_double), ("lambda_min", C.c_double), ("sdp_lambda", C.c_double),
+                ("sdp_mu", C.c_double), ("robust", C.c_int32), ("verbose", C.c_int32), ("mode", C.c_int32),
+                ("refresh_every", C.c_int32)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("sweeps", C.c_int32), ("status", C.c_int32), ("mode", C.c_int32), ("launches", C.c_int32),
+                ("trace", C.c_double * KB_MAX_TRACE), ("solve_ms", C.c_double), ("init_ms", C.c_double),
+                ("ref_bytes", C.c_double), ("touched_bytes", C.c_double), ("flops", C.c_double),
+                ("updates", C.c_double), ("objective", C.c_double)]
+
+
+# name -> (restype, argtypes); mirrors include/knockoffs_b200.h one to one
+_vp, _i32, _i64, _u64, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+SIGNATURES = {
+    "kb_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "kb_destroy": (None, [_vp]),
+    "kb_last_error": (C.c_char_p, [_vp]),
+    "kb_version": (C.c_char_p, []),
+    "kb_default_solve_opts": (None, [C.POINTER(SolveOpts)]),
+    "kb_launch_count": (_u64, [_vp]),
+    "kb_stream": (_vp, [_vp]),
+    "kb_synchronize": (C.c_int, [_vp]),
+    "kb_set_sample_chunk_rows": (C.c_int, [_vp, _i64]),
+    "kb_solve_s": (C.c_int, [_vp, _vp, _i64, _i32, _d, C.POINTER(SolveOpts), _vp, _vp, C.POINTER(SolveInfo)]),
+    "kb_solve_s_dev": (C.c_int, [_vp, _vp, _i64, _i32, _d, C.POINTER(SolveOpts), _vp, _vp, C.POINTER(SolveInfo)]),
+    "kb_eigmin": (C.c_int, [_vp, _vp, _i64, c_double_p]),
+    "kb_gram": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _d, _vp, _vp]),
+    "kb_gram_partial_dev": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "kb_gram_finish_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _d]),
+    "kb_cond_factor": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "kb_cond_factor_dev": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "kb_sample": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _u64, _i64, _vp]),
+    "kb_sample_dev": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _u64, _i64, _vp, _i64]),
+    "kb_modelx_gaussian_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, C.POINTER(SolveOpts), _vp,
+                                               _vp, _u64, _i64, _vp, _vp, C.POINTER(SolveInfo)]),
+    "kb_test_dgemm": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
+    "kb_test_potrf": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "kb_test_spd_inverse": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "kb_test_randn": (C.c_int, [_vp, _u64, _i64, _i64, _i64, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree shared library and set every prototype.  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is not built (run `make` or `python -c 'import __graft_entry__ as g; g.build()'`); "
+                "knockoffs_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)     # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class KnockoffsError(RuntimeError):
+    """error(...) of the reference (invalid arguments, NaN/Inf delta) or a CUDA failure."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class PosDefException(KnockoffsError):
+    """LinearAlgebra.PosDefException of the reference (initial cholesky / downdate)."""
+
+
+def check(ctx_handle, rc: int):
+    if rc == KB_OK:
+        return
+    msg = load().kb_last_error(ctx_handle).decode("utf-8", "replace")
+    if rc == KB_ERR_NOT_PD:
+        raise PosDefException(rc, msg)
+    raise KnockoffsError(rc, msg)

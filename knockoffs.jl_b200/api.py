@@ -1,0 +1,313 @@
+"""Host-side mirror of the reference's interface for the model-X Gaussian knockoff path.
+
+Same names, argument meaning and error behaviour as Knockoffs.jl v2.0.2 (paths relative to that repo):
+``solve_s`` (src/utilities.jl:27-51), ``modelX_gaussian_knockoffs`` (src/modelX.jl:39-66),
+``condition`` (src/modelX.jl:96-122).  Every function is a thin ctypes call into
+libknockoffs_b200.so; numpy arrays are passed as Fortran-ordered float64 (Julia ``Matrix{Float64}``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import METHODS, SolveInfo, SolveOpts, check
+
+SINGLE_KNOCKOFFS = ["mvr", "maxent", "equi", "sdp", "sdp_ccd"]   # src/Knockoffs.jl:99
+
+
+def _f(a, name="array"):
+    a = np.asarray(a)
+    if a.dtype != np.float64 or not a.flags.f_contiguous:
+        a = np.asfortranarray(a, dtype=np.float64)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One per host thread / device (include/knockoffs_b200.h: kb_create)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.kb_create(C.byref(h), int(device))
+        if rc != 0:
+            raise _lib.KnockoffsError(rc, f"kb_create(device={device}) failed: no usable CUDA device "
+                                          "(knockoffs_b200 has no CPU fallback)")
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.kb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.kb_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.kb_stream(self.h) or 0)
+
+    def set_sample_chunk_rows(self, rows: int):
+        check(self.h, self._lib.kb_set_sample_chunk_rows(self.h, int(rows)))
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _method_id(method) -> int:
+    name = str(method).lstrip(":")
+    if name == "sdp":
+        # src/utilities.jl:37-38 sends non-group :sdp to the Hypatia interior-point solver, which is out of
+        # scope; the coordinate-descent SDP is :sdp_ccd.
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID,
+                                  "method :sdp is the interior-point solver (not on the GPU path); use :sdp_ccd")
+    if name not in METHODS:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Method must be one of {SINGLE_KNOCKOFFS} but was {name}")
+    return METHODS[name]
+
+
+def make_opts(niter=100, tol=1e-6, λmin=None, lambda_min=1e-6, λ=None, sdp_lambda=0.5, μ=None, sdp_mu=0.8,
+              robust=False, verbose=False, refresh_every=1, **unknown) -> SolveOpts:
+    """Keyword arguments of solve_MVR / solve_max_entropy / solve_sdp_ccd (utilities.jl:124-133, 221-230, 291-300)."""
+    if unknown:
+        raise TypeError(f"unsupported keyword argument(s): {sorted(unknown)}")   # Julia: MethodError
+    o = SolveOpts()
+    _lib.load().kb_default_solve_opts(C.byref(o))
+    o.niter = int(niter)
+    o.tol = float(tol)
+    o.lambda_min = float(lambda_min if λmin is None else λmin)
+    o.sdp_lambda = float(sdp_lambda if λ is None else λ)
+    o.sdp_mu = float(sdp_mu if μ is None else μ)
+    o.robust = int(bool(robust))
+    o.verbose = int(bool(verbose))
+    o.refresh_every = int(refresh_every)
+    return o
+
+
+def _info_dict(info: SolveInfo, method: str) -> dict:
+    n = max(0, min(info.sweeps, _lib.KB_MAX_TRACE))
+    return dict(sweeps=info.sweeps, status=info.status, launches=info.launches, trace=list(info.trace[:n]),
+                solve_ms=info.solve_ms, init_ms=info.init_ms, ref_bytes=info.ref_bytes,
+                touched_bytes=info.touched_bytes, updates=info.updates, method=method)
+
+
+def _print_trace(info: dict):
+    # what `verbose=true` prints in the reference (utilities.jl:167-170, 273-276, 313-316)
+    for l, v in enumerate(info["trace"], 1):
+        if info["method"] == "sdp_ccd":
+            print(f"Iter {l}: sum(s) = {v}")
+        else:
+            print(f"Iter {l}: δ = {v}")
+
+
+def solve_s(Sigma, method, m=1, s_init=None, ctx: Optional[Context] = None, return_info=False, **kwargs):
+    """``solve_s(Σ::Symmetric, method; m, kwargs...)`` -- src/utilities.jl:27-51.  Only the upper
+    triangle of ``Sigma`` is read.  Returns ``s`` (and the solver info dict if ``return_info``)."""
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    if Sigma.ndim != 2 or Sigma.shape[0] != Sigma.shape[1]:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Sigma must be square")
+    p = Sigma.shape[0]
+    mid = _method_id(method)
+    opts = make_opts(**kwargs)
+    info = SolveInfo()
+    s = np.empty(p)
+    si = None if s_init is None else np.ascontiguousarray(s_init, dtype=np.float64)
+    rc = ctx._lib.kb_solve_s(ctx.h, _ptr(Sigma), p, mid, float(m), C.byref(opts), _ptr(si), _ptr(s), C.byref(info))
+    check(ctx.h, rc)
+    d = _info_dict(info, str(method).lstrip(":"))
+    if opts.verbose:
+        _print_trace(d)
+    return (s, d) if return_info else s
+
+
+def eigmin(Sigma, ctx: Optional[Context] = None) -> float:
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    out = C.c_double()
+    check(ctx.h, ctx._lib.kb_eigmin(ctx.h, _ptr(Sigma), Sigma.shape[0], C.byref(out)))
+    return out.value
+
+
+def solve_equi(Sigma, m=1, ctx: Optional[Context] = None):
+    """src/utilities.jl:104-111 (on a correlation matrix)."""
+    return solve_s(Sigma, "equi", m=m, ctx=ctx)
+
+
+def gram(X, center=True, denom=None, ctx: Optional[Context] = None):
+    """(Xc'Xc)/denom and the column means -- the Gram inside ``cov(estimator, X)`` and
+    ``mean(X, dims=1)`` of the 2-argument entry (src/modelX.jl:47-49)."""
+    ctx = ctx or default_context()
+    X = _f(X)
+    n, p = X.shape
+    G = np.empty((p, p), order="F")
+    mu = np.empty(p)
+    check(ctx.h, ctx._lib.kb_gram(ctx.h, _ptr(X), n, p, int(bool(center)), float(denom or 0.0), _ptr(G), _ptr(mu)))
+    return G, mu
+
+
+def cond_factor(Sigma, S, m=1, ctx: Optional[Context] = None):
+    """ΣinvS and the factor blocks of src/modelX.jl:106-120.  ``S`` is a vector (``Diagonal(s)``) or a
+    dense p x p matrix.  Returns (SigmaInvS, Lblocks) with Lblocks of shape (p, p, 2m-1):
+    [L_11, M_1, L_22, M_2, ..., L_mm] (block (i,k) of the pm x pm lower factor is L_kk if i == k, M_k if i > k)."""
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    p = Sigma.shape[0]
+    S = np.asarray(S, dtype=np.float64)
+    is_diag = S.ndim == 1
+    S = np.ascontiguousarray(S) if is_diag else _f(S)
+    m = int(m)
+    if m < 1:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
+    SiS = np.empty((p, p), order="F")
+    Lb = np.empty((p, p, 2 * m - 1), order="F")
+    check(ctx.h, ctx._lib.kb_cond_factor(ctx.h, _ptr(Sigma), p, _ptr(S), int(is_diag), m, _ptr(SiS), _ptr(Lb)))
+    return SiS, Lb
+
+
+def dense_factor_from_blocks(Lb: np.ndarray) -> np.ndarray:
+    """The pm x pm lower factor of modelX.jl:120 assembled from the block form (tests / inspection)."""
+    p = Lb.shape[0]
+    m = (Lb.shape[2] + 1) // 2
+    L = np.zeros((p * m, p * m))
+    for k in range(m):
+        L[k * p:(k + 1) * p, k * p:(k + 1) * p] = Lb[:, :, 2 * k]
+        for i in range(k + 1, m):
+            L[i * p:(i + 1) * p, k * p:(k + 1) * p] = Lb[:, :, 2 * k + 1]
+    return L
+
+
+def sample(X, mu, SigmaInvS, Lblocks, m=1, Z=None, seed=0, row_offset=0, ctx: Optional[Context] = None):
+    """X̃ = repeat(X − (X .− μ')ΣinvS, 1, m) + Z·L (src/modelX.jl:112, 118-121).  ``Z`` (n x mp) is the
+    injected ``randn(n, mp)``; ``Z=None`` draws it on the device (Philox4x32-10, keyed by seed/row/column)."""
+    ctx = ctx or default_context()
+    X = _f(X)
+    n, p = X.shape
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    SiS = _f(SigmaInvS)
+    Lb = _f(Lblocks)
+    Zf = None if Z is None else _f(Z)
+    if Zf is not None and Zf.shape != (n, m * p):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
+    Xko = np.empty((n, m * p), order="F")
+    check(ctx.h, ctx._lib.kb_sample(ctx.h, _ptr(X), n, p, _ptr(mu), _ptr(SiS), _ptr(Lb), int(m), _ptr(Zf),
+                                    int(seed), int(row_offset), _ptr(Xko)))
+    return Xko
+
+
+def condition(X, mu, Sigma, S, m=1, Z=None, seed=0, ctx: Optional[Context] = None):
+    """``condition(X, μ, Σ, S; m)`` -- src/modelX.jl:96-122."""
+    m = int(m)
+    if m < 1:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
+    SiS, Lb = cond_factor(Sigma, S, m=m, ctx=ctx)
+    return sample(X, mu, SiS, Lb, m=m, Z=Z, seed=seed, ctx=ctx)
+
+
+@dataclass
+class GaussianKnockoff:
+    """src/struct.jl:6-13 (field names as in the reference)."""
+    X: np.ndarray
+    Xko: np.ndarray
+    s: np.ndarray
+    Sigma: np.ndarray
+    method: str
+    m: int
+    info: dict = field(default_factory=dict)
+
+
+def modelX_gaussian_knockoffs(X, method, mu=None, Sigma=None, m=1, Z=None, seed=0, s_init=None,
+                              ctx: Optional[Context] = None, **kwargs) -> GaussianKnockoff:
+    """``modelX_gaussian_knockoffs(X, method, μ, Σ; m, kwargs...)`` -- src/modelX.jl:53-66: one library call
+    (solve_s -> conditional factor -> sampling; intermediates never leave the device).
+    With ``mu``/``Sigma`` omitted this is the 2-argument entry (src/modelX.jl:39-51) with the sample
+    covariance computed on the device."""
+    ctx = ctx or default_context()
+    X = _f(X)
+    n, p = X.shape
+    m = int(m)
+    if m < 1:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
+    if (mu is None) != (Sigma is None):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "give both mu and Sigma, or neither")
+    if Sigma is None:
+        Sigma, mu = gram(X, center=True, ctx=ctx)
+    Sigma = _f(Sigma)
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    if Sigma.shape != (p, p) or mu.shape != (p,):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "dimension mismatch between X, mu and Sigma")
+    mid = _method_id(method)
+    opts = make_opts(**kwargs)
+    info = SolveInfo()
+    Zf = None if Z is None else _f(Z)
+    if Zf is not None and Zf.shape != (n, m * p):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
+    si = None if s_init is None else np.ascontiguousarray(s_init, dtype=np.float64)
+    Xko = np.empty((n, m * p), order="F")
+    s = np.empty(p)
+    rc = ctx._lib.kb_modelx_gaussian_knockoffs(ctx.h, _ptr(X), n, p, _ptr(mu), _ptr(Sigma), mid, m, C.byref(opts),
+                                               _ptr(si), _ptr(Zf), int(seed), 0, _ptr(Xko), _ptr(s), C.byref(info))
+    check(ctx.h, rc)
+    d = _info_dict(info, str(method).lstrip(":"))
+    if opts.verbose:
+        _print_trace(d)
+    Ssym = np.triu(Sigma) + np.triu(Sigma, 1).T
+    return GaussianKnockoff(X, Xko, s, Ssym, str(method).lstrip(":"), m, d)
+
+
+# ---- hooks used by tests ---------------------------------------------------------------------------
+def hook_dgemm(A, B, C_in=None, transa=False, transb=False, alpha=1.0, beta=0.0, ctx: Optional[Context] = None):
+    ctx = ctx or default_context()
+    A, B = _f(A), _f(B)
+    M = A.shape[1] if transa else A.shape[0]
+    K = A.shape[0] if transa else A.shape[1]
+    N = B.shape[0] if transb else B.shape[1]
+    Cm = np.zeros((M, N), order="F") if C_in is None else np.array(C_in, dtype=np.float64, order="F")
+    check(ctx.h, ctx._lib.kb_test_dgemm(ctx.h, int(transa), int(transb), M, N, K, float(alpha), _ptr(A), A.shape[0],
+                                        _ptr(B), B.shape[0], float(beta), _ptr(Cm), M))
+    return Cm
+
+
+def hook_potrf(A, ctx: Optional[Context] = None):
+    ctx = ctx or default_context()
+    A = _f(A)
+    L = np.empty_like(A, order="F")
+    check(ctx.h, ctx._lib.kb_test_potrf(ctx.h, _ptr(A), A.shape[0], _ptr(L)))
+    return L
+
+
+def hook_spd_inverse(A, ctx: Optional[Context] = None):
+    ctx = ctx or default_context()
+    A = _f(A)
+    O = np.empty_like(A, order="F")
+    check(ctx.h, ctx._lib.kb_test_spd_inverse(ctx.h, _ptr(A), A.shape[0], _ptr(O)))
+    return O
+
+
+def hook_randn(seed, row_offset, n, ncols, ctx: Optional[Context] = None):
+    ctx = ctx or default_context()
+    Z = np.empty((n, ncols), order="F")
+    check(ctx.h, ctx._lib.kb_test_randn(ctx.h, int(seed), int(row_offset), int(n), int(ncols), _ptr(Z)))
+    return Z

@@ -1,0 +1,416 @@
+// extern "C" entry points of libknockoffs_b200 (see include/knockoffs_b200.h for the contract and the
+// reference lines each call replaces).  Host-pointer calls copy in/out; nothing is retained after return.
+#include "kb_common.cuh"
+#include "linalg.cuh"
+#include "pipeline.cuh"
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+using namespace kb;
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int bad_ctx() { return KB_ERR_INVALID; }
+
+// column-major host matrix (rows x cols, ld hld) <-> device (ld dld)
+int h2d_matrix(kb_ctx* ctx, const double* h, long hld, double* d, long dld, long rows, long cols, cudaStream_t st) {
+    KB_CUDA(ctx, cudaMemcpy2DAsync(d, dld * sizeof(double), h, hld * sizeof(double), rows * sizeof(double), cols,
+                                   cudaMemcpyHostToDevice, st));
+    return KB_OK;
+}
+int d2h_matrix(kb_ctx* ctx, const double* d, long dld, double* h, long hld, long rows, long cols, cudaStream_t st) {
+    KB_CUDA(ctx, cudaMemcpy2DAsync(h, hld * sizeof(double), d, dld * sizeof(double), rows * sizeof(double), cols,
+                                   cudaMemcpyDeviceToHost, st));
+    return KB_OK;
+}
+
+// Row-chunk pipeline for host-resident X / Z / X̃: H2D of chunk i+1 and D2H of chunk i-1 overlap the
+// GEMMs of chunk i (three streams, double-buffered device slabs).
+int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const double* dmu, const double* dSiS,
+                         const double* dLb, long ldo, int m, const double* Z, uint64_t seed, int64_t row_offset,
+                         double* Xko) {
+    if (n <= 0) return KB_OK;
+    long chunk = ctx->sample_chunk_rows > 0 ? ctx->sample_chunk_rows : 4096;
+    if (chunk > n) chunk = n;
+    chunk = (chunk + 1) & ~1L;
+    Scope sc(ctx);
+    SamplePlan plan;
+    KB_TRY(sample_plan_create(ctx, sc, p, m, dmu, dSiS, dLb, ldo, chunk, Z == nullptr, &plan));
+    double *dXc[2], *dZc[2] = {nullptr, nullptr}, *dOut[2];
+    for (int b = 0; b < 2; ++b) {
+        KB_TRY(sc.alloc(&dXc[b], (size_t)chunk * p));
+        if (Z) KB_TRY(sc.alloc(&dZc[b], (size_t)chunk * p * m));
+        KB_TRY(sc.alloc(&dOut[b], (size_t)chunk * p * m));
+    }
+    cudaEvent_t* ev_h2d = ctx->pipe_ev;        // [2]
+    cudaEvent_t* ev_comp = ctx->pipe_ev + 2;   // [2]
+    cudaEvent_t* ev_d2h = ctx->pipe_ev + 4;    // [2]
+    // the plan's constants were enqueued on ctx->stream; the copy streams only touch their own slabs
+    long i = 0;
+    for (long r0 = 0; r0 < n; r0 += chunk, ++i) {
+        const int b = (int)(i & 1);
+        const long rows = std::min(chunk, n - r0);
+        if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
+        KB_TRY(h2d_matrix(ctx, X + r0, n, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        if (Z) KB_TRY(h2d_matrix(ctx, Z + r0, n, dZc[b], chunk, rows, (long)p * m, ctx->stream_h2d));
+        KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
+        KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
+        if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[b], 0));
+        KB_TRY(sample_chunk(ctx, plan, dXc[b], rows, chunk, Z ? dZc[b] : nullptr, chunk, seed, row_offset + r0, dOut[b],
+                            chunk));
+        KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
+        KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ev_comp[b], 0));
+        KB_TRY(d2h_matrix(ctx, dOut[b], chunk, Xko + r0, n, rows, (long)p * m, ctx->stream_d2h));
+        KB_CUDA(ctx, cudaEventRecord(ev_d2h[b], ctx->stream_d2h));
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_d2h));
+    return KB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* kb_version(void) { return "knockoffs_b200 0.1.0 (sm_100a)"; }
+
+int kb_create(kb_ctx** out, int device) {
+    if (!out) return KB_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return KB_ERR_CUDA;   // no CPU fallback, by design
+    if (device < 0 || device >= ndev) return KB_ERR_INVALID;
+    kb_ctx* ctx = new (std::nothrow) kb_ctx();
+    if (!ctx) return KB_ERR_CUDA;
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    bool ok = cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+    if (ok) {
+        ctx->num_sms = prop.multiProcessorCount;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        ok = coop != 0;
+    }
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
+    for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        kb_destroy(ctx);
+        return KB_ERR_CUDA;
+    }
+    *out = ctx;
+    return KB_OK;
+}
+
+void kb_destroy(kb_ctx* ctx) {
+    if (!ctx) return;
+    {
+        DeviceGuard g(ctx->device);
+        if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+        if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
+        if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
+        if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+        if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+        for (int i = 0; i < 6; ++i)
+            if (ctx->pipe_ev[i]) cudaEventDestroy(ctx->pipe_ev[i]);
+    }
+    delete ctx;
+}
+
+const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "invalid context"; }
+void kb_default_solve_opts(kb_solve_opts* o) { if (o) default_solve_opts(o); }
+uint64_t kb_launch_count(const kb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* kb_stream(const kb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int kb_set_sample_chunk_rows(kb_ctx* ctx, int64_t rows) {
+    if (!ctx || rows < 0) return KB_ERR_INVALID;
+    ctx->sample_chunk_rows = rows;
+    return KB_OK;
+}
+int kb_synchronize(kb_ctx* ctx) {
+    if (!ctx) return bad_ctx();
+    DeviceGuard g(ctx->device);
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+// ---- (1) s-solvers --------------------------------------------------------------------------------
+int kb_solve_s_dev(kb_ctx* ctx, const double* dSigma, int64_t p, int32_t method, double m, const kb_solve_opts* opts,
+                   const double* d_s_init, double* d_s_out, kb_solve_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!dSigma || !d_s_out || p < 1 || p > 0x3fffffff) return set_error(ctx, KB_ERR_INVALID, "solve_s: bad arguments");
+    DeviceGuard g(ctx->device);
+    return solve_s_dev(ctx, dSigma, (long)p, (int)p, method, m, opts, d_s_init, d_s_out, info);
+}
+
+int kb_solve_s(kb_ctx* ctx, const double* Sigma, int64_t p, int32_t method, double m, const kb_solve_opts* opts,
+               const double* s_init, double* s_out, kb_solve_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !s_out || p < 1 || p > 0x3fffffff) return set_error(ctx, KB_ERR_INVALID, "solve_s: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double *dS, *ds_init = nullptr, *ds;
+    KB_TRY(sc.alloc(&dS, (size_t)p * p));
+    KB_TRY(sc.alloc(&ds, p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dS, Sigma, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+    if (s_init) {
+        KB_TRY(sc.alloc(&ds_init, p));
+        KB_CUDA(ctx, cudaMemcpyAsync(ds_init, s_init, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int rc = solve_s_dev(ctx, dS, (long)p, (int)p, method, m, opts, ds_init, ds, info);
+    // like the reference, nothing is returned when the solver throws; s_out is only written on success
+    if (rc != KB_OK) return rc;
+    KB_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_eigmin(kb_ctx* ctx, const double* Sigma, int64_t p, double* lambda_min_out) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !lambda_min_out || p < 1) return set_error(ctx, KB_ERR_INVALID, "eigmin: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double* dS;
+    KB_TRY(sc.alloc(&dS, (size_t)p * p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dS, Sigma, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+    return eigmin_dev(ctx, dS, (long)p, (int)p, lambda_min_out);
+}
+
+// ---- (2) Gram -------------------------------------------------------------------------------------
+int kb_gram_partial_dev(kb_ctx* ctx, const double* dX, int64_t n_local, int64_t ldx, int64_t p, double* dG,
+                        double* dcolsum) {
+    if (!ctx) return bad_ctx();
+    if (!dX || !dG || p < 1 || n_local < 0 || ldx < n_local) return set_error(ctx, KB_ERR_INVALID, "gram_partial: bad arguments");
+    DeviceGuard g(ctx->device);
+    KB_TRY(fill_zero(ctx, dG, (size_t)p * p));
+    if (dcolsum) KB_TRY(fill_zero(ctx, dcolsum, p));
+    KB_TRY(gram_partial_dev(ctx, dX, (long)n_local, (long)ldx, (int)p, dG, (long)p, dcolsum, 0));
+    KB_TRY(mirror_lower_to_upper(ctx, dG, (long)p, (int)p));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_gram_finish_dev(kb_ctx* ctx, double* dG, double* dcolsum, int64_t n_total, int64_t p, int32_t center,
+                       double denom) {
+    if (!ctx) return bad_ctx();
+    if (!dG || p < 1 || n_total < 1) return set_error(ctx, KB_ERR_INVALID, "gram_finish: bad arguments");
+    DeviceGuard g(ctx->device);
+    KB_TRY(gram_finish_dev(ctx, dG, (long)p, dcolsum, (long)n_total, (int)p, center, denom));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_gram(kb_ctx* ctx, const double* X, int64_t n, int64_t p, int32_t center, double denom, double* G_out,
+            double* colmean_out) {
+    if (!ctx) return bad_ctx();
+    if (!X || !G_out || p < 1 || n < 1) return set_error(ctx, KB_ERR_INVALID, "gram: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const long ld = (p + 1) & ~1L;
+    long chunk = 65536;
+    if (chunk > n) chunk = (n + 1) & ~1L;
+    double *dG, *dcs, *dXc[2];
+    KB_TRY(sc.alloc(&dG, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dcs, p));
+    for (int b = 0; b < 2; ++b) KB_TRY(sc.alloc(&dXc[b], (size_t)chunk * p));
+    KB_TRY(fill_zero(ctx, dG, (size_t)ld * p));
+    KB_TRY(fill_zero(ctx, dcs, p));
+    cudaEvent_t* ev_h2d = ctx->pipe_ev;
+    cudaEvent_t* ev_comp = ctx->pipe_ev + 2;
+    long i = 0;
+    for (long r0 = 0; r0 < n; r0 += chunk, ++i) {
+        const int b = (int)(i & 1);
+        const long rows = std::min(chunk, (long)n - r0);
+        if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
+        KB_TRY(h2d_matrix(ctx, X + r0, n, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
+        KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
+        KB_TRY(gram_partial_dev(ctx, dXc[b], rows, chunk, (int)p, dG, ld, dcs, 1));
+        KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
+    }
+    KB_TRY(gram_finish_dev(ctx, dG, ld, dcs, (long)n, (int)p, center, denom));
+    KB_TRY(d2h_matrix(ctx, dG, ld, G_out, p, p, p, ctx->stream));
+    if (colmean_out) KB_CUDA(ctx, cudaMemcpyAsync(colmean_out, dcs, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+// ---- (3) conditional factor -----------------------------------------------------------------------
+int kb_cond_factor_dev(kb_ctx* ctx, const double* dSigma, int64_t p, const double* dS, int32_t s_is_diag, int32_t m,
+                       double* dSigmaInvS, double* dLblocks) {
+    if (!ctx) return bad_ctx();
+    if (!dSigma || !dS || !dSigmaInvS || !dLblocks || p < 1) return set_error(ctx, KB_ERR_INVALID, "cond_factor: bad arguments");
+    DeviceGuard g(ctx->device);
+    KB_TRY(cond_factor_dev(ctx, dSigma, (long)p, (int)p, dS, (long)p, s_is_diag, m, dSigmaInvS, dLblocks, (long)p));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_cond_factor(kb_ctx* ctx, const double* Sigma, int64_t p, const double* S, int32_t s_is_diag, int32_t m,
+                   double* SigmaInvS_out, double* Lblocks_out) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !S || !SigmaInvS_out || !Lblocks_out || p < 1) return set_error(ctx, KB_ERR_INVALID, "cond_factor: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const size_t pp = (size_t)p * p;
+    const size_t nblk = (size_t)(2 * m - 1);
+    double *dSig, *dS, *dSiS, *dLb;
+    KB_TRY(sc.alloc(&dSig, pp));
+    KB_TRY(sc.alloc(&dS, s_is_diag ? (size_t)p : pp));
+    KB_TRY(sc.alloc(&dSiS, pp));
+    KB_TRY(sc.alloc(&dLb, pp * nblk));
+    KB_CUDA(ctx, cudaMemcpyAsync(dSig, Sigma, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dS, S, sizeof(double) * (s_is_diag ? (size_t)p : pp), cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(cond_factor_dev(ctx, dSig, (long)p, (int)p, dS, (long)p, s_is_diag, m, dSiS, dLb, (long)p));
+    KB_CUDA(ctx, cudaMemcpyAsync(SigmaInvS_out, dSiS, sizeof(double) * pp, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(Lblocks_out, dLb, sizeof(double) * pp * nblk, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+// ---- (4) sampling ---------------------------------------------------------------------------------
+int kb_sample_dev(kb_ctx* ctx, const double* dX, int64_t n, int64_t ldx, int64_t p, const double* dmu,
+                  const double* dSigmaInvS, const double* dLblocks, int32_t m, const double* dZ, int64_t ldz,
+                  uint64_t seed, int64_t row_offset, double* dXko, int64_t ldxko) {
+    if (!ctx) return bad_ctx();
+    if (!dX || !dmu || !dSigmaInvS || !dLblocks || !dXko || p < 1 || n < 0 || ldx < n || ldxko < n || (dZ && ldz < n))
+        return set_error(ctx, KB_ERR_INVALID, "sample: bad arguments");
+    DeviceGuard g(ctx->device);
+    return sample_dev(ctx, dX, (long)n, (long)ldx, (int)p, dmu, dSigmaInvS, dLblocks, (long)p, m, dZ, (long)ldz, seed,
+                      row_offset, dXko, (long)ldxko);
+}
+
+int kb_sample(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* mu, const double* SigmaInvS,
+              const double* Lblocks, int32_t m, const double* Z, uint64_t seed, int64_t row_offset, double* Xko_out) {
+    if (!ctx) return bad_ctx();
+    if (!X || !mu || !SigmaInvS || !Lblocks || !Xko_out || p < 1 || n < 0) return set_error(ctx, KB_ERR_INVALID, "sample: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const size_t pp = (size_t)p * p;
+    const size_t nblk = (size_t)(2 * m - 1);
+    double *dmu, *dSiS, *dLb;
+    KB_TRY(sc.alloc(&dmu, p));
+    KB_TRY(sc.alloc(&dSiS, pp));
+    KB_TRY(sc.alloc(&dLb, pp * nblk));
+    KB_CUDA(ctx, cudaMemcpyAsync(dmu, mu, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dSiS, SigmaInvS, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dLb, Lblocks, sizeof(double) * pp * nblk, cudaMemcpyHostToDevice, ctx->stream));
+    return sample_host_pipeline(ctx, X, (long)n, (int)p, dmu, dSiS, dLb, (long)p, m, Z, seed, row_offset, Xko_out);
+}
+
+// ---- one-shot ---------------------------------------------------------------------------------------
+int kb_modelx_gaussian_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* mu,
+                                 const double* Sigma, int32_t method, int32_t m, const kb_solve_opts* opts,
+                                 const double* s_init, const double* Z, uint64_t seed, int64_t row_offset,
+                                 double* Xko_out, double* s_out, kb_solve_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!X || !mu || !Sigma || !Xko_out || !s_out || p < 1 || n < 0) return set_error(ctx, KB_ERR_INVALID, "modelX: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const size_t pp = (size_t)p * p;
+    const size_t nblk = (size_t)(2 * m - 1);
+    double *dSig, *ds, *ds_init = nullptr, *dmu, *dSiS, *dLb;
+    KB_TRY(sc.alloc(&dSig, pp));
+    KB_TRY(sc.alloc(&ds, p));
+    KB_TRY(sc.alloc(&dmu, p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dSig, Sigma, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dmu, mu, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    if (s_init) {
+        KB_TRY(sc.alloc(&ds_init, p));
+        KB_CUDA(ctx, cudaMemcpyAsync(ds_init, s_init, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // s = solve_s(Symmetric(Σ), method; m, kwargs...)                    (modelX.jl:62)
+    KB_TRY(solve_s_dev(ctx, dSig, (long)p, (int)p, method, (double)m, opts, ds_init, ds, info));
+    KB_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    // X̃ = condition(X, μ, Symmetric(Σ), Diagonal(s); m)                 (modelX.jl:64)
+    KB_TRY(sc.alloc(&dSiS, pp));
+    KB_TRY(sc.alloc(&dLb, pp * nblk));
+    KB_TRY(cond_factor_dev(ctx, dSig, (long)p, (int)p, ds, (long)p, 1, m, dSiS, dLb, (long)p));
+    return sample_host_pipeline(ctx, X, (long)n, (int)p, dmu, dSiS, dLb, (long)p, m, Z, seed, row_offset, Xko_out);
+}
+
+// ---- test hooks -------------------------------------------------------------------------------------
+int kb_test_dgemm(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_t N, int64_t K, double alpha,
+                  const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+    if (!ctx) return bad_ctx();
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const long ar = transa ? K : M, ac = transa ? M : K, br = transb ? N : K, bc = transb ? K : N;
+    double *dA, *dB, *dC;
+    const long dlda = (ar + 1) & ~1L, dldb = (br + 1) & ~1L, dldc = (M + 1) & ~1L;
+    KB_TRY(sc.alloc(&dA, (size_t)dlda * ac));
+    KB_TRY(sc.alloc(&dB, (size_t)dldb * bc));
+    KB_TRY(sc.alloc(&dC, (size_t)dldc * N));
+    KB_TRY(h2d_matrix(ctx, A, lda, dA, dlda, ar, ac, ctx->stream));
+    KB_TRY(h2d_matrix(ctx, B, ldb, dB, dldb, br, bc, ctx->stream));
+    KB_TRY(h2d_matrix(ctx, C, ldc, dC, dldc, M, N, ctx->stream));
+    KB_TRY(gemm1(ctx, transa ? A_KCONTIG : A_MCONTIG, transb ? B_NCONTIG : B_KCONTIG, (int)M, (int)N, (int)K, alpha, dA,
+                 dlda, dB, dldb, beta, dC, dldc));
+    KB_TRY(d2h_matrix(ctx, dC, dldc, C, ldc, M, N, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_test_potrf(kb_ctx* ctx, const double* A, int64_t p, double* L_out) {
+    if (!ctx) return bad_ctx();
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double *dA, *dL;
+    KB_TRY(sc.alloc(&dA, (size_t)p * p));
+    KB_TRY(sc.alloc(&dL, (size_t)p * p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dA, A, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(fill_zero(ctx, dL, (size_t)p * p));
+    KB_TRY(potrf_dev(ctx, dA, (long)p, (int)p, dL, (long)p));
+    KB_CUDA(ctx, cudaMemcpyAsync(L_out, dL, sizeof(double) * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_test_spd_inverse(kb_ctx* ctx, const double* A, int64_t p, double* Ainv_out) {
+    if (!ctx) return bad_ctx();
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double *dA, *dO;
+    KB_TRY(sc.alloc(&dA, (size_t)p * p));
+    KB_TRY(sc.alloc(&dO, (size_t)p * p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dA, A, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(fill_zero(ctx, dO, (size_t)p * p));
+    KB_TRY(spd_inverse_dev(ctx, dA, (long)p, (int)p, dO, (long)p));
+    KB_CUDA(ctx, cudaMemcpyAsync(Ainv_out, dO, sizeof(double) * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_test_randn(kb_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n, int64_t ncols, double* Z_out) {
+    if (!ctx) return bad_ctx();
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double* dZ;
+    KB_TRY(sc.alloc(&dZ, (size_t)n * ncols));
+    KB_TRY(randn_dev(ctx, seed, row_offset, (long)n, (long)ncols, 0, dZ, (long)n));
+    KB_CUDA(ctx, cudaMemcpyAsync(Z_out, dZ, sizeof(double) * n * ncols, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+// Coordinate-descent s-solvers (MVR / maximum entropy / SDP-ccd) as ONE persistent kernel per launch.
+//
+// Reference (paths relative to biona001/Knockoffs.jl v2.0.2): solve_MVR src/utilities.jl:124-175,
+// solve_max_entropy :221-280, solve_sdp_ccd :291-343, rank-1 factor updates :516-625.
+//
+// Device formulation.  The reference keeps the Cholesky factor U of A = κΣ − S (+ λmin I) and per
+// coordinate j does 2-3 triangular solves with e_j / κΣ[:,j] and one Givens rank-1 up/downdate --
+// every one of them an O(p)-deep dependency chain.  All the scalars those solves produce are
+// entries of A⁻¹:   ‖L⁻¹e_j‖² = (A⁻¹)_jj,   ‖A⁻¹e_j‖² = ‖(A⁻¹)[:,j]‖²,
+// ‖L⁻¹ỹ‖² = A_jj (A_jj (A⁻¹)_jj − 1)  for ỹ = κΣ[:,j] with ỹ_j = 0 (because ỹ = A e_j − A_jj e_j).
+// So the kernel keeps the symmetric inverse M = A⁻¹ (lower triangle, column-major) resident in HBM
+// and the factor modification A ← A − δ e_j e_jᵀ becomes the rank-1 Sherman–Morrison update
+//      M ← M + c · m_j m_jᵀ,   c = δ / (1 − δ M_jj),   m_j = M[:, j]
+// -- a perfectly parallel, fully coalesced streaming pass over the p(p+1)/2 stored entries
+// (8 B read + 8 B written per entry = 8p² B per coordinate, the same count as the reference's
+// solves + update), with no dependency chain at all.  The only cross-CTA communication
+// per coordinate is the next column m_{j+1}, which its owners publish (already updated) BEFORE
+// they stream the rest of their slots, so the flag wait at the next coordinate is normally
+// already satisfied.
+//
+// Work decomposition: the lower triangle is cut into "slots" = (column k, 64-row block rb >= k/64);
+// slots are enumerated column-major and each CTA owns a contiguous, equal-sized slot range.  The
+// buffer's leading dimension is a multiple of 64 with zero padding rows, and the 64 x 64 diagonal
+// blocks are kept fully symmetric, so every slot is one unmasked 512-byte warp access
+// (32 lanes x double2) -- no per-element predicates in the streaming loop.
+// Line-search scalars (‖m_j‖², max|m| per 64-row block) use warp-shuffle reductions; every CTA
+// derives bit-identical scalars from the same published column, so all CTAs take identical
+// skip / clip / convergence decisions without any further exchange.
+#include "kb_common.cuh"
+#include "ccd.cuh"
+
+namespace kb {
+
+constexpr int CCD_THREADS = 384;
+constexpr int CCD_WARPS = CCD_THREADS / 32;
+constexpr int SLOT_ROWS = CCD_SLOT_ROWS;
+constexpr int CCD_ILP = 4;            // slots in flight per warp
+constexpr double SKIP_ABS = 1e-40;    // slot updates with |c m_k| max|m_rb| below this are dropped (banded Σ)
+constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: watchdog, never reached in a correct run
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct SlotPos {
+    int k;    // column
+    int rb;   // 64-row block
+};
+
+// slot enumeration: column k owns row blocks rb = k/64 .. nrb-1
+__device__ __forceinline__ SlotPos slot_from_index(long idx, int nrb) {
+    // columns come in groups of 64 with the same slot count (nrb - g); walk groups (<= p/64 steps, once)
+    int g = 0;
+    long per = (long)SLOT_ROWS * nrb;
+    while (g < nrb - 1 && idx >= per) {
+        idx -= per;
+        ++g;
+        per = (long)SLOT_ROWS * (nrb - g);
+    }
+    const int cnt = nrb - g;
+    SlotPos s;
+    s.k = g * SLOT_ROWS + (int)(idx / cnt);
+    s.rb = g + (int)(idx % cnt);
+    return s;
+}
+
+__host__ __device__ __forceinline__ long slot_index(int k, int rb, int nrb) {
+    const int g = k / SLOT_ROWS;
+    // slots before group g: 64 * sum_{h<g} (nrb - h)
+    const long before = (long)SLOT_ROWS * ((long)g * nrb - (long)g * (g - 1) / 2);
+    return before + (long)(k - g * SLOT_ROWS) * (nrb - g) + (rb - g);
+}
+
+// deterministic block reduction of (sum) -- identical instruction sequence in every CTA, so every
+// CTA derives bit-identical line-search scalars from the same published column.
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < CCD_WARPS; ++w) t += red[w];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(CCD_THREADS, 2) ccd_stream_kernel(const CcdParams P) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int s_abort;
+    const int p = P.p;
+    const long ld = P.ld;                  // multiple of 64
+    const int nrb = (int)(ld / SLOT_ROWS);
+    double* col = smem;                    // current column m_j, ld doubles (rows >= p are zero)
+    double* rbmax = smem + ld;             // max|m| per 64-row block
+    double* red = rbmax + ((nrb + 3) & ~3);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* __restrict__ M = P.M;
+    const long colstride = ld + 8;         // colbuf entry: ld values (rows >= p zero), then s_j, adiag_j
+
+    const long total_slots = slot_index(p - 1, nrb - 1, nrb) + 1;
+    const long s_begin = total_slots * blockIdx.x / gridDim.x;
+    const long s_end = total_slots * (blockIdx.x + 1) / gridDim.x;
+    const bool have_slots = s_end > s_begin;
+    const SlotPos first = slot_from_index(have_slots ? s_begin : 0, nrb);
+    const SlotPos last = slot_from_index(have_slots ? s_end - 1 : 0, nrb);
+
+    const double m = P.m;
+    const int method = P.method;
+    double lam = P.sdp_lambda;
+    unsigned long long target = gridDim.x;
+    int buf = 0;
+    int status = 0;
+    int sweeps = 0;
+    double touched = 0.0, nupd = 0.0;
+
+    for (int l = 0; l < P.nsweeps && status == 0; ++l) {
+        ++sweeps;
+        double max_delta = 0.0;
+        for (int j = 0; j < p; ++j) {
+            // ---- 1. wait for column j (published during the previous coordinate) ----
+            if (tid == 0) {
+                int ab = 0;
+                unsigned spins = 0;
+                const long long t0 = clock64();
+                while (ld_acquire_u64(P.ready) < target) {
+                    if ((++spins & 255u) == 0u) {
+                        if (ld_acquire_u64(P.ready + 1) != 0ULL) { ab = 1; break; }
+                        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+                            atomicExch(P.ready + 1, 1ULL);
+                            ab = 1;
+                            break;
+                        }
+                    }
+                }
+                s_abort = ab;
+            }
+            __syncthreads();
+            if (s_abort) { status = KB_ERR_CUDA; break; }
+            target += gridDim.x;
+            const double* cb = P.colbuf + (long)buf * colstride;
+            // ---- 2. stage the column, sum of squares, per-row-block max ----
+            double ss = 0.0;
+            for (int rb = warp; rb < nrb; rb += CCD_WARPS) {
+                const int r = rb * SLOT_ROWS + 2 * lane;
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(cb + r));
+                *reinterpret_cast<double2*>(col + r) = v;
+                ss = fma(v.x, v.x, ss);
+                ss = fma(v.y, v.y, ss);
+                double mx = fmax(fabs(v.x), fabs(v.y));
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0) rbmax[rb] = mx;
+            }
+            const double sj = __ldcg(cb + ld);
+            const double ajj = __ldcg(cb + ld + 1);
+            ss = block_sum(ss, red, tid);          // includes the barrier that publishes col[] / rbmax[]
+            const double Mjj = col[j];
+
+            // ---- 3. line search (every thread, identical arithmetic) ----
+            double delta = 0.0;      // A <- A - delta e_j e_j'
+            double s_new = sj;
+            bool skip = false;
+            if (method == KB_METHOD_MVR) {
+                // utilities.jl:149-159, solve_quadratic :187-199
+                const double cn = -ss, cd = Mjj;
+                const double qa = -cn - cd * cd * m * m;
+                const double qb = 2.0 * (-cn * sj + cd * m * m);
+                const double qc = -cn * sj * sj - m * m;
+                double dj;
+                if (qa == 0.0 && qc == 0.0) {
+                    dj = 0.0;
+                } else {
+                    const double disc = sqrt(qb * qb - 4.0 * qa * qc);
+                    const double x1 = (-qb + disc) / (2.0 * qa);
+                    const double x2 = (-qb - disc) / (2.0 * qa);
+                    dj = (-sj < x1 && x1 < 1.0 / cd) ? x1 : x2;
+                    if (isinf(dj) || isnan(dj)) status = KB_ERR_NAN;
+                }
+                const double ub = 1.0 / cd - P.lambda_min;
+                if (dj > ub) dj = ub;
+                if (fabs(dj) < 1e-15) skip = true;
+                else { s_new = sj + dj; delta = dj; }
+            } else {
+                // utilities.jl:243-264 / :318-336 with  ‖L⁻¹ỹ‖² = A_jj (A_jj M_jj − 1)
+                const double kSjj = P.ksig_diag[j];
+                const double x_l2 = ajj * (ajj * Mjj - 1.0);
+                const double zeta = kSjj - sj;
+                const double c = (zeta * x_l2) / (zeta + x_l2);
+                if (method == KB_METHOD_MAXENT) {
+                    const double sn = (kSjj - c) / 2.0;
+                    const double ub = 1.0 / Mjj - P.lambda_min;
+                    double d = sn - sj;
+                    if (d > ub) d = ub;
+                    if (fabs(d) < 1e-15) skip = true;
+                    else { s_new = sn; delta = d; }              // Q2: s takes the unclipped value
+                } else {
+                    double sn = kSjj - c - lam;
+                    sn = sn < 0.0 ? 0.0 : (sn > 1.0 ? 1.0 : sn);
+                    const double d = sj - sn;
+                    if (fabs(d) < 1e-15) skip = true;
+                    else { s_new = sn; delta = -d; }
+                    if (isnan(sn)) status = KB_ERR_NAN;
+                }
+            }
+            double cfac = 0.0;
+            if (!skip && status == 0) {
+                const double den = 1.0 - delta * Mjj;
+                if (!(den > 0.0)) status = KB_ERR_NOT_PD;        // downdate would leave the PD cone (:591-593)
+                else cfac = delta / den;
+                if (fabs(delta) > max_delta) max_delta = fabs(delta);
+                nupd += 1.0;
+            }
+            if (status != 0) cfac = 0.0;
+
+            // ---- 4. publish column jn = j+1 (already updated) ----
+            const int jn = (j + 1 == p) ? 0 : j + 1;
+            const int nbuf = (buf + 1 == 3) ? 0 : buf + 1;
+            double* ob = P.colbuf + (long)nbuf * colstride;
+            const int rbn = jn / SLOT_ROWS;
+            if (have_slots) {
+                const double mjn = col[jn];
+                // (a) row jn of my columns k < jn:   entry (jn, k) lives in slot (k, rbn)
+                const int kend = min(last.k, jn - 1);
+                for (int k = first.k + tid; k <= kend; k += CCD_THREADS) {
+                    const long si = slot_index(k, rbn, nrb);
+                    if (si >= s_begin && si < s_end) {
+                        const double old = M[(long)jn + (long)k * ld];
+                        ob[k] = fma(cfac * col[k], mjn, old);
+                    }
+                }
+                // (b) column jn itself, rows i >= jn, for the slots (jn, rb) that are mine
+                if (jn >= first.k && jn <= last.k) {
+                    const double cjn = cfac * mjn;
+                    const int rb_lo = (jn == first.k) ? max(first.rb, rbn) : rbn;
+                    const int rb_hi = (jn == last.k) ? last.rb : nrb - 1;
+                    const int i_lo = max(jn, rb_lo * SLOT_ROWS);
+                    const int i_hi = min(p, (rb_hi + 1) * SLOT_ROWS);
+                    for (int i = i_lo + tid; i < i_hi; i += CCD_THREADS) {
+                        const double old = M[(long)i + (long)jn * ld];
+                        ob[i] = fma(cjn, col[i], old);
+                    }
+                }
+            }
+            // s_j / A_jj bookkeeping: the owner of the diagonal slot of column j records them; the
+            // owner of column jn's diagonal slot forwards s_jn, A_jn,jn with the column.
+            {
+                const long sdiag_j = slot_index(j, j / SLOT_ROWS, nrb);
+                if (tid == 0 && sdiag_j >= s_begin && sdiag_j < s_end && !skip && status == 0) {
+                    P.s[j] = s_new;
+                    P.adiag[j] = ajj - delta;
+                }
+                __syncthreads();   // s[j] visible to this CTA's thread 0 below if jn == j (p == 1)
+                const long sdiag_n = slot_index(jn, rbn, nrb);
+                if (tid == 0 && sdiag_n >= s_begin && sdiag_n < s_end) {
+                    ob[ld] = P.s[jn];
+                    ob[ld + 1] = P.adiag[jn];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(P.ready, 1ULL);
+            }
+            buf = nbuf;
+
+            // ---- 5. stream my slots:  M(i,k) += (c m_k) m_i ----
+            if (cfac != 0.0 && have_slots) {
+                int k = first.k, rb = first.rb;
+                long si = s_begin;
+                auto advance = [&](int steps) {
+                    si += steps;
+                    rb += steps;
+                    while (rb >= nrb && k < p) {
+                        const int over = rb - nrb;
+                        ++k;
+                        rb = k / SLOT_ROWS + over;
+                    }
+                };
+                advance(warp);
+                int nact = 0;
+                while (si < s_end) {
+                    double2* ptr[CCD_ILP];
+                    double ck[CCD_ILP];
+                    int rr[CCD_ILP];
+                    bool act[CCD_ILP];
+#pragma unroll
+                    for (int u = 0; u < CCD_ILP; ++u) {
+                        act[u] = si < s_end;
+                        ck[u] = 0.0;
+                        rr[u] = 0;
+                        ptr[u] = nullptr;
+                        if (act[u]) {
+                            ck[u] = cfac * col[k];
+                            act[u] = fabs(ck[u]) * rbmax[rb] >= SKIP_ABS;
+                            rr[u] = rb * SLOT_ROWS + 2 * lane;
+                            ptr[u] = reinterpret_cast<double2*>(M + (long)rr[u] + (long)k * ld);
+                            advance(CCD_WARPS);
+                        }
+                    }
+                    double2 v[CCD_ILP];
+#pragma unroll
+                    for (int u = 0; u < CCD_ILP; ++u)
+                        if (act[u]) v[u] = *ptr[u];
+#pragma unroll
+                    for (int u = 0; u < CCD_ILP; ++u) {
+                        if (act[u]) {
+                            const double2 mv = *reinterpret_cast<const double2*>(col + rr[u]);
+                            v[u].x = fma(ck[u], mv.x, v[u].x);
+                            v[u].y = fma(ck[u], mv.y, v[u].y);
+                            *ptr[u] = v[u];
+                            ++nact;
+                        }
+                    }
+                }
+                if (lane == 0) touched += (double)nact;
+            }
+            if (status != 0) break;
+        }
+        if (blockIdx.x == 0 && tid == 0 && status == 0) {
+            if (P.sweep0 + l < KB_MAX_TRACE) P.trace[P.sweep0 + l] = max_delta;
+            P.counters[3] = max_delta;
+        }
+        if (status != 0) break;
+        if (method == KB_METHOD_SDP_CCD) {
+            lam *= P.sdp_mu;                       // utilities.jl:339-340
+            if (lam < P.tol) break;
+        } else if (max_delta < P.tol) {
+            break;                                 // utilities.jl:172 / :277
+        }
+    }
+    // per-CTA counters
+    const double tsum = block_sum((lane == 0) ? touched : 0.0, red, tid);
+    if (tid == 0) {
+        atomicAdd(P.counters + 0, tsum);
+        if (blockIdx.x == 0) {
+            P.counters[1] += nupd;
+            P.counters[2] = lam;
+            *P.sweeps_out = sweeps;
+            *P.status = status;
+        }
+    }
+}
+
+// column 0 of the current M (+ s_0, A_00) into colbuf[0]; ready = number of CTAs, abort flag cleared
+__global__ void ccd_stream_init_kernel(const CcdParams P, unsigned long long nctas) {
+    const int p = P.p;
+    const long ld = P.ld;
+    const long colstride = ld + 8;
+    for (long i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * colstride; i += (long)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (i < p) v = P.M[i];              // column 0, rows 0..p-1 (all in the lower triangle)
+        else if (i == ld) v = P.s[0];
+        else if (i == ld + 1) v = P.adiag[0];
+        P.colbuf[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.ready[0] = nctas;
+        P.ready[1] = 0ULL;
+        *P.status = 0;
+        *P.sweeps_out = 0;
+    }
+}
+
+size_t ccd_stream_colbuf_doubles(int p) { return 3 * (size_t)(ccd_stream_ld(p) + 8); }
+
+int ccd_stream_run(kb_ctx* ctx, const CcdParams& P, int* nctas_out) {
+    const int p = P.p;
+    if (P.ld != ccd_stream_ld(p)) return set_error(ctx, KB_ERR_INVALID, "ccd_stream_run: bad leading dimension");
+    const int nrb = (int)(P.ld / SLOT_ROWS);
+    const size_t smem = (size_t)(P.ld + ((nrb + 3) & ~3) + CCD_WARPS + 4) * sizeof(double);
+    if (smem > 227 * 1024) return set_error(ctx, KB_ERR_INVALID, "p = %d too large for the streaming CCD kernel", p);
+    KB_CUDA(ctx, cudaFuncSetAttribute(ccd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    KB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccd_stream_kernel, CCD_THREADS, smem));
+    if (per_sm < 1) return set_error(ctx, KB_ERR_CUDA, "streaming CCD kernel does not fit on an SM");
+    if (per_sm > 2) per_sm = 2;
+    const long total_slots = slot_index(p - 1, nrb - 1, nrb) + 1;
+    long nctas = (long)ctx->num_sms * per_sm;
+    // small problems: keep a few slot passes per warp so CTAs are not empty
+    const long min_slots_per_cta = 64;
+    if (nctas > (total_slots + min_slots_per_cta - 1) / min_slots_per_cta)
+        nctas = (total_slots + min_slots_per_cta - 1) / min_slots_per_cta;
+    if (nctas < 1) nctas = 1;
+    ccd_stream_init_kernel<<<8, 256, 0, ctx->stream>>>(P, (unsigned long long)nctas);
+    ctx->launches++;
+    KB_CUDA(ctx, cudaGetLastError());
+    void* args[] = {(void*)&P};
+    KB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)ccd_stream_kernel, dim3((unsigned)nctas), dim3(CCD_THREADS), args,
+                                             smem, ctx->stream));
+    ctx->launches++;
+    if (nctas_out) *nctas_out = (int)nctas;
+    return KB_OK;
+}
+
+}  // namespace kb

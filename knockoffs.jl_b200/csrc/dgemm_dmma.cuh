@@ -1,0 +1,285 @@
+// Hand-written FP64 tensor-core GEMM for sm_100a.
+//
+// C (M x N, column-major) = alpha * sum_seg A_seg * B_seg + beta * Cin + bias_n
+//
+// The FP64 tensor path on Blackwell is the warp-level DMMA: `mma.sync.aligned.m8n8k4.f64`
+// (SASS DMMA.8x8x4; tcgen05 has no f64 kind, and the m16n8k* f64 shapes are split into 8x8x4 by
+// ptxas on sm_100a), fed from shared memory.  Tiles are staged global -> shared with a 3-stage
+// cp.async (LDGSTS) pipeline, 16-byte transactions, padded rows so that every fragment load is
+// bank-conflict free.
+//
+// CTA tile 128 x 128 x 16, 256 threads = 8 warps laid out 2 (M) x 4 (N); a warp owns 64 x 32 =
+// 8 x 4 DMMA tiles (64 accumulator doubles per thread).
+//
+// Up to 3 K-segments (A_i, B_i) are accumulated into one tile so that the sampling stage
+// X̃ = X − X·ΣinvS + Z·L (+ T·M) is ONE fused GEMM.  Each segment may declare triangular
+// structure (k-range clipped per tile) so triangular operands cost half the flops.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace kb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BN = 128;
+constexpr int GEMM_BK = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_PADM = GEMM_BM + 4;   // [k][m] rows: stride mod 16 == 4 -> conflict-free fragments
+constexpr int GEMM_PADK = GEMM_BK + 4;   // [m][k] rows: stride mod 16 == 4
+constexpr int GEMM_TILE_DOUBLES = (GEMM_BK * GEMM_PADM > GEMM_BM * GEMM_PADK) ? GEMM_BK * GEMM_PADM
+                                                                              : GEMM_BM * GEMM_PADK;
+constexpr size_t GEMM_SMEM_BYTES = (size_t)GEMM_STAGES * 2 * GEMM_TILE_DOUBLES * sizeof(double);
+
+enum : int { A_MCONTIG = 0, A_KCONTIG = 1 };   // A(m,k) at m + k*lda   |   k + m*lda
+enum : int { B_KCONTIG = 0, B_NCONTIG = 1 };   // B(k,n) at k + n*ldb   |   n + k*ldb
+
+// per-segment k-range clipping (operand known to be zero outside)
+enum : int {
+    SEG_KLO_N = 1,   // k >= n0            (B lower-triangular in (k,n):  B[k,n] = 0 for k < n)
+    SEG_KLO_M = 2,   // k >= m0            (A upper-triangular in (m,k):  A[m,k] = 0 for k < m)
+    SEG_KHI_N = 4,   // k <  n0 + BN       (B upper-triangular in (k,n))
+    SEG_KHI_M = 8,   // k <  m0 + BM       (A lower-triangular in (m,k))
+};
+
+struct GemmSeg {
+    const double* A;
+    long lda;
+    const double* B;
+    long ldb;
+    int K;
+    int flags;
+};
+
+struct GemmParams {
+    int M, N;
+    int nseg;
+    GemmSeg seg[3];
+    double* C;
+    long ldc;
+    const double* Cin;   // may alias C (each element is read then written by the same thread)
+    long ldcin;
+    double alpha, beta;
+    const double* bias_n;   // optional, added per column n
+    int tile_mode;          // 0 all tiles, 1 lower tiles only (skip tiles with m0 + BM <= n0)
+    int store_mode;         // 0 all, 1 only elements with m >= n (lower incl. diagonal)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Stage one BM x BK tile of A and one BK x BN tile of B into shared memory.
+template <int AL, int BL, bool VEC>
+__device__ __forceinline__ void gemm_load_stage(const GemmSeg& sg, int M, int N, int m0, int n0, int k0,
+                                                int kend, double* As, double* Bs, int tid) {
+    // ---- A tile ----
+    if (AL == A_MCONTIG) {
+        if (VEC) {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BM * GEMM_BK / 2) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int k = c / (GEMM_BM / 2), m = (c % (GEMM_BM / 2)) * 2;
+                int gm = m0 + m, gk = k0 + k;
+                int valid = (gk < kend) ? max(0, min(2, M - gm)) : 0;
+                const double* src = valid ? sg.A + (long)gm + (long)gk * sg.lda : sg.A;
+                cp_async16(As + k * GEMM_PADM + m, src, valid * 8);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BM * GEMM_BK) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int k = c / GEMM_BM, m = c % GEMM_BM;
+                int gm = m0 + m, gk = k0 + k;
+                int valid = (gk < kend && gm < M);
+                const double* src = valid ? sg.A + (long)gm + (long)gk * sg.lda : sg.A;
+                cp_async8(As + k * GEMM_PADM + m, src, valid * 8);
+            }
+        }
+    } else {
+        if (VEC) {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BM * GEMM_BK / 2) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int m = c / (GEMM_BK / 2), k = (c % (GEMM_BK / 2)) * 2;
+                int gm = m0 + m, gk = k0 + k;
+                int valid = (gm < M) ? max(0, min(2, kend - gk)) : 0;
+                const double* src = valid ? sg.A + (long)gk + (long)gm * sg.lda : sg.A;
+                cp_async16(As + m * GEMM_PADK + k, src, valid * 8);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BM * GEMM_BK) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int m = c / GEMM_BK, k = c % GEMM_BK;
+                int gm = m0 + m, gk = k0 + k;
+                int valid = (gk < kend && gm < M);
+                const double* src = valid ? sg.A + (long)gk + (long)gm * sg.lda : sg.A;
+                cp_async8(As + m * GEMM_PADK + k, src, valid * 8);
+            }
+        }
+    }
+    // ---- B tile ----
+    if (BL == B_KCONTIG) {
+        if (VEC) {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BN * GEMM_BK / 2) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int n = c / (GEMM_BK / 2), k = (c % (GEMM_BK / 2)) * 2;
+                int gn = n0 + n, gk = k0 + k;
+                int valid = (gn < N) ? max(0, min(2, kend - gk)) : 0;
+                const double* src = valid ? sg.B + (long)gk + (long)gn * sg.ldb : sg.B;
+                cp_async16(Bs + n * GEMM_PADK + k, src, valid * 8);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BN * GEMM_BK) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int n = c / GEMM_BK, k = c % GEMM_BK;
+                int gn = n0 + n, gk = k0 + k;
+                int valid = (gk < kend && gn < N);
+                const double* src = valid ? sg.B + (long)gk + (long)gn * sg.ldb : sg.B;
+                cp_async8(Bs + n * GEMM_PADK + k, src, valid * 8);
+            }
+        }
+    } else {
+        if (VEC) {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BN * GEMM_BK / 2) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int k = c / (GEMM_BN / 2), n = (c % (GEMM_BN / 2)) * 2;
+                int gn = n0 + n, gk = k0 + k;
+                int valid = (gk < kend) ? max(0, min(2, N - gn)) : 0;
+                const double* src = valid ? sg.B + (long)gn + (long)gk * sg.ldb : sg.B;
+                cp_async16(Bs + k * GEMM_PADM + n, src, valid * 8);
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < (GEMM_BN * GEMM_BK) / GEMM_THREADS; ++it) {
+                int c = tid + it * GEMM_THREADS;
+                int k = c / GEMM_BN, n = c % GEMM_BN;
+                int gn = n0 + n, gk = k0 + k;
+                int valid = (gk < kend && gn < N);
+                const double* src = valid ? sg.B + (long)gn + (long)gk * sg.ldb : sg.B;
+                cp_async8(Bs + k * GEMM_PADM + n, src, valid * 8);
+            }
+        }
+    }
+}
+
+template <int AL, int BL, bool VEC>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmParams P) {
+    extern __shared__ __align__(16) double gemm_smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps
+    const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
+    if (P.tile_mode == 1 && m0 + GEMM_BM <= n0) return;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int lr = lane >> 2, lc = lane & 3;
+
+    for (int s = 0; s < P.nseg; ++s) {
+        const GemmSeg sg = P.seg[s];
+        int kbeg = 0, kend = sg.K;
+        if (sg.flags & SEG_KLO_N) kbeg = max(kbeg, n0);
+        if (sg.flags & SEG_KLO_M) kbeg = max(kbeg, m0);
+        if (sg.flags & SEG_KHI_N) kend = min(kend, n0 + GEMM_BN);
+        if (sg.flags & SEG_KHI_M) kend = min(kend, m0 + GEMM_BM);
+        kbeg = (kbeg / GEMM_BK) * GEMM_BK;
+        if (kend <= kbeg) continue;
+        const int nkt = (kend - kbeg + GEMM_BK - 1) / GEMM_BK;
+
+        __syncthreads();   // previous segment's readers are done with the stage buffers
+        // prologue
+#pragma unroll
+        for (int st = 0; st < GEMM_STAGES - 1; ++st) {
+            if (st < nkt)
+                gemm_load_stage<AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + st * GEMM_BK, kend,
+                                             gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES,
+                                             gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES + GEMM_TILE_DOUBLES, tid);
+            cp_async_commit();
+        }
+        for (int kt = 0; kt < nkt; ++kt) {
+            cp_async_wait<GEMM_STAGES - 2>();
+            __syncthreads();
+            // prefetch tile kt + STAGES - 1 into the buffer consumed at iteration kt - 1
+            {
+                int nk = kt + GEMM_STAGES - 1;
+                if (nk < nkt) {
+                    int st = nk % GEMM_STAGES;
+                    gemm_load_stage<AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + nk * GEMM_BK, kend,
+                                                 gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES,
+                                                 gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES + GEMM_TILE_DOUBLES,
+                                                 tid);
+                }
+                cp_async_commit();
+            }
+            const double* As = gemm_smem + (size_t)(kt % GEMM_STAGES) * 2 * GEMM_TILE_DOUBLES;
+            const double* Bs = As + GEMM_TILE_DOUBLES;
+#pragma unroll
+            for (int kk = 0; kk < GEMM_BK / 4; ++kk) {
+                double af[8], bf[4];
+                const int k = kk * 4 + lc;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int m = wm * 64 + i * 8 + lr;
+                    af[i] = (AL == A_MCONTIG) ? As[k * GEMM_PADM + m] : As[m * GEMM_PADK + k];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = wn * 32 + j * 8 + lr;
+                    bf[j] = (BL == B_KCONTIG) ? Bs[n * GEMM_PADK + k] : Bs[k * GEMM_PADM + n];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+        cp_async_wait<0>();
+    }
+
+    // epilogue: thread holds (row = lr, cols = 2*lc + {0,1}) of every 8x8 tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + wm * 64 + i * 8 + lr;
+        if (m >= P.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
+                if (n >= P.N) continue;
+                if (P.store_mode == 1 && m < n) continue;
+                double v = P.alpha * acc[i][j][e];
+                if (P.beta != 0.0) v += P.beta * P.Cin[(long)m + (long)n * P.ldcin];
+                if (P.bias_n) v += P.bias_n[n];
+                P.C[(long)m + (long)n * P.ldc] = v;
+            }
+        }
+    }
+}
+
+}  // namespace kb

@@ -1,0 +1,11 @@
+"""Loader: makes the package directory ``knockoffs.jl_b200/`` importable as ``knockoffs_b200``."""
+import importlib.util as _u
+import os as _os
+import sys as _sys
+
+_dir = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "knockoffs.jl_b200")
+_spec = _u.spec_from_file_location("knockoffs_b200", _os.path.join(_dir, "__init__.py"),
+                                   submodule_search_locations=[_dir])
+_mod = _u.module_from_spec(_spec)
+_sys.modules["knockoffs_b200"] = _mod
+_spec.loader.exec_module(_mod)

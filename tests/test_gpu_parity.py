@@ -1,0 +1,256 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI
+(libknockoffs_b200.so via ctypes) and is compared with the CPU oracle on the same seeded inputs.
+Tolerances (BASELINE.json north_star): s 1e-8 relative, factors 1e-8, X̃ 1e-10, objectives 1e-8."""
+import numpy as np
+import pytest
+
+from conftest import toeplitz
+from oracle import c_oracle, knockoffs_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+S_RTOL = 1e-8
+XKO_TOL = 1e-10
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+# ---- dense building blocks -------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,ta,tb", [(128, 128, 16, 0, 0), (257, 131, 77, 0, 0), (300, 200, 129, 1, 0),
+                                         (64, 500, 333, 0, 1), (511, 129, 260, 1, 1), (1, 1, 1, 0, 0)])
+def test_dgemm(kb, ctx, M, N, K, ta, tb):
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((K, M) if ta else (M, K))
+    B = rng.standard_normal((N, K) if tb else (K, N))
+    C0 = rng.standard_normal((M, N))
+    got = kb.hook_dgemm(A, B, C0, transa=ta, transb=tb, alpha=0.7, beta=-1.3, ctx=ctx)
+    want = 0.7 * (A.T if ta else A) @ (B.T if tb else B) - 1.3 * C0
+    assert np.max(np.abs(got - want)) < 1e-11 * max(1, K)
+
+
+@pytest.mark.parametrize("p", [1, 5, 127, 128, 129, 500, 777])
+def test_potrf_and_inverse(kb, ctx, p):
+    rng = np.random.default_rng(p)
+    B = rng.standard_normal((p, p + 3))
+    A = B @ B.T / p + 0.5 * np.eye(p)
+    Au = np.triu(A) + np.tril(rng.standard_normal((p, p)), -1)      # garbage below: only the upper triangle is read
+    L = kb.hook_potrf(Au, ctx=ctx)
+    assert np.max(np.abs(L - np.linalg.cholesky(A))) < 1e-11
+    Ai = kb.hook_spd_inverse(Au, ctx=ctx)
+    assert np.max(np.abs(Ai - np.linalg.inv(A))) < 1e-9
+    assert np.max(np.abs(Ai - Ai.T)) == 0.0
+
+
+def test_potrf_not_pd_raises(kb, ctx):
+    A = np.eye(200); A[150, 150] = -1.0
+    with pytest.raises(kb.PosDefException):
+        kb.hook_potrf(A, ctx=ctx)
+
+
+def test_eigmin(kb, ctx):
+    for p, rho in [(50, 0.4), (300, 0.5), (1000, 0.4)]:
+        S = toeplitz(p, rho)
+        lam = kb.eigmin(S, ctx=ctx)
+        assert abs(lam - np.linalg.eigvalsh(S).min()) < 1e-11
+
+
+# ---- CCD solvers --------------------------------------------------------------------------------------
+def _sigma(kind, p):
+    if kind == "ar1":
+        return toeplitz(p, 0.5)
+    g = np.repeat(np.arange((p + 9) // 10), 10)[:p]
+    return np.asfortranarray(ko.simulate_block_covariance(g, 0.5, 0.25))
+
+
+@pytest.mark.parametrize("kind,p,method,m", [
+    ("ar1", 500, "mvr", 1),          # BASELINE config 1
+    ("ar1", 500, "maxent", 1), ("ar1", 300, "sdp_ccd", 1),
+    ("block", 400, "mvr", 5), ("block", 400, "maxent", 5), ("block", 250, "sdp_ccd", 5),
+    ("ar1", 63, "mvr", 1), ("ar1", 64, "maxent", 2), ("ar1", 65, "sdp_ccd", 1), ("ar1", 1, "mvr", 1),
+    ("ar1", 2, "maxent", 1), ("block", 130, "mvr", 3),
+])
+@pytest.mark.parametrize("refresh", [1, 0])
+def test_solve_s_matches_oracle(kb, ctx, kind, p, method, m, refresh):
+    Sigma = _sigma(kind, p)
+    s0 = ko.solve_equi(Sigma, m)
+    want = c_oracle.solve_ccd(Sigma, method, m=m, s_init=s0)
+    got, info = kb.solve_s(Sigma, method, m=m, s_init=s0, ctx=ctx, return_info=True, refresh_every=refresh)
+    assert info["sweeps"] == want["sweeps"]
+    assert rel(got, want["s"]) < S_RTOL
+    if method != "sdp_ccd":
+        assert np.allclose(info["trace"], want["trace"], rtol=1e-6, atol=1e-12)
+    assert info["updates"] == want["n_updates"]
+
+
+def test_solve_s_default_init_and_covariance_scaling(kb, ctx):
+    """NULL s_init -> solve_equi on the device; covariance input -> cov2cor and s .*= sigma^2 (utilities.jl:31-49)."""
+    p = 300
+    Sigma = toeplitz(p, 0.5)
+    d = np.linspace(0.5, 2.0, p)
+    Cov = np.asfortranarray(Sigma * np.outer(d, d))
+    want = ko.solve_s(Cov, "maxent", m=1)
+    got = kb.solve_s(Cov, "maxent", m=1, ctx=ctx)
+    assert rel(got, want) < S_RTOL
+    # only the upper triangle is trusted, inputs are never written
+    junk = np.asfortranarray(np.triu(Cov) + np.tril(np.full((p, p), 7.0), -1))
+    keep = junk.copy()
+    got2 = kb.solve_s(junk, "maxent", m=1, ctx=ctx)
+    assert np.array_equal(junk, keep) and np.array_equal(got, got2)
+
+
+def test_golden_K1_on_gpu(kb, ctx, golden):
+    """docs/src/man/modelX/modelX.md:143-169: 16-digit MVR vector, Toeplitz rho=0.4, p=1000, all defaults."""
+    g = golden["K1_mvr_ar1_rho0.4_p1000_m1"]
+    s = kb.solve_s(toeplitz(1000, 0.4), "mvr", ctx=ctx)
+    h, t = np.array(g["head"]), np.array(g["tail"])
+    assert np.max(np.abs(s[:len(h)] - h)) < 1e-9 and np.max(np.abs(s[-len(t):] - t)) < 1e-9
+
+
+def test_reference_property_tests(kb, ctx):
+    """runtests.jl:773-808 ('multiple knockoffs'): PSD of (m+1)/m Sigma - diag(s), 0 <= s <= 1."""
+    Sigma = toeplitz(500, 0.4)
+    for method, m in [("mvr", 3), ("maxent", 5), ("sdp_ccd", 5)]:
+        s = kb.solve_s(Sigma, method, m=m, ctx=ctx)
+        assert np.all(s >= 0) and np.all(s <= 1 + 1e-12)
+        assert np.linalg.eigvalsh((m + 1) / m * Sigma - np.diag(s)).min() > -1e-8
+    # runtests.jl:349-365 keyword pass-through
+    a = kb.solve_s(Sigma, "sdp_ccd", ctx=ctx, λ=0.7, μ=0.7)
+    b = kb.solve_s(Sigma, "sdp_ccd", ctx=ctx, λ=0.9, μ=0.9)
+    assert np.max(np.abs(a - b)) < 0.05
+
+
+def test_error_behaviour(kb, ctx):
+    Sigma = toeplitz(50, 0.4)
+    with pytest.raises(kb.KnockoffsError):      # utilities.jl:28
+        kb.solve_s(Sigma, "mvr", m=0.5, ctx=ctx)
+    with pytest.raises(kb.KnockoffsError):      # utilities.jl:46
+        kb.solve_s(Sigma, "nonsense", ctx=ctx)
+    with pytest.raises(kb.KnockoffsError):      # utilities.jl:301
+        kb.solve_s(Sigma, "sdp_ccd", ctx=ctx, μ=1.5)
+    with pytest.raises(kb.KnockoffsError):      # utilities.jl:302
+        kb.solve_s(Sigma, "sdp_ccd", ctx=ctx, λ=0.0)
+    bad = -np.eye(50)
+    with pytest.raises(kb.KnockoffsError):
+        kb.solve_s(bad, "mvr", ctx=ctx, s_init=np.full(50, 0.5))
+    notpd = np.asfortranarray(np.full((50, 50), 0.999) + 0.001 * np.eye(50))
+    with pytest.raises(kb.PosDefException):     # cholesky at utilities.jl:140 throws
+        kb.solve_s(notpd, "mvr", ctx=ctx, s_init=np.full(50, 1.0))
+    with pytest.raises(kb.KnockoffsError):      # modelX.jl:105
+        kb.condition(np.zeros((4, 50)), np.zeros(50), Sigma, np.full(50, 0.3), m=0, ctx=ctx)
+
+
+# ---- conditional factor + sampling ---------------------------------------------------------------------
+@pytest.mark.parametrize("p,m", [(200, 1), (130, 3), (257, 2)])
+def test_cond_factor_matches_oracle(kb, ctx, p, m):
+    Sigma = toeplitz(p, 0.5)
+    s = c_oracle.solve_ccd(Sigma, "maxent", m=m, s_init=ko.solve_equi(Sigma, m))["s"]
+    SiS_w, L_w = ko.cond_factor(Sigma, s, m)
+    SiS, Lb = kb.cond_factor(Sigma, s, m=m, ctx=ctx)
+    assert np.max(np.abs(SiS - SiS_w)) < 1e-11
+    L = kb.dense_factor_from_blocks(Lb)
+    assert np.max(np.abs(L - L_w)) / np.max(np.abs(L_w)) < 1e-8
+
+
+@pytest.mark.parametrize("n,p,m", [(1000, 500, 1), (333, 130, 3), (4097, 200, 2), (1, 64, 1), (9000, 96, 5)])
+def test_condition_matches_oracle_with_injected_Z(kb, ctx, n, p, m):
+    rng = np.random.default_rng(n + p + m)
+    Sigma = toeplitz(p, 0.5)
+    mu = rng.standard_normal(p)
+    X = np.asfortranarray(rng.standard_normal((n, p)) @ np.linalg.cholesky(Sigma).T + mu)
+    Z = np.asfortranarray(rng.standard_normal((n, m * p)))
+    s = c_oracle.solve_ccd(Sigma, "mvr", m=m, s_init=ko.solve_equi(Sigma, m))["s"]
+    want = ko.condition(X, mu, Sigma, s, m=m, Z=Z)
+    got = kb.condition(X, mu, Sigma, s, m=m, Z=Z, ctx=ctx)
+    assert got.shape == (n, m * p)
+    assert np.max(np.abs(got - want)) < XKO_TOL
+
+
+def test_condition_dense_S(kb, ctx):
+    """group path: S dense block-diagonal (group.jl:125 -> modelX.jl:107-108)."""
+    rng = np.random.default_rng(5)
+    p, n, m = 120, 400, 2
+    g = np.repeat(np.arange(p // 5), 5)
+    Sigma = np.asfortranarray(ko.simulate_block_covariance(g, 0.6, 0.3))
+    S = np.where(g[:, None] == g[None, :], Sigma, 0.0) * 0.4
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    Z = np.asfortranarray(rng.standard_normal((n, m * p)))
+    want = ko.condition(X, np.zeros(p), Sigma, S, m=m, Z=Z)
+    got = kb.condition(X, np.zeros(p), Sigma, S, m=m, Z=Z, ctx=ctx)
+    assert np.max(np.abs(got - want)) < XKO_TOL
+
+
+def test_modelX_one_shot_config1(kb, ctx):
+    """BASELINE config 1 end to end through kb_modelx_gaussian_knockoffs with Z injected."""
+    p, n = 500, 1000
+    Sigma = kb.harness.ar1_sigma(p, 0.5)
+    X = kb.harness.gaussian_X(n, Sigma, 20260001)
+    Z = np.asfortranarray(np.random.default_rng(7).standard_normal((n, p)))
+    mu = np.zeros(p)
+    want_X, want_s = ko.modelX_gaussian_knockoffs(X, "mvr", mu, Sigma, m=1, Z=Z)
+    ko_res = kb.modelX_gaussian_knockoffs(X, "mvr", mu, Sigma, m=1, Z=Z, ctx=ctx)
+    assert rel(ko_res.s, want_s) < S_RTOL
+    assert np.max(np.abs(ko_res.Xko - want_X)) < XKO_TOL
+    assert ko_res.method == "mvr" and ko_res.m == 1 and ko_res.Xko.shape == (n, p)
+
+
+# ---- device RNG ------------------------------------------------------------------------------------------
+def _philox_ref(seed, rows, colpairs):
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    r, c = np.meshgrid(rows.astype(np.uint64), colpairs.astype(np.uint64), indexing="ij")
+    c0 = (r & 0xFFFFFFFF).astype(np.uint64); c1 = (r >> 32).astype(np.uint64)
+    c2 = c.copy(); c3 = np.zeros_like(c)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64(seed >> 32)
+    for _ in range(10):
+        p0 = M0 * c0; p1 = M1 * c2
+        hi0, lo0 = p0 >> 32, p0 & 0xFFFFFFFF
+        hi1, lo1 = p1 >> 32, p1 & 0xFFFFFFFF
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF; k1 = (k1 + W1) & 0xFFFFFFFF
+    a = (c0 << 32) | c1; b = (c2 << 32) | c3
+    u1 = ((a >> 11) + 1).astype(np.float64) * 2.0 ** -53
+    u2 = (b >> 11).astype(np.float64) * 2.0 ** -53
+    rad = np.sqrt(-2.0 * np.log(u1))
+    return rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)
+
+
+def test_device_randn_is_philox_boxmuller_and_shardable(kb, ctx):
+    n, nc = 257, 11
+    Z = kb.hook_randn(12345678901, 1000, n, nc, ctx=ctx)
+    z0, z1 = _philox_ref(12345678901, 1000 + np.arange(n), np.arange((nc + 1) // 2))
+    want = np.empty((n, 2 * ((nc + 1) // 2)))
+    want[:, 0::2], want[:, 1::2] = z0, z1
+    assert np.max(np.abs(Z - want[:, :nc])) < 1e-12
+    # a row shard regenerates the same numbers
+    Zs = kb.hook_randn(12345678901, 1100, 50, nc, ctx=ctx)
+    assert np.array_equal(Zs, Z[100:150])
+    big = kb.hook_randn(7, 0, 20000, 100, ctx=ctx).ravel()
+    assert abs(big.mean()) < 4 / np.sqrt(big.size) and abs(big.var() - 1) < 0.01
+    assert abs(np.mean(big ** 4) - 3) < 0.05
+
+
+def test_device_sampling_moments(kb, ctx):
+    """Z drawn on the device: Cov of the noise part is L'L (reference-literal Z*L)."""
+    p, n = 40, 200000
+    Sigma = toeplitz(p, 0.5)
+    s = c_oracle.solve_ccd(Sigma, "maxent", m=1, s_init=ko.solve_equi(Sigma, 1))["s"]
+    SiS, Lb = kb.cond_factor(Sigma, s, ctx=ctx)
+    X = np.zeros((n, p), order="F")
+    Xko = kb.sample(X, np.zeros(p), SiS, Lb, m=1, Z=None, seed=99, ctx=ctx)
+    L = Lb[:, :, 0]
+    C = Xko.T @ Xko / n
+    assert np.max(np.abs(C - L.T @ L)) < 0.02
+
+
+# ---- Gram --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p", [(1000, 500), (70001, 130), (5, 3)])
+def test_gram(kb, ctx, n, p):
+    rng = np.random.default_rng(n)
+    X = np.asfortranarray(rng.standard_normal((n, p)) + rng.standard_normal(p))
+    G, mu = kb.gram(X, center=True, ctx=ctx)
+    Xc = X - X.mean(0)
+    assert np.max(np.abs(mu - X.mean(0))) < 1e-12
+    assert np.max(np.abs(G - Xc.T @ Xc / n)) < 1e-10
+    G2, _ = kb.gram(X, center=False, denom=n - 1, ctx=ctx)
+    assert np.max(np.abs(G2 - X.T @ X / (n - 1))) < 1e-10
