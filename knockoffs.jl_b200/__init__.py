@@ -7,7 +7,7 @@ from ._lib import KnockoffsError, PosDefException, LIB_PATH, SIGNATURES, load  #
 from .api import (Context, GaussianKnockoff, cond_factor, condition, default_context, dense_factor_from_blocks,  # noqa: F401
                   eigmin, gram, hook_dgemm, hook_potrf, hook_randn, hook_spd_inverse, make_opts,
                   modelX_gaussian_knockoffs, sample, solve_equi, solve_s)
-from . import harness  # noqa: F401
+from . import harness, dev, dist  # noqa: F401
 
 __all__ = ["Context", "GaussianKnockoff", "KnockoffsError", "PosDefException", "cond_factor", "condition", "eigmin",
            "gram", "modelX_gaussian_knockoffs", "sample", "solve_equi", "solve_s", "harness"]

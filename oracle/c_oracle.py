@@ -28,7 +28,7 @@ def lib():
         dp = C.POINTER(C.c_double)
         _LIB.ko_solve_ccd.restype = C.c_int
         _LIB.ko_solve_ccd.argtypes = [C.c_int, dp, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double,
-                                      C.c_double, C.c_double, C.c_int, dp, dp, C.POINTER(C.c_int), dp, dp, C.c_int]
+                                      C.c_double, C.c_double, C.c_int, dp, dp, C.POINTER(C.c_int), dp, dp, C.c_int, C.c_int64, dp]
     return _LIB
 
 
@@ -37,17 +37,26 @@ def _dp(a):
 
 
 def solve_ccd(Sigma, method, m=1, niter=100, tol=1e-6, lambda_min=1e-6, sdp_lambda=0.5, sdp_mu=0.8,
-              robust=False, s_init=None, max_sweeps=0):
+              robust=False, s_init=None, max_sweeps=0, max_coords=0, lapack_init=False):
     """Returns dict(s, sweeps, trace, touched_entries, n_updates, rc)."""
     Sigma = np.asfortranarray(Sigma, dtype=np.float64)
     p = Sigma.shape[0]
     s = np.zeros(p)
     trace = np.zeros(max(niter, 1))
-    stats = np.zeros(2)
+    stats = np.zeros(3)
+    U0 = None
+    if lapack_init:
+        # the reference's `cholesky(Symmetric(...))` is LAPACK dpotrf (utilities.jl:140, :237, :309)
+        import scipy.linalg as sla
+        kap = (m + 1) / m
+        A = kap * (np.triu(Sigma) + np.triu(Sigma, 1).T)
+        if method != "sdp_ccd":
+            A[np.diag_indices(p)] += lambda_min - np.asarray(s_init, dtype=np.float64)
+        U0 = np.ascontiguousarray(sla.cholesky(A, lower=False, check_finite=False))
     sw = C.c_int(0)
     si = None if s_init is None else np.ascontiguousarray(s_init, dtype=np.float64)
     rc = lib().ko_solve_ccd(METHODS[method], _dp(Sigma), p, float(m), int(niter), float(tol), float(lambda_min),
                             float(sdp_lambda), float(sdp_mu), int(robust), _dp(si), _dp(s), C.byref(sw),
-                            _dp(trace), _dp(stats), int(max_sweeps))
+                            _dp(trace), _dp(stats), int(max_sweeps), int(max_coords), _dp(U0))
     return dict(s=s, sweeps=sw.value, trace=trace[:sw.value].copy(), touched_entries=stats[0],
-                n_updates=stats[1], rc=rc)
+                n_updates=stats[1], loop_seconds=stats[2], rc=rc)

@@ -24,7 +24,9 @@
  * Return codes: 0 ok, -1 invalid argument, -2 not positive definite (PosDefException),
  * -3 Inf/NaN delta (utilities.jl:195-196).
  */
+#define _POSIX_C_SOURCE 200809L
 #include <math.h>
+#include <time.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -175,11 +177,17 @@ static inline double sym(const double *Sigma, int64_t p, int64_t i, int64_t j) {
  * s_init: required for MVR/ME (the caller evaluates solve_equi); ignored for sdp_ccd.
  * trace[niter]: per-sweep max|delta| (MVR/ME) or sum(s) (sdp_ccd); may be NULL.
  * stats[2]: [0] factor entries read+written by the rank-1 updates, [1] coordinates updated.
+ * max_sweeps_override / max_coords_override (> 0): stop after that many sweeps / coordinates -- used
+ * only by bench.py to time a BOUNDED sample of a large solve on the CPU.
+ * U_init (optional): row-major upper factor of the initial matrix computed by the caller with LAPACK
+ * dpotrf (what the reference's `cholesky` calls, utilities.jl:140); NULL = factor here.
+ * stats[3]: [2] = seconds spent in the sweep loop (excludes the initial factorisation).
  */
 int ko_solve_ccd(int method, const double *Sigma, int64_t p, double m, int niter, double tol,
                  double lambda_min, double sdp_lambda, double sdp_mu, int robust,
                  const double *s_init, double *s_out, int *sweeps_out, double *trace,
-                 double *stats, int max_sweeps_override) {
+                 double *stats, int max_sweeps_override, int64_t max_coords_override,
+                 const double *U_init) {
     if (p < 1 || m < 1.0 || niter < 0) return -1;
     if (method == 2 && (!(sdp_mu >= 0.0 && sdp_mu <= 1.0) || !(sdp_lambda > 0.0))) return -1;
     if (method != 2 && !s_init) return -1;
@@ -188,19 +196,31 @@ int ko_solve_ccd(int method, const double *Sigma, int64_t p, double m, int niter
     double *s = s_out;
     if (method == 2) memset(s, 0, sizeof(double) * (size_t)p);
     else memcpy(s, s_init, sizeof(double) * (size_t)p);
-    double *U = build_factor(Sigma, p, kappa, method == 2 ? NULL : s, method == 2 ? 0.0 : lambda_min, &rc);
-    if (!U) return rc;
+    double *U;
+    if (U_init) {
+        U = (double *)malloc(sizeof(double) * (size_t)p * (size_t)p);
+        if (!U) return -1;
+        memcpy(U, U_init, sizeof(double) * (size_t)p * (size_t)p);
+    } else {
+        U = build_factor(Sigma, p, kappa, method == 2 ? NULL : s, method == 2 ? 0.0 : lambda_min, &rc);
+        if (!U) return rc;
+    }
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     double *vd = (double *)calloc((size_t)p, sizeof(double));
     double *vn = (double *)calloc((size_t)p, sizeof(double));
     double *x = (double *)calloc((size_t)p, sizeof(double));
     double touched = 0.0, nupd = 0.0;
     double lam = sdp_lambda;
-    int sweeps = 0;
+    int sweeps = 0, stop = 0;
+    int64_t ncoord = 0;
     if (max_sweeps_override > 0 && max_sweeps_override < niter) niter = max_sweeps_override;
     for (int l = 0; l < niter && rc == 0; ++l) {
         ++sweeps;
         double max_delta = 0.0;
         for (int64_t j = 0; j < p && rc == 0; ++j) {
+            if (max_coords_override > 0 && ncoord >= max_coords_override) { stop = 1; break; }
+            ++ncoord;
             double delta;      /* signed change used for the factor: A <- A - delta e_j e_j' */
             if (method == 0) {
                 memset(vd, 0, sizeof(double) * (size_t)p);
@@ -253,7 +273,7 @@ int ko_solve_ccd(int method, const double *Sigma, int64_t p, double m, int niter
             nupd += 1.0;
             if (fabs(delta) > max_delta) max_delta = fabs(delta);
         }
-        if (rc) break;
+        if (rc || stop) break;
         if (method == 2) {
             if (trace) { double t = 0; for (int64_t i = 0; i < p; ++i) t += s[i]; trace[l] = t; }
             lam *= sdp_mu;                                      /* :339-340 */
@@ -264,7 +284,11 @@ int ko_solve_ccd(int method, const double *Sigma, int64_t p, double m, int niter
         }
     }
     if (sweeps_out) *sweeps_out = sweeps;
-    if (stats) { stats[0] = 2.0 * touched; stats[1] = nupd; }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (stats) {
+        stats[0] = 2.0 * touched; stats[1] = nupd;
+        stats[2] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    }
     free(U); free(vd); free(vn); free(x);
     return rc;
 }
