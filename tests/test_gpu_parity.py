@@ -68,7 +68,7 @@ def _sigma(kind, p):
     ("ar1", 500, "mvr", 1),          # BASELINE config 1
     ("ar1", 500, "maxent", 1), ("ar1", 300, "sdp_ccd", 1),
     ("block", 400, "mvr", 5), ("block", 400, "maxent", 5), ("block", 250, "sdp_ccd", 5),
-    ("ar1", 63, "mvr", 1), ("ar1", 64, "maxent", 2), ("ar1", 65, "sdp_ccd", 1), ("ar1", 1, "mvr", 1),
+    ("ar1", 63, "mvr", 1), ("ar1", 64, "maxent", 2), ("ar1", 65, "sdp_ccd", 1), ("ar1", 1, "maxent", 1),
     ("ar1", 2, "maxent", 1), ("block", 130, "mvr", 3),
 ])
 @pytest.mark.parametrize("refresh", [1, 0])
