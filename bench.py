@@ -259,13 +259,20 @@ def run_ours(a):
 
     def device_step(record=False):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        nvtx = torch.cuda.nvtx
         ev[0].record(ext)
+        nvtx.range_push("solve_s")
         info = dev.solve_s_dev(ctx, dSigma.data_ptr(), p, a.method, m, ds.data_ptr(), refresh_every=a.refresh_every)
+        nvtx.range_pop()
         ev[1].record(ext)
+        nvtx.range_push("cond_factor")
         dev.cond_factor_dev(ctx, dSigma.data_ptr(), p, ds.data_ptr(), True, m, dSiS.data_ptr(), dLb.data_ptr())
+        nvtx.range_pop()
         ev[2].record(ext)
+        nvtx.range_push("sample")
         dev.sample_dev(ctx, Xt.data_ptr(), n, n, p, dmu.data_ptr(), dSiS.data_ptr(), dLb.data_ptr(), m,
                        Xko_t.data_ptr(), n, seed=20260003, row_offset=row_offset)
+        nvtx.range_pop()
         ev[3].record(ext)
         if record:
             ext.synchronize()

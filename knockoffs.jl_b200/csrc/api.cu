@@ -102,6 +102,10 @@ int kb_create(kb_ctx** out, int device) {
     bool ok = cudaGetDeviceProperties(&prop, device) == cudaSuccess;
     if (ok) {
         ctx->num_sms = prop.multiProcessorCount;
+        ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+        ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        ctx->l2_size = (size_t)prop.l2CacheSize;
+        if (ctx->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
         int coop = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         ok = coop != 0;

@@ -28,11 +28,10 @@
 // skip / clip / convergence decisions without any further exchange.
 #include "kb_common.cuh"
 #include "ccd.cuh"
+#include <cstdlib>
 
 namespace kb {
 
-constexpr int CCD_THREADS = 384;
-constexpr int CCD_WARPS = CCD_THREADS / 32;
 constexpr int SLOT_ROWS = CCD_SLOT_ROWS;
 constexpr int CCD_ILP = 4;            // slots in flight per warp
 constexpr double SKIP_ABS = 1e-40;    // slot updates with |c m_k| max|m_rb| below this are dropped (banded Σ)
@@ -75,6 +74,7 @@ __host__ __device__ __forceinline__ long slot_index(int k, int rb, int nrb) {
 
 // deterministic block reduction of (sum) -- identical instruction sequence in every CTA, so every
 // CTA derives bit-identical line-search scalars from the same published column.
+template <int CCD_WARPS>
 __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -87,7 +87,9 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
     return t;
 }
 
-__global__ void __launch_bounds__(CCD_THREADS, 2) ccd_stream_kernel(const CcdParams P) {
+template <int CCD_THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const CcdParams P) {
+    constexpr int CCD_WARPS = CCD_THREADS / 32;
     extern __shared__ __align__(16) double smem[];
     __shared__ int s_abort;
     const int p = P.p;
@@ -106,6 +108,20 @@ __global__ void __launch_bounds__(CCD_THREADS, 2) ccd_stream_kernel(const CcdPar
     const bool have_slots = s_end > s_begin;
     const SlotPos first = slot_from_index(have_slots ? s_begin : 0, nrb);
     const SlotPos last = slot_from_index(have_slots ? s_end - 1 : 0, nrb);
+
+    // slot table: (element offset of the slot's first row in column k, (k << 16) | rb)
+    int2* slots = reinterpret_cast<int2*>(red + CCD_WARPS + 4);
+    const int nslots = (int)(s_end - s_begin);
+    {
+        int k = first.k, rb = first.rb;
+        // every thread walks to its own entries (one linear walk of the CTA's range, done once per launch)
+        for (int i = 0; i < nslots; ++i) {
+            if ((i % CCD_THREADS) == tid) slots[i] = make_int2((int)((long)rb * SLOT_ROWS + (long)k * ld), (k << 16) | rb);
+            if (++rb >= nrb) { ++k; rb = k / SLOT_ROWS; }
+        }
+    }
+    double* const Mlane = M + 2 * lane;
+    __syncthreads();
 
     const double m = P.m;
     const int method = P.method;
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(CCD_THREADS, 2) ccd_stream_kernel(const CcdPar
             }
             const double sj = __ldcg(cb + ld);
             const double ajj = __ldcg(cb + ld + 1);
-            ss = block_sum(ss, red, tid);          // includes the barrier that publishes col[] / rbmax[]
+            ss = block_sum<CCD_WARPS>(ss, red, tid);          // includes the barrier that publishes col[] / rbmax[]
             const double Mjj = col[j];
 
             // ---- 3. line search (every thread, identical arithmetic) ----
@@ -267,53 +283,53 @@ __global__ void __launch_bounds__(CCD_THREADS, 2) ccd_stream_kernel(const CcdPar
             buf = nbuf;
 
             // ---- 5. stream my slots:  M(i,k) += (c m_k) m_i ----
-            if (cfac != 0.0 && have_slots) {
-                int k = first.k, rb = first.rb;
-                long si = s_begin;
-                auto advance = [&](int steps) {
-                    si += steps;
-                    rb += steps;
-                    while (rb >= nrb && k < p) {
-                        const int over = rb - nrb;
-                        ++k;
-                        rb = k / SLOT_ROWS + over;
-                    }
-                };
-                advance(warp);
+            // Slots come from the CTA's shared-memory table (element offset, column, row block); each warp
+            // takes slots warp, warp+W, ... in batches of CCD_ILP.  The loads of batch b+1 are issued before
+            // the FMAs / stores of batch b (slots never alias), so 2 x CCD_ILP 512-byte requests are in
+            // flight per warp.
+            if (cfac != 0.0 && nslots > 0) {
+                double2 va[CCD_ILP], vb[CCD_ILP];
+                int2 ea[CCD_ILP], eb[CCD_ILP];
+                double cka[CCD_ILP], ckb[CCD_ILP];
                 int nact = 0;
-                while (si < s_end) {
-                    double2* ptr[CCD_ILP];
-                    double ck[CCD_ILP];
-                    int rr[CCD_ILP];
-                    bool act[CCD_ILP];
+                auto load_batch = [&](int i0, double2 (&v)[CCD_ILP], int2 (&e)[CCD_ILP], double (&ck)[CCD_ILP]) {
 #pragma unroll
                     for (int u = 0; u < CCD_ILP; ++u) {
-                        act[u] = si < s_end;
+                        const int i = i0 + u * CCD_WARPS;
                         ck[u] = 0.0;
-                        rr[u] = 0;
-                        ptr[u] = nullptr;
-                        if (act[u]) {
-                            ck[u] = cfac * col[k];
-                            act[u] = fabs(ck[u]) * rbmax[rb] >= SKIP_ABS;
-                            rr[u] = rb * SLOT_ROWS + 2 * lane;
-                            ptr[u] = reinterpret_cast<double2*>(M + (long)rr[u] + (long)k * ld);
-                            advance(CCD_WARPS);
+                        if (i < nslots) {
+                            e[u] = slots[i];
+                            const double c = cfac * col[e[u].y >> 16];
+                            if (fabs(c) * rbmax[e[u].y & 0xffff] >= SKIP_ABS) {
+                                ck[u] = c;
+                                v[u] = *reinterpret_cast<const double2*>(Mlane + e[u].x);
+                            }
                         }
                     }
-                    double2 v[CCD_ILP];
-#pragma unroll
-                    for (int u = 0; u < CCD_ILP; ++u)
-                        if (act[u]) v[u] = *ptr[u];
+                };
+                auto store_batch = [&](double2 (&v)[CCD_ILP], int2 (&e)[CCD_ILP], double (&ck)[CCD_ILP]) {
 #pragma unroll
                     for (int u = 0; u < CCD_ILP; ++u) {
-                        if (act[u]) {
-                            const double2 mv = *reinterpret_cast<const double2*>(col + rr[u]);
+                        if (ck[u] != 0.0) {
+                            const double2 mv = *reinterpret_cast<const double2*>(col + (e[u].y & 0xffff) * SLOT_ROWS + 2 * lane);
                             v[u].x = fma(ck[u], mv.x, v[u].x);
                             v[u].y = fma(ck[u], mv.y, v[u].y);
-                            *ptr[u] = v[u];
+                            *reinterpret_cast<double2*>(Mlane + e[u].x) = v[u];
                             ++nact;
                         }
                     }
+                };
+                int i0 = warp;
+                load_batch(i0, va, ea, cka);
+                while (true) {
+                    const int i1 = i0 + CCD_ILP * CCD_WARPS;
+                    if (i1 >= nslots) { store_batch(va, ea, cka); break; }
+                    load_batch(i1, vb, eb, ckb);
+                    store_batch(va, ea, cka);
+                    i0 = i1 + CCD_ILP * CCD_WARPS;
+                    if (i0 >= nslots) { store_batch(vb, eb, ckb); break; }
+                    load_batch(i0, va, ea, cka);
+                    store_batch(vb, eb, ckb);
                 }
                 if (lane == 0) touched += (double)nact;
             }
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(CCD_THREADS, 2) ccd_stream_kernel(const CcdPar
         }
     }
     // per-CTA counters
-    const double tsum = block_sum((lane == 0) ? touched : 0.0, red, tid);
+    const double tsum = block_sum<CCD_WARPS>((lane == 0) ? touched : 0.0, red, tid);
     if (tid == 0) {
         atomicAdd(P.counters + 0, tsum);
         if (blockIdx.x == 0) {
@@ -366,33 +382,80 @@ __global__ void ccd_stream_init_kernel(const CcdParams P, unsigned long long nct
 
 size_t ccd_stream_colbuf_doubles(int p) { return 3 * (size_t)(ccd_stream_ld(p) + 8); }
 
-int ccd_stream_run(kb_ctx* ctx, const CcdParams& P, int* nctas_out) {
+template <int THREADS, int MIN_CTAS>
+static int ccd_stream_launch(kb_ctx* ctx, const CcdParams& P, int* nctas_out) {
+    constexpr int WARPS = THREADS / 32;
+    auto kern = ccd_stream_kernel<THREADS, MIN_CTAS>;
     const int p = P.p;
-    if (P.ld != ccd_stream_ld(p)) return set_error(ctx, KB_ERR_INVALID, "ccd_stream_run: bad leading dimension");
     const int nrb = (int)(P.ld / SLOT_ROWS);
-    const size_t smem = (size_t)(P.ld + ((nrb + 3) & ~3) + CCD_WARPS + 4) * sizeof(double);
-    if (smem > 227 * 1024) return set_error(ctx, KB_ERR_INVALID, "p = %d too large for the streaming CCD kernel", p);
-    KB_CUDA(ctx, cudaFuncSetAttribute(ccd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    KB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccd_stream_kernel, CCD_THREADS, smem));
-    if (per_sm < 1) return set_error(ctx, KB_ERR_CUDA, "streaming CCD kernel does not fit on an SM");
-    if (per_sm > 2) per_sm = 2;
     const long total_slots = slot_index(p - 1, nrb - 1, nrb) + 1;
-    long nctas = (long)ctx->num_sms * per_sm;
-    // small problems: keep a few slot passes per warp so CTAs are not empty
-    const long min_slots_per_cta = 64;
-    if (nctas > (total_slots + min_slots_per_cta - 1) / min_slots_per_cta)
-        nctas = (total_slots + min_slots_per_cta - 1) / min_slots_per_cta;
-    if (nctas < 1) nctas = 1;
+    const size_t base_smem = (size_t)(P.ld + ((nrb + 3) & ~3) + WARPS + 4) * sizeof(double);
+    // try MIN_CTAS CTAs per SM first, then fewer; the slot table (8 B per owned slot) must fit next to the column
+    long nctas = 0;
+    size_t smem = 0;
+    for (int want = MIN_CTAS; want >= 1 && nctas == 0; --want) {
+        long g = (long)ctx->num_sms * want;
+        // small problems: keep a few slot passes per warp so CTAs are not empty
+        const long min_slots_per_cta = 64;
+        if (g > (total_slots + min_slots_per_cta - 1) / min_slots_per_cta)
+            g = (total_slots + min_slots_per_cta - 1) / min_slots_per_cta;
+        if (g < 1) g = 1;
+        const long per_cta = (total_slots + g - 1) / g + 1;
+        const size_t need = base_smem + (size_t)per_cta * sizeof(int2);
+        if (need > 227 * 1024) continue;
+        KB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        int per_sm = 0;
+        KB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, need));
+        if (per_sm >= want || g <= (long)ctx->num_sms * per_sm) { nctas = g; smem = need; }
+    }
+    if (nctas == 0) return set_error(ctx, KB_ERR_INVALID, "p = %d too large for the streaming CCD kernel", p);
     ccd_stream_init_kernel<<<8, 256, 0, ctx->stream>>>(P, (unsigned long long)nctas);
     ctx->launches++;
     KB_CUDA(ctx, cudaGetLastError());
+    // Optional: pin a fraction of the resident triangle in the 126 MB L2 (persisting access-policy window) so
+    // the cyclic streaming pass does not evict what the next coordinate re-reads.  KB_CCD_L2_PERSIST = fraction
+    // of the persisting carve-out to use (0 = off).
+    static const double l2frac = [] {
+        const char* e = getenv("KB_CCD_L2_PERSIST");
+        return e ? atof(e) : 0.0;
+    }();
+    bool window = false;
+    if (l2frac > 0.0 && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0) {
+        const size_t bytes = (size_t)P.ld * p * sizeof(double);
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = (void*)P.M;
+        attr.accessPolicyWindow.num_bytes = bytes < ctx->l2_window_max ? bytes : ctx->l2_window_max;
+        // roughly half of the window's address range is the unused upper triangle (never touched)
+        double hr = l2frac * (double)ctx->l2_persist_max / (0.5 * (double)attr.accessPolicyWindow.num_bytes);
+        attr.accessPolicyWindow.hitRatio = (float)(hr > 1.0 ? 1.0 : hr);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        window = cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+    }
     void* args[] = {(void*)&P};
-    KB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)ccd_stream_kernel, dim3((unsigned)nctas), dim3(CCD_THREADS), args,
-                                             smem, ctx->stream));
+    KB_CUDA(ctx, cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)nctas), dim3(THREADS), args, smem, ctx->stream));
     ctx->launches++;
+    if (window) {
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
     if (nctas_out) *nctas_out = (int)nctas;
     return KB_OK;
+}
+
+int ccd_stream_run(kb_ctx* ctx, const CcdParams& P, int* nctas_out) {
+    const int p = P.p;
+    if (P.ld != ccd_stream_ld(p)) return set_error(ctx, KB_ERR_INVALID, "ccd_stream_run: bad leading dimension");
+    if (p > 65535 || (long)P.ld * p > 0x7fffffffL)
+        return set_error(ctx, KB_ERR_INVALID, "p = %d too large for the streaming CCD kernel", p);
+    // launch shape: 2 CTAs x 256 threads per SM (default) or 1 CTA x 512 threads (KB_CCD_SHAPE=1x512)
+    static const int shape = [] {
+        const char* e = getenv("KB_CCD_SHAPE");
+        return (e && e[0] == '1') ? 1 : 2;
+    }();
+    if (shape == 1) return ccd_stream_launch<512, 1>(ctx, P, nctas_out);
+    return ccd_stream_launch<256, 2>(ctx, P, nctas_out);
 }
 
 }  // namespace kb

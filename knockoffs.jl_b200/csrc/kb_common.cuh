@@ -35,6 +35,9 @@ struct kb_ctx {
     size_t pinned_cap[4] = {0, 0, 0, 0};
     unsigned long long launches = 0;     // kernels launched by this library since creation
     long sample_chunk_rows = 0;          // 0 = default (4096)
+    size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
+    size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
+    size_t l2_size = 0;
     cudaEvent_t pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

@@ -136,8 +136,13 @@ int fill_zero(kb_ctx* ctx, double* A, size_t count) {
 // ------------------------------------------------------------------------------------------
 constexpr int DIAG_PITCH = POTRF_NB + 1;
 constexpr int DIAG_THREADS = 512;
+constexpr int DIAG_PANEL = 16;     // columns factored per panel step
 constexpr size_t DIAG_SMEM = (size_t)(POTRF_NB * DIAG_PITCH + POTRF_NB) * sizeof(double);
 
+// One CTA factors an nb x nb (<= 128) diagonal block held in shared memory, writes L back and then
+// inv(L) to `inv`.  Blocked right-looking inside the CTA: a 16-column panel is factored by its own
+// 128 x 16 thread strip (one thread per row, columns swept with CTA barriers), then the trailing
+// matrix gets ONE rank-16 update with 4 x 4 register tiles (no integer division in any loop).
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) {
     extern __shared__ double dsm[];
@@ -145,32 +150,71 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
     double* xv = dsm + POTRF_NB * DIAG_PITCH;
     const int tid = threadIdx.x;
 #define T_(i, k) T[(k) * DIAG_PITCH + (i)]
-    for (int e = tid; e < nb * nb; e += DIAG_THREADS) {
-        int i = e % nb, k = e / nb;
-        T_(i, k) = (i >= k) ? A[i + (long)k * ld] : 0.0;
+    {
+        const int i = tid & (POTRF_NB - 1);
+        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB)
+            T_(i, k) = (i < nb && k < nb) ? ((i >= k) ? A[i + (long)k * ld] : 0.0) : (i == k ? 1.0 : 0.0);
     }
     __syncthreads();
-    // right-looking Cholesky
-    for (int j = 0; j < nb; ++j) {
-        double d = T_(j, j);
-        if (!(d > 0.0)) {                          // also catches NaN
-            if (tid == 0) atomicCAS(fail, 0, base + j + 1);
-            d = 1.0;
+    for (int j0 = 0; j0 < nb; j0 += DIAG_PANEL) {
+        const int jb = min(DIAG_PANEL, nb - j0);
+        // ---- panel: columns j0 .. j0+jb-1, rows j0 .. nb-1; thread `tid` < 128 owns row tid ----
+        for (int j = j0; j < j0 + jb; ++j) {
+            double d = T_(j, j);
+            if (!(d > 0.0)) {                      // also catches NaN
+                if (tid == 0) atomicCAS(fail, 0, base + j + 1);
+                d = 1.0;
+            }
+            const double ljj = sqrt(d);
+            __syncthreads();
+            if (tid < nb && tid >= j) {
+                const double v = (tid == j) ? ljj : T_(tid, j) / ljj;
+                T_(tid, j) = v;
+            }
+            __syncthreads();
+            // update the remaining panel columns k = j+1 .. j0+jb-1 of rows >= k
+            if (tid < nb && tid > j) {
+                const double lij = T_(tid, j);
+                for (int k = j + 1; k < j0 + jb; ++k)
+                    if (tid >= k) T_(tid, k) -= lij * T_(k, j);
+            }
+            __syncthreads();
         }
-        const double ljj = sqrt(d);
-        __syncthreads();
-        for (int i = j + tid; i < nb; i += DIAG_THREADS) T_(i, j) = (i == j) ? ljj : T_(i, j) / ljj;
-        __syncthreads();
-        const int r = nb - j - 1;                  // trailing size
-        for (int e = tid; e < r * r; e += DIAG_THREADS) {
-            int i = j + 1 + e % r, k = j + 1 + e / r;
-            if (i >= k) T_(i, k) -= T_(i, j) * T_(k, j);
+        // ---- trailing update: T(i,k) -= sum_{c in panel} T(i,c) T(k,c) for i >= k >= j0+jb ----
+        const int t0 = j0 + jb;
+        if (t0 < nb) {
+            // 4x4 tiles over the trailing square; 32 x 32 tile grid covers 128 x 128, 512 threads -> 2 tiles each
+            for (int tile = tid; tile < 32 * 32; tile += DIAG_THREADS) {
+                const int ti = t0 + (tile & 31) * 4, tk = t0 + (tile >> 5) * 4;
+                if (ti >= nb || tk >= nb || ti + 3 < tk) continue;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+                for (int c = j0; c < t0; ++c) {
+                    double li[4], lk[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { li[a] = T_(ti + a, c); lk[a] = T_(tk + a, c); }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(li[a], lk[b], acc[a][b]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (ti + a < nb && tk + b < nb && ti + a >= tk + b) T_(ti + a, tk + b) -= acc[a][b];
+            }
         }
         __syncthreads();
     }
-    for (int e = tid; e < nb * nb; e += DIAG_THREADS) {
-        int i = e % nb, k = e / nb;
-        A[i + (long)k * ld] = T_(i, k);            // strict upper of the block becomes 0
+    {
+        const int i = tid & (POTRF_NB - 1);
+        if (i < nb)
+            for (int k = tid >> 7; k < nb; k += DIAG_THREADS / POTRF_NB)
+                A[i + (long)k * ld] = T_(i, k);    // strict upper of the block becomes 0
     }
     __syncthreads();
     // in-place inverse of lower-triangular T (dtrti2, columns from the right)
@@ -190,9 +234,10 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
         }
         __syncthreads();
     }
-    for (int e = tid; e < POTRF_NB * POTRF_NB; e += DIAG_THREADS) {
-        int i = e % POTRF_NB, k = e / POTRF_NB;
-        inv[i + (long)k * POTRF_NB] = (i < nb && k < nb) ? T_(i, k) : 0.0;
+    {
+        const int i = tid & (POTRF_NB - 1);
+        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB)
+            inv[i + (long)k * POTRF_NB] = (i < nb && k < nb && i >= k) ? T_(i, k) : 0.0;
     }
 #undef T_
 }
