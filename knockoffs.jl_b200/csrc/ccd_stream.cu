@@ -33,7 +33,6 @@
 namespace kb {
 
 constexpr int SLOT_ROWS = CCD_SLOT_ROWS;
-constexpr int CCD_ILP = 4;            // slots in flight per warp
 constexpr double SKIP_ABS = 1e-40;    // slot updates with |c m_k| max|m_rb| below this are dropped (banded Σ)
 constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;   // ~2 s: watchdog, never reached in a correct run
 
@@ -87,7 +86,7 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
     return t;
 }
 
-template <int CCD_THREADS, int MIN_CTAS>
+template <int CCD_THREADS, int MIN_CTAS, int CCD_ILP, bool DOUBLE_BUF>
 __global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const CcdParams P) {
     constexpr int CCD_WARPS = CCD_THREADS / 32;
     extern __shared__ __align__(16) double smem[];
@@ -131,6 +130,13 @@ __global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const
     int status = 0;
     int sweeps = 0;
     double touched = 0.0, nupd = 0.0;
+    long long t_wait = 0, t_stage = 0, t_pub = 0, t_stream = 0, t_mark = clock64();   // phase cycle counters (thread 0)
+#define KB_PHASE(acc)                                   \
+    do {                                                \
+        const long long _t = clock64();                 \
+        acc += _t - t_mark;                             \
+        t_mark = _t;                                    \
+    } while (0)
 
     for (int l = 0; l < P.nsweeps && status == 0; ++l) {
         ++sweeps;
@@ -155,20 +161,33 @@ __global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const
             }
             __syncthreads();
             if (s_abort) { status = KB_ERR_CUDA; break; }
+            KB_PHASE(t_wait);
             target += gridDim.x;
             const double* cb = P.colbuf + (long)buf * colstride;
             // ---- 2. stage the column, sum of squares, per-row-block max ----
             double ss = 0.0;
-            for (int rb = warp; rb < nrb; rb += CCD_WARPS) {
-                const int r = rb * SLOT_ROWS + 2 * lane;
-                const double2 v = __ldcg(reinterpret_cast<const double2*>(cb + r));
-                *reinterpret_cast<double2*>(col + r) = v;
-                ss = fma(v.x, v.x, ss);
-                ss = fma(v.y, v.y, ss);
-                double mx = fmax(fabs(v.x), fabs(v.y));
+            for (int rb0 = warp; rb0 < nrb; rb0 += 4 * CCD_WARPS) {
+                // 4 independent L2 loads in flight per lane before any of them is consumed
+                double2 v[4];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                if (lane == 0) rbmax[rb] = mx;
+                for (int u = 0; u < 4; ++u) {
+                    const int rb = rb0 + u * CCD_WARPS;
+                    v[u] = make_double2(0.0, 0.0);
+                    if (rb < nrb) v[u] = __ldcg(reinterpret_cast<const double2*>(cb + rb * SLOT_ROWS + 2 * lane));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int rb = rb0 + u * CCD_WARPS;
+                    if (rb < nrb) {
+                        *reinterpret_cast<double2*>(col + rb * SLOT_ROWS + 2 * lane) = v[u];
+                        ss = fma(v[u].x, v[u].x, ss);
+                        ss = fma(v[u].y, v[u].y, ss);
+                        double mx = fmax(fabs(v[u].x), fabs(v[u].y));
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        if (lane == 0) rbmax[rb] = mx;
+                    }
+                }
             }
             const double sj = __ldcg(cb + ld);
             const double ajj = __ldcg(cb + ld + 1);
@@ -231,6 +250,7 @@ __global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const
             }
             if (status != 0) cfac = 0.0;
 
+            KB_PHASE(t_stage);
             // ---- 4. publish column jn = j+1 (already updated) ----
             const int jn = (j + 1 == p) ? 0 : j + 1;
             const int nbuf = (buf + 1 == 3) ? 0 : buf + 1;
@@ -281,6 +301,7 @@ __global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const
                 atomicAdd(P.ready, 1ULL);
             }
             buf = nbuf;
+            KB_PHASE(t_pub);
 
             // ---- 5. stream my slots:  M(i,k) += (c m_k) m_i ----
             // Slots come from the CTA's shared-memory table (element offset, column, row block); each warp
@@ -320,19 +341,28 @@ __global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const
                     }
                 };
                 int i0 = warp;
-                load_batch(i0, va, ea, cka);
-                while (true) {
-                    const int i1 = i0 + CCD_ILP * CCD_WARPS;
-                    if (i1 >= nslots) { store_batch(va, ea, cka); break; }
-                    load_batch(i1, vb, eb, ckb);
-                    store_batch(va, ea, cka);
-                    i0 = i1 + CCD_ILP * CCD_WARPS;
-                    if (i0 >= nslots) { store_batch(vb, eb, ckb); break; }
+                if (DOUBLE_BUF) {
                     load_batch(i0, va, ea, cka);
-                    store_batch(vb, eb, ckb);
+                    while (true) {
+                        const int i1 = i0 + CCD_ILP * CCD_WARPS;
+                        if (i1 >= nslots) { store_batch(va, ea, cka); break; }
+                        load_batch(i1, vb, eb, ckb);
+                        store_batch(va, ea, cka);
+                        i0 = i1 + CCD_ILP * CCD_WARPS;
+                        if (i0 >= nslots) { store_batch(vb, eb, ckb); break; }
+                        load_batch(i0, va, ea, cka);
+                        store_batch(vb, eb, ckb);
+                    }
+                } else {
+                    for (; i0 < nslots; i0 += CCD_ILP * CCD_WARPS) {
+                        load_batch(i0, va, ea, cka);
+                        store_batch(va, ea, cka);
+                    }
                 }
                 if (lane == 0) touched += (double)nact;
             }
+            __syncwarp();
+            if (tid == 0) KB_PHASE(t_stream);
             if (status != 0) break;
         }
         if (blockIdx.x == 0 && tid == 0 && status == 0) {
@@ -350,6 +380,10 @@ __global__ void __launch_bounds__(CCD_THREADS, MIN_CTAS) ccd_stream_kernel(const
     // per-CTA counters
     const double tsum = block_sum<CCD_WARPS>((lane == 0) ? touched : 0.0, red, tid);
     if (tid == 0) {
+        atomicAdd(P.counters + 4, (double)t_wait);
+        atomicAdd(P.counters + 5, (double)t_stage);
+        atomicAdd(P.counters + 6, (double)t_pub);
+        atomicAdd(P.counters + 7, (double)t_stream);
         atomicAdd(P.counters + 0, tsum);
         if (blockIdx.x == 0) {
             P.counters[1] += nupd;
@@ -382,10 +416,10 @@ __global__ void ccd_stream_init_kernel(const CcdParams P, unsigned long long nct
 
 size_t ccd_stream_colbuf_doubles(int p) { return 3 * (size_t)(ccd_stream_ld(p) + 8); }
 
-template <int THREADS, int MIN_CTAS>
+template <int THREADS, int MIN_CTAS, int ILP, bool DB>
 static int ccd_stream_launch(kb_ctx* ctx, const CcdParams& P, int* nctas_out) {
     constexpr int WARPS = THREADS / 32;
-    auto kern = ccd_stream_kernel<THREADS, MIN_CTAS>;
+    auto kern = ccd_stream_kernel<THREADS, MIN_CTAS, ILP, DB>;
     const int p = P.p;
     const int nrb = (int)(P.ld / SLOT_ROWS);
     const long total_slots = slot_index(p - 1, nrb - 1, nrb) + 1;
@@ -449,13 +483,17 @@ int ccd_stream_run(kb_ctx* ctx, const CcdParams& P, int* nctas_out) {
     if (P.ld != ccd_stream_ld(p)) return set_error(ctx, KB_ERR_INVALID, "ccd_stream_run: bad leading dimension");
     if (p > 65535 || (long)P.ld * p > 0x7fffffffL)
         return set_error(ctx, KB_ERR_INVALID, "p = %d too large for the streaming CCD kernel", p);
-    // launch shape: 2 CTAs x 256 threads per SM (default) or 1 CTA x 512 threads (KB_CCD_SHAPE=1x512)
-    static const int shape = [] {
+    // launch shape: 2 CTAs x 384 threads per SM, 4 slots in flight per warp -- the best of the variants
+    // measured on B200 at p = 5000 (profiles/r01_ccd_variants.md); KB_CCD_SHAPE=D/F select the alternatives.
+    static const char shape = [] {
         const char* e = getenv("KB_CCD_SHAPE");
-        return (e && e[0] == '1') ? 1 : 2;
+        return e ? e[0] : 'C';
     }();
-    if (shape == 1) return ccd_stream_launch<512, 1>(ctx, P, nctas_out);
-    return ccd_stream_launch<256, 2>(ctx, P, nctas_out);
+    switch (shape) {
+        case 'D': return ccd_stream_launch<512, 2, 2, false>(ctx, P, nctas_out);
+        case 'F': return ccd_stream_launch<256, 2, 4, false>(ctx, P, nctas_out);
+        default: return ccd_stream_launch<384, 2, 4, false>(ctx, P, nctas_out);
+    }
 }
 
 }  // namespace kb

@@ -6,6 +6,7 @@
 #include "pipeline.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace kb {
@@ -221,7 +222,7 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
     KB_TRY(sc.alloc(&adiag, p));
     KB_TRY(sc.alloc(&s, p));
     KB_TRY(sc.alloc(&trace, KB_MAX_TRACE));
-    KB_TRY(sc.alloc(&counters, 4));
+    KB_TRY(sc.alloc(&counters, 8));
     KB_TRY(sc.alloc(&d_fail, 4));
     KB_TRY(sc.alloc(&d_status, 4));
     KB_TRY(sc.alloc(&d_sweeps, 4));
@@ -269,7 +270,7 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
         KB_TRY(sc.alloc(&work, (size_t)ld * p / 2 + 2 * ld + 64));
         KB_TRY(sc.alloc(&colbuf, ccd_stream_colbuf_doubles(p)));
         KB_TRY(fill_zero(ctx, trace, KB_MAX_TRACE));
-        KB_TRY(fill_zero(ctx, counters, 4));
+        KB_TRY(fill_zero(ctx, counters, 8));
         const double shift = (method == KB_METHOD_SDP_CCD) ? 0.0 : opts.lambda_min;
         const double pd = (double)p;
         const int refresh_every = opts.refresh_every < 0 ? 1 : opts.refresh_every;
@@ -326,11 +327,11 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
             KB_TRY(ccd_stream_run(ctx, P, nullptr));
             KB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
             int hsweeps = 0;
-            double hcount[4] = {0, 0, 0, 0};
+            double hcount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             double htrace[KB_MAX_TRACE];
             KB_CUDA(ctx, cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             KB_CUDA(ctx, cudaMemcpyAsync(&hsweeps, d_sweeps, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            KB_CUDA(ctx, cudaMemcpyAsync(hcount, counters, sizeof(double) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            KB_CUDA(ctx, cudaMemcpyAsync(hcount, counters, sizeof(double) * 8, cudaMemcpyDeviceToHost, ctx->stream));
             KB_CUDA(ctx, cudaMemcpyAsync(htrace, trace, sizeof(double) * KB_MAX_TRACE, cudaMemcpyDeviceToHost, ctx->stream));
             KB_CUDA(ctx, cudaMemcpyAsync(hs.data(), s, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
             KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -348,6 +349,10 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
                 for (int l = 0; l < sweeps_done && l < KB_MAX_TRACE; ++l) info->trace[l] = htrace[l];
                 info->updates = hcount[1];
                 info->touched_bytes = 16.0 * CCD_SLOT_ROWS * hcount[0];
+                if (getenv("KB_CCD_PHASES"))
+                    fprintf(stderr, "[ccd launch %d: %.2f ms; phases, Mcycles summed over CTAs so far] wait=%.1f stage=%.1f "
+                                    "publish=%.1f stream=%.1f slots=%.0f\n", sweeps_done, ms,
+                            hcount[4] / 1e6, hcount[5] / 1e6, hcount[6] / 1e6, hcount[7] / 1e6, hcount[0]);
             }
             if (status != KB_OK) break;
             if (method == KB_METHOD_SDP_CCD) {
