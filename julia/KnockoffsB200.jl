@@ -1,0 +1,86 @@
+# KnockoffsB200.jl -- the binding a Knockoffs.jl maintainer adds to route the model-X Gaussian hot path
+# to libknockoffs_b200.so.  Source only: Julia is not installed in the build image, so this file is not
+# exercised by the test-suite; the identical exported C symbols are driven from Python ctypes instead
+# (knockoffs.jl_b200/_lib.py).  Struct layouts mirror include/knockoffs_b200.h.
+module KnockoffsB200
+
+using LinearAlgebra
+import Knockoffs: GaussianKnockoff
+
+const libkb = get(ENV, "KNOCKOFFS_B200_LIB", "libknockoffs_b200.so")
+const KB_MAX_TRACE = 128
+const METHODS = Dict(:mvr => 0, :maxent => 1, :sdp_ccd => 2, :equi => 3)
+
+struct SolveOpts          # kb_solve_opts
+    niter::Int32; tol::Float64; lambda_min::Float64; sdp_lambda::Float64; sdp_mu::Float64
+    robust::Int32; verbose::Int32; mode::Int32; refresh_every::Int32
+end
+struct SolveInfo          # kb_solve_info
+    sweeps::Int32; status::Int32; mode::Int32; launches::Int32
+    trace::NTuple{KB_MAX_TRACE,Float64}
+    solve_ms::Float64; init_ms::Float64; ref_bytes::Float64; touched_bytes::Float64
+    flops::Float64; updates::Float64; objective::Float64
+end
+
+mutable struct Context
+    h::Ptr{Cvoid}
+    function Context(device::Integer=0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:kb_create, libkb), Cint, (Ptr{Ptr{Cvoid}}, Cint), r, device)
+        rc == 0 || error("kb_create failed ($rc): no usable CUDA device")
+        ctx = new(r[])
+        finalizer(c -> ccall((:kb_destroy, libkb), Cvoid, (Ptr{Cvoid},), c.h), ctx)
+    end
+end
+const CTX = Ref{Union{Nothing,Context}}(nothing)
+ctx() = (CTX[] === nothing && (CTX[] = Context()); CTX[])
+
+function check(c::Context, rc::Integer)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:kb_last_error, libkb), Cstring, (Ptr{Cvoid},), c.h))
+    rc == -2 && throw(PosDefException(0))        # cholesky / downdate failure (utilities.jl:140, :591-593)
+    error(msg)                                    # error(...) sites: modelX.jl:105, utilities.jl:28,46,195-196,301-302
+end
+
+opts(; niter::Int=100, tol=1e-6, λmin=1e-6, λ=0.5, μ=0.8, robust::Bool=false, verbose::Bool=false) =
+    SolveOpts(niter, tol, λmin, λ, μ, robust, verbose, 0, 1)
+
+"Drop-in for `solve_s(Σ::Symmetric, method; m, kwargs...)` (src/utilities.jl:27-51) for :mvr, :maxent, :sdp_ccd, :equi."
+function solve_s(Σ::Symmetric{Float64}, method::Union{Symbol,String}; m::Number=1, s_init=nothing, kwargs...)
+    c = ctx(); p = size(Σ, 1); s = Vector{Float64}(undef, p)
+    o = Ref(opts(; kwargs...)); info = Ref{SolveInfo}()
+    A = Σ.data                                   # only the upper triangle is read (Symmetric, uplo = :U)
+    si = s_init === nothing ? C_NULL : pointer(s_init)
+    GC.@preserve A s s_init begin
+        rc = ccall((:kb_solve_s, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Float64, Ptr{SolveOpts}, Ptr{Float64}, Ptr{Float64}, Ptr{SolveInfo}),
+                   c.h, A, p, METHODS[Symbol(method)], Float64(m), o, si, s, info)
+        check(c, rc)
+    end
+    if o[].verbose != 0                            # same lines the reference prints (utilities.jl:167-170)
+        for l in 1:info[].sweeps
+            println("Iter $l: δ = $(info[].trace[l])")
+        end
+    end
+    return s
+end
+
+"Drop-in for `modelX_gaussian_knockoffs(X, method, μ, Σ; m, kwargs...)` (src/modelX.jl:53-66)."
+function modelX_gaussian_knockoffs(X::Matrix{Float64}, method::Union{Symbol,String}, μ::Vector{Float64},
+                                   Σ::AbstractMatrix{Float64}; m::Number=1, seed::Integer=rand(UInt64), kwargs...)
+    c = ctx(); n, p = size(X); mi = Int(m)
+    mi < 1 && error("m should be 1 or larger but was $m.")
+    Xko = Matrix{Float64}(undef, n, mi * p); s = Vector{Float64}(undef, p)
+    Σd = Matrix{Float64}(Σ isa Symmetric ? Σ.data : Σ)
+    o = Ref(opts(; kwargs...)); info = Ref{SolveInfo}()
+    GC.@preserve X μ Σd Xko s begin
+        rc = ccall((:kb_modelx_gaussian_knockoffs, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{SolveOpts},
+                    Ptr{Float64}, Ptr{Float64}, UInt64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{SolveInfo}),
+                   c.h, X, n, p, μ, Σd, METHODS[Symbol(method)], mi, o, C_NULL, C_NULL, seed, 0, Xko, s, info)
+        check(c, rc)
+    end
+    return GaussianKnockoff(X, Xko, s, Symmetric(Σd), Symbol(method), mi)   # src/struct.jl:6-13, fields unchanged
+end
+
+end # module
