@@ -254,3 +254,43 @@ def test_gram(kb, ctx, n, p):
     assert np.max(np.abs(G - Xc.T @ Xc / n)) < 1e-10
     G2, _ = kb.gram(X, center=False, denom=n - 1, ctx=ctx)
     assert np.max(np.abs(G2 - X.T @ X / (n - 1))) < 1e-10
+
+
+# ---- multi-GPU building blocks on one device (the N>1 NCCL path is exercised by bench.py --gpus N) ----------
+def test_sharded_gram_dev_equals_single(kb, ctx):
+    import torch
+    rng = np.random.default_rng(11)
+    n, p = 3001, 96
+    X = rng.standard_normal((n, p)) + 1.5
+    G_acc = torch.zeros((p, p), dtype=torch.float64, device="cuda")
+    cs_acc = torch.zeros(p, dtype=torch.float64, device="cuda")
+    for r in range(2):
+        lo, hi = kb.dist.shard_rows(n, 2, r)
+        Xt = torch.from_numpy(np.ascontiguousarray(X[lo:hi].T)).cuda()        # (p, n_local): column-major rows
+        G = torch.empty((p, p), dtype=torch.float64, device="cuda")
+        cs = torch.empty(p, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        kb.dev.gram_partial_dev(ctx, Xt.data_ptr(), hi - lo, hi - lo, p, G.data_ptr(), cs.data_ptr())
+        G_acc += G; cs_acc += cs                                            # what the NCCL all-reduce does
+    torch.cuda.synchronize()
+    kb.dev.gram_finish_dev(ctx, G_acc.data_ptr(), cs_acc.data_ptr(), n, p, True, 0.0)
+    Xc = X - X.mean(0)
+    assert np.max(np.abs(G_acc.cpu().numpy() - Xc.T @ Xc / n)) < 1e-10
+    assert np.max(np.abs(cs_acc.cpu().numpy() - X.mean(0))) < 1e-12
+
+
+def test_row_sharded_sampling_equals_single(kb, ctx):
+    """Device RNG keyed by the GLOBAL row: two shards with row offsets reproduce the unsharded X~ bit for bit."""
+    rng = np.random.default_rng(12)
+    n, p, m = 5000, 64, 3
+    Sigma = toeplitz(p, 0.5)
+    s = c_oracle.solve_ccd(Sigma, "maxent", m=m, s_init=ko.solve_equi(Sigma, m))["s"]
+    SiS, Lb = kb.cond_factor(Sigma, s, m=m, ctx=ctx)
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    mu = np.zeros(p)
+    full = kb.sample(X, mu, SiS, Lb, m=m, Z=None, seed=77, ctx=ctx)
+    parts = []
+    for r in range(2):
+        lo, hi = kb.dist.shard_rows(n, 2, r)
+        parts.append(kb.sample(np.asfortranarray(X[lo:hi]), mu, SiS, Lb, m=m, Z=None, seed=77, row_offset=lo, ctx=ctx))
+    assert np.array_equal(np.vstack(parts), full)
