@@ -88,6 +88,8 @@ uint64_t kb_launch_count(const kb_ctx* ctx);
 /* the cudaStream_t all of ctx's kernels are launched on (for CUDA-event timing by the caller) */
 void* kb_stream(const kb_ctx* ctx);
 int kb_synchronize(kb_ctx* ctx);
+/* release the device workspace the context keeps between calls */
+int kb_trim(kb_ctx* ctx);
 /* rows per chunk of the sampling pipeline (0 = default 4096) */
 int kb_set_sample_chunk_rows(kb_ctx* ctx, int64_t rows);
 

@@ -42,6 +42,7 @@ SIGNATURES = {
     "kb_launch_count": (_u64, [_vp]),
     "kb_stream": (_vp, [_vp]),
     "kb_synchronize": (C.c_int, [_vp]),
+    "kb_trim": (C.c_int, [_vp]),
     "kb_set_sample_chunk_rows": (C.c_int, [_vp, _i64]),
     "kb_solve_s": (C.c_int, [_vp, _vp, _i64, _i32, _d, C.POINTER(SolveOpts), _vp, _vp, C.POINTER(SolveInfo)]),
     "kb_solve_s_dev": (C.c_int, [_vp, _vp, _i64, _i32, _d, C.POINTER(SolveOpts), _vp, _vp, C.POINTER(SolveInfo)]),

@@ -133,6 +133,8 @@ void kb_destroy(kb_ctx* ctx) {
     {
         DeviceGuard g(ctx->device);
         if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+        for (auto& b : ctx->pool_free) cudaFree(b.ptr);
+        ctx->pool_free.clear();
         if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
         if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -150,6 +152,15 @@ void* kb_stream(const kb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; 
 int kb_set_sample_chunk_rows(kb_ctx* ctx, int64_t rows) {
     if (!ctx || rows < 0) return KB_ERR_INVALID;
     ctx->sample_chunk_rows = rows;
+    return KB_OK;
+}
+int kb_trim(kb_ctx* ctx) {
+    if (!ctx) return bad_ctx();
+    DeviceGuard g(ctx->device);
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& b : ctx->pool_free) cudaFree(b.ptr);
+    ctx->pool_free.clear();
+    ctx->pool_bytes = 0;
     return KB_OK;
 }
 int kb_synchronize(kb_ctx* ctx) {

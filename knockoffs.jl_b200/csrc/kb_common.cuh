@@ -38,6 +38,11 @@ struct kb_ctx {
     size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
     size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
     size_t l2_size = 0;
+    // workspace pool: device buffers released by a call's Scope are kept for the next call
+    // (cudaMalloc / cudaFree synchronise the device and cost ms each at the 200 MB - 2 GB sizes used here)
+    struct PoolBlock { void* ptr; size_t bytes; };
+    std::vector<PoolBlock> pool_free;
+    size_t pool_bytes = 0;
     cudaEvent_t pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -59,25 +64,48 @@ int set_error(kb_ctx* ctx, int code, const char* fmt, ...);
         if (_rc != KB_OK) return _rc;    \
     } while (0)
 
-// scoped device allocations: freed by Scope's destructor
+// scoped device allocations: returned to ctx's workspace pool by Scope's destructor
 struct Scope {
     kb_ctx* ctx;
-    std::vector<void*> ptrs;
+    std::vector<kb_ctx::PoolBlock> blocks;
     explicit Scope(kb_ctx* c) : ctx(c) {}
     ~Scope() {
-        for (void* p : ptrs) cudaFree(p);
+        for (auto& b : blocks) ctx->pool_free.push_back(b);
     }
     template <typename T>
     int alloc(T** out, size_t count) {
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 256);
-        if (e != cudaSuccess) {
-            *out = nullptr;
-            return set_error(ctx, KB_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T),
-                             cudaGetErrorString(e));
+        const size_t want = ((count * sizeof(T) + 256 + 255) / 256) * 256;
+        // best fit among the free blocks that are not more than 25 % larger than needed
+        int best = -1;
+        for (int i = 0; i < (int)ctx->pool_free.size(); ++i) {
+            const size_t b = ctx->pool_free[i].bytes;
+            if (b >= want && b <= want + want / 4 + 4096 && (best < 0 || b < ctx->pool_free[best].bytes)) best = i;
         }
-        ptrs.push_back(p);
-        *out = reinterpret_cast<T*>(p);
+        kb_ctx::PoolBlock blk{nullptr, 0};
+        if (best >= 0) {
+            blk = ctx->pool_free[best];
+            ctx->pool_free.erase(ctx->pool_free.begin() + best);
+        } else {
+            cudaError_t e = cudaMalloc(&blk.ptr, want);
+            if (e != cudaSuccess) {
+                // release the cached blocks and retry once
+                cudaGetLastError();
+                for (auto& f : ctx->pool_free) cudaFree(f.ptr);
+                ctx->pool_bytes = 0;
+                for (auto& f : ctx->pool_free) (void)f;
+                ctx->pool_free.clear();
+                e = cudaMalloc(&blk.ptr, want);
+            }
+            if (e != cudaSuccess) {
+                *out = nullptr;
+                cudaGetLastError();
+                return set_error(ctx, KB_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            }
+            blk.bytes = want;
+            ctx->pool_bytes += want;
+        }
+        blocks.push_back(blk);
+        *out = reinterpret_cast<T*>(blk.ptr);
         return KB_OK;
     }
 };
