@@ -77,6 +77,32 @@ typedef struct {
     double objective;             /* MVR trace / ME logdet / SDP sum(s) of the returned s (on the correlation scale) */
 } kb_solve_info;
 
+/* Keyword arguments of solve_group_{max_entropy,mvr,sdp}_hybrid (group.jl:870-881, 951-962, 1057-1068). */
+typedef struct {
+    int32_t outer_iter;      /* 100 */
+    int32_t inner_pca_iter;  /* 1 */
+    int32_t inner_ccd_iter;  /* 1 */
+    double tol;              /* 1e-4: |Δobj/obj| < tol or max δ < 1e-4 ends an inner loop */
+    double eps;              /* ϵ = 1e-6 added to the feasible-interval bounds */
+    int32_t robust;          /* accepted, no effect */
+    int32_t verbose;
+} kb_group_opts;
+
+typedef struct {
+    int32_t outer_iters;              /* outer iterations executed */
+    int32_t inner_sweeps;             /* PCA + CCD sweeps executed (entries of the traces) */
+    int32_t n_directions;             /* columns of the PCA direction set V */
+    int32_t status;
+    double obj_init, obj;             /* accumulated objective as the reference tracks it (obj_new += change_obj) */
+    double gamma_equi;                /* γ of solve_group_equi used by initialize_S */
+    double trace_obj[KB_MAX_TRACE];   /* per inner sweep: what `verbose` prints (group.jl:1198-1206, ...) */
+    double trace_delta[KB_MAX_TRACE];
+    int32_t trace_kind[KB_MAX_TRACE]; /* 0 = PCA sweep, 1 = CCD sweep */
+    double steps, accepted;           /* 1-D line searches done / accepted */
+    double solve_ms;                  /* device time of the sweeps (CUDA events) */
+    double touched_bytes;             /* bytes the rank-1/2 streaming updates read + wrote */
+} kb_group_info;
+
 /* ---- context ----------------------------------------------------------------------------- */
 int kb_create(kb_ctx** ctx, int device);
 void kb_destroy(kb_ctx* ctx);
@@ -105,6 +131,26 @@ int kb_solve_s_dev(kb_ctx* ctx, const double* dSigma, int64_t p, int32_t method,
 
 /* λmin(Symmetric(Sigma)) -- the `eigvals(Σ) |> minimum` of solve_equi (utilities.jl:108). */
 int kb_eigmin(kb_ctx* ctx, const double* Sigma, int64_t p, double* lambda_min_out);
+
+/* ---- (1b) group s-solvers ------------------------------------------------------------------
+ * kb_solve_s_group replaces `solve_s_group(Σ::Symmetric, groups, method; m, kwargs...)` (group.jl:348-422)
+ * for method = KB_METHOD_MAXENT / KB_METHOD_MVR / KB_METHOD_SDP_CCD (group `:sdp` IS coordinate descent,
+ * group.jl:403-404) / KB_METHOD_EQUI.  groups: p 1-based ids in any order (sorted contiguous inside, S is
+ * returned in the caller's order).  V (p x nv, column-major, in the caller's variable order, each column
+ * supported on one group) replaces get_PCA_vectors' direction set; NULL = computed here
+ * (per-group eigenvectors, block by block, eigenvalues ascending, then the unit vectors).
+ * S_out: p x p dense (group-block-diagonal); obj_out: the accumulated objective the reference returns. */
+void kb_default_group_opts(kb_group_opts* opts);
+int kb_solve_s_group(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups, int32_t method, double m,
+                     const kb_group_opts* opts, const double* V, int64_t nv, double* S_out, double* obj_out,
+                     kb_group_info* info);
+/* `modelX_gaussian_group_knockoffs(X, method, groups, μ, Σ; m, kwargs...)` (group.jl:109-127):
+ * S = solve_s_group(...), X̃ = condition(X, μ, Σ, S; m). */
+int kb_modelx_gaussian_group_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* groups,
+                                       const double* mu, const double* Sigma, int32_t method, int32_t m,
+                                       const kb_group_opts* opts, const double* V, int64_t nv, const double* Z,
+                                       uint64_t seed, int64_t row_offset, double* Xko_out, double* S_out,
+                                       double* obj_out, kb_group_info* info);
 
 /* ---- (2) Gram / covariance ------------------------------------------------------------------
  * G = (Xc' Xc) / denom with Xc = X - colmean if center != 0.  Replaces the Gram inside

@@ -31,6 +31,19 @@ class SolveInfo(C.Structure):
                 ("updates", C.c_double), ("objective", C.c_double)]
 
 
+class GroupOpts(C.Structure):
+    _fields_ = [("outer_iter", C.c_int32), ("inner_pca_iter", C.c_int32), ("inner_ccd_iter", C.c_int32),
+                ("tol", C.c_double), ("eps", C.c_double), ("robust", C.c_int32), ("verbose", C.c_int32)]
+
+
+class GroupInfo(C.Structure):
+    _fields_ = [("outer_iters", C.c_int32), ("inner_sweeps", C.c_int32), ("n_directions", C.c_int32),
+                ("status", C.c_int32), ("obj_init", C.c_double), ("obj", C.c_double), ("gamma_equi", C.c_double),
+                ("trace_obj", C.c_double * KB_MAX_TRACE), ("trace_delta", C.c_double * KB_MAX_TRACE),
+                ("trace_kind", C.c_int32 * KB_MAX_TRACE), ("steps", C.c_double), ("accepted", C.c_double),
+                ("solve_ms", C.c_double), ("touched_bytes", C.c_double)]
+
+
 # name -> (restype, argtypes); mirrors include/knockoffs_b200.h one to one
 _vp, _i32, _i64, _u64, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
 SIGNATURES = {
@@ -47,6 +60,12 @@ SIGNATURES = {
     "kb_solve_s": (C.c_int, [_vp, _vp, _i64, _i32, _d, C.POINTER(SolveOpts), _vp, _vp, C.POINTER(SolveInfo)]),
     "kb_solve_s_dev": (C.c_int, [_vp, _vp, _i64, _i32, _d, C.POINTER(SolveOpts), _vp, _vp, C.POINTER(SolveInfo)]),
     "kb_eigmin": (C.c_int, [_vp, _vp, _i64, c_double_p]),
+    "kb_default_group_opts": (None, [C.POINTER(GroupOpts)]),
+    "kb_solve_s_group": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _d, C.POINTER(GroupOpts), _vp, _i64, _vp, c_double_p,
+                                   C.POINTER(GroupInfo)]),
+    "kb_modelx_gaussian_group_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32,
+                                                     C.POINTER(GroupOpts), _vp, _i64, _vp, _u64, _i64, _vp, _vp,
+                                                     c_double_p, C.POINTER(GroupInfo)]),
     "kb_gram": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _d, _vp, _vp]),
     "kb_gram_partial_dev": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "kb_gram_finish_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _d]),

@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import METHODS, SolveInfo, SolveOpts, check
+from ._lib import METHODS, GroupInfo, GroupOpts, SolveInfo, SolveOpts, check
 
 SINGLE_KNOCKOFFS = ["mvr", "maxent", "equi", "sdp", "sdp_ccd"]   # src/Knockoffs.jl:99
 
@@ -275,6 +275,123 @@ def modelX_gaussian_knockoffs(X, method, mu=None, Sigma=None, m=1, Z=None, seed=
         _print_trace(d)
     Ssym = np.triu(Sigma) + np.triu(Sigma, 1).T
     return GaussianKnockoff(X, Xko, s, Ssym, str(method).lstrip(":"), m, d)
+
+
+# ---- group knockoffs ---------------------------------------------------------------------------------
+GROUP_METHODS = {"mvr": 0, "maxent": 1, "sdp": 2, "equi": 3}      # group :sdp is coordinate descent (group.jl:403-404)
+
+
+def make_group_opts(outer_iter=100, inner_pca_iter=1, inner_ccd_iter=1, tol=1e-4, ϵ=None, eps=1e-6, robust=False,
+                    verbose=False, **unknown) -> GroupOpts:
+    """Keyword arguments of solve_group_{max_entropy,mvr,sdp}_hybrid (group.jl:870-881, 951-962, 1057-1068)."""
+    if unknown:
+        raise TypeError(f"unsupported keyword argument(s): {sorted(unknown)}")
+    o = GroupOpts()
+    _lib.load().kb_default_group_opts(C.byref(o))
+    o.outer_iter, o.inner_pca_iter, o.inner_ccd_iter = int(outer_iter), int(inner_pca_iter), int(inner_ccd_iter)
+    o.tol = float(tol)
+    o.eps = float(eps if ϵ is None else ϵ)
+    o.robust, o.verbose = int(bool(robust)), int(bool(verbose))
+    return o
+
+
+def _group_info_dict(info: GroupInfo, method: str) -> dict:
+    n = max(0, min(info.inner_sweeps, _lib.KB_MAX_TRACE))
+    return dict(outer_iters=info.outer_iters, inner_sweeps=info.inner_sweeps, n_directions=info.n_directions,
+                obj_init=info.obj_init, obj=info.obj, gamma_equi=info.gamma_equi,
+                trace=[("pca" if info.trace_kind[i] == 0 else "ccd", info.trace_obj[i], info.trace_delta[i])
+                       for i in range(n)],
+                steps=info.steps, accepted=info.accepted, solve_ms=info.solve_ms, touched_bytes=info.touched_bytes,
+                method=method)
+
+
+def _group_method_id(method) -> int:
+    name = str(method).lstrip(":")
+    if name not in GROUP_METHODS:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID,
+                                  f"Method must be one of {sorted(GROUP_METHODS)} (the conic-solver group methods are "
+                                  f"not on the GPU path) but was {name}")
+    return GROUP_METHODS[name]
+
+
+def _print_group_trace(d: dict):
+    print(f"{d['method']} initial obj = {d['obj_init']}")
+    for it, (kind, obj, delta) in enumerate(d["trace"], 1):
+        print(f"Iter {it} ({kind.upper()}): obj = {obj}, δ = {delta}")
+
+
+def solve_s_group(Sigma, groups, method, m=1, V=None, ctx: Optional[Context] = None, return_info=False, **kwargs):
+    """``solve_s_group(Σ::Symmetric, groups, method; m, kwargs...)`` -- src/group.jl:348-422.
+    Returns ``(S, gammas, obj)`` like the reference (``gammas`` is empty for the CCD methods).
+    ``V`` (p x nv, caller's variable order) replaces get_PCA_vectors' direction set."""
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    p = Sigma.shape[0]
+    groups = np.ascontiguousarray(groups, dtype=np.int64)
+    if groups.shape != (p,):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Length of groups should be equal to dimension of Σ")
+    mid = _group_method_id(method)
+    opts = make_group_opts(**kwargs)
+    info = GroupInfo()
+    Vf = None if V is None else _f(V)
+    nv = 0 if Vf is None else Vf.shape[1]
+    S = np.empty((p, p), order="F")
+    obj = C.c_double()
+    rc = ctx._lib.kb_solve_s_group(ctx.h, _ptr(Sigma), p, _ptr(groups), mid, float(m), C.byref(opts), _ptr(Vf), nv,
+                                   _ptr(S), C.byref(obj), C.byref(info))
+    check(ctx.h, rc)
+    d = _group_info_dict(info, str(method).lstrip(":"))
+    if opts.verbose:
+        _print_group_trace(d)
+    gam = np.array([info.gamma_equi]) if str(method).lstrip(":") == "equi" else np.zeros(0)
+    out = (S, gam, obj.value)
+    return out + (d,) if return_info else out
+
+
+@dataclass
+class GaussianGroupKnockoff:
+    """src/struct.jl:24-34."""
+    X: np.ndarray
+    Xko: np.ndarray
+    groups: np.ndarray
+    S: np.ndarray
+    gammas: np.ndarray
+    m: int
+    Sigma: np.ndarray
+    method: str
+    obj: float
+    info: dict = field(default_factory=dict)
+
+
+def modelX_gaussian_group_knockoffs(X, method, groups, mu, Sigma, m=1, V=None, Z=None, seed=0,
+                                    ctx: Optional[Context] = None, **kwargs) -> GaussianGroupKnockoff:
+    """``modelX_gaussian_group_knockoffs(X, method, groups, μ, Σ; m, kwargs...)`` -- src/group.jl:109-127."""
+    ctx = ctx or default_context()
+    X = _f(X)
+    n, p = X.shape
+    groups = np.ascontiguousarray(groups, dtype=np.int64)
+    if groups.shape != (p,):                                         # group.jl:119-120
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Length of groups should be equal to number of variables")
+    m = int(m)
+    Sigma = _f(Sigma)
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    mid = _group_method_id(method)
+    opts = make_group_opts(**kwargs)
+    info = GroupInfo()
+    Vf = None if V is None else _f(V)
+    Zf = None if Z is None else _f(Z)
+    if Zf is not None and Zf.shape != (n, m * p):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
+    Xko = np.empty((n, m * p), order="F")
+    S = np.empty((p, p), order="F")
+    obj = C.c_double()
+    rc = ctx._lib.kb_modelx_gaussian_group_knockoffs(
+        ctx.h, _ptr(X), n, p, _ptr(groups), _ptr(mu), _ptr(Sigma), mid, m, C.byref(opts), _ptr(Vf),
+        0 if Vf is None else Vf.shape[1], _ptr(Zf), int(seed), 0, _ptr(Xko), _ptr(S), C.byref(obj), C.byref(info))
+    check(ctx.h, rc)
+    d = _group_info_dict(info, str(method).lstrip(":"))
+    Ssym = np.triu(Sigma) + np.triu(Sigma, 1).T
+    return GaussianGroupKnockoff(X, Xko, groups, S, np.zeros(0), m, Ssym, str(method).lstrip(":"), obj.value, d)
 
 
 # ---- hooks used by tests ---------------------------------------------------------------------------

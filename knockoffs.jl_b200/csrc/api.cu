@@ -3,6 +3,7 @@
 #include "kb_common.cuh"
 #include "linalg.cuh"
 #include "pipeline.cuh"
+#include "group.cuh"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -210,6 +211,48 @@ int kb_eigmin(kb_ctx* ctx, const double* Sigma, int64_t p, double* lambda_min_ou
     KB_TRY(sc.alloc(&dS, (size_t)p * p));
     KB_CUDA(ctx, cudaMemcpyAsync(dS, Sigma, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
     return eigmin_dev(ctx, dS, (long)p, (int)p, lambda_min_out);
+}
+
+// ---- (1b) group s-solvers ---------------------------------------------------------------------------
+void kb_default_group_opts(kb_group_opts* o) { if (o) default_group_opts(o); }
+
+int kb_solve_s_group(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups, int32_t method, double m,
+                     const kb_group_opts* opts, const double* V, int64_t nv, double* S_out, double* obj_out,
+                     kb_group_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !groups || !S_out || p < 1 || p > 46000 || nv < 0 || nv > 0x3fffffff)
+        return set_error(ctx, KB_ERR_INVALID, "solve_s_group: bad arguments");
+    DeviceGuard g(ctx->device);
+    return solve_s_group_host(ctx, Sigma, (int)p, groups, method, m, opts, V, (int)nv, S_out, obj_out, info);
+}
+
+int kb_modelx_gaussian_group_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* groups,
+                                       const double* mu, const double* Sigma, int32_t method, int32_t m,
+                                       const kb_group_opts* opts, const double* V, int64_t nv, const double* Z,
+                                       uint64_t seed, int64_t row_offset, double* Xko_out, double* S_out,
+                                       double* obj_out, kb_group_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!X || !mu || !Sigma || !groups || !Xko_out || !S_out || p < 1 || n < 0)
+        return set_error(ctx, KB_ERR_INVALID, "modelX group: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    // (S, γs, obj) = solve_s_group(Symmetric(Σ), groups, method; m, kwargs...)      (group.jl:123)
+    KB_TRY(solve_s_group_host(ctx, Sigma, (int)p, groups, method, (double)m, opts, V, (int)nv, S_out, obj_out, info));
+    // X̃ = condition(X, μ, Σ, S; m)                                                  (group.jl:125)
+    Scope sc(ctx);
+    const size_t pp = (size_t)p * p;
+    const size_t nblk = (size_t)(2 * m - 1);
+    double *dSig, *dS, *dmu, *dSiS, *dLb;
+    KB_TRY(sc.alloc(&dSig, pp));
+    KB_TRY(sc.alloc(&dS, pp));
+    KB_TRY(sc.alloc(&dmu, p));
+    KB_TRY(sc.alloc(&dSiS, pp));
+    KB_TRY(sc.alloc(&dLb, pp * nblk));
+    KB_CUDA(ctx, cudaMemcpyAsync(dSig, Sigma, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dS, S_out, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dmu, mu, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(cond_factor_dev(ctx, dSig, (long)p, (int)p, dS, (long)p, 0, m, dSiS, dLb, (long)p));
+    return sample_host_pipeline(ctx, X, (long)n, (int)p, dmu, dSiS, dLb, (long)p, m, Z, seed, row_offset, Xko_out);
 }
 
 // ---- (2) Gram -------------------------------------------------------------------------------------

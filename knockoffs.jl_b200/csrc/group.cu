@@ -1,0 +1,920 @@
+// Group knockoff solvers (solve_s_group -> solve_group_{max_entropy,mvr,sdp}_hybrid) on the device.
+//
+// Reference (biona001/Knockoffs.jl v2.0.2, src/group.jl): solve_s_group :348-422, initialize_S :432-443,
+// solve_group_equi :479-495, hybrids :870-1106, _X_ccd_iter! :1108-1458, _X_pca_ccd_iter! :1460-1673,
+// objectives :1675-1727, rank1/rank2_cholesky_update! :1729-1768, get_PCA_vectors :2161-2187.
+//
+// Device formulation (same idea as the single-knockoff kernel, ccd_stream.cu).  The reference keeps two
+// Cholesky factors, L of D = κΣ − S and C of S, and per step does 2-12 triangular solves plus 2-4 Givens
+// rank-1 updates.  Every scalar those solves produce is a quadratic form in D⁻¹ or S⁻¹:
+//     ‖L⁻¹v‖² = vᵀD⁻¹v,  ‖D⁻¹v‖² (forward_backward!),  ‖C⁻¹v‖² = vᵀS⁻¹v,  ‖S⁻¹v‖²,  and the (i,j) cross terms.
+// S is group-block-diagonal, so S⁻¹ is too: it lives as g x g blocks and costs O(g²) per step.
+// MD = D⁻¹ (dense, symmetric, fully stored) stays resident in HBM; a step that changes S by δ vvᵀ
+// (PCA direction or diagonal entry) is the Sherman–Morrison update MD += δ/(1−δ vᵀMDv) (MDv)(MDv)ᵀ, and an
+// off-diagonal step S_ij, S_ji += δ is ONE rank-2 Woodbury update (the reference needs 2 rank-1 updates of
+// each factor, :1743-1768).  Per step: `group_step_kernel` (one CTA: gathers MD·v from the group's columns,
+// reduces the scalars with warp shuffles, runs the line search -- closed form, quadratic roots or Brent --
+// on the device, updates the g x g blocks and writes the update coefficients) followed by
+// `group_apply_kernel` (streams the rank-1/2 update over MD; exits at once if the step was rejected).
+// The host only sequences launches and reads (obj, max δ, converged) once per inner sweep, exactly where
+// the reference tests convergence (:1207-1212, :1335-1340, :1450-1455, :1515-1520).
+#include "kb_common.cuh"
+#include "linalg.cuh"
+#include "pipeline.cuh"
+#include "group.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+namespace kb {
+
+// ------------------------------------------------------------------------------------------------
+// small dense host routines for the g x g group blocks (setup only: O(p g²) work)
+// ------------------------------------------------------------------------------------------------
+// cyclic Jacobi: A (n x n, column-major, symmetric) -> eigenvalues w (ascending), eigenvectors in V (columns)
+static void jacobi_eigh(int n, std::vector<double>& A, std::vector<double>& w, std::vector<double>& V) {
+    V.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) V[i + (size_t)i * n] = 1.0;
+    auto a = [&](int i, int j) -> double& { return A[i + (size_t)j * n]; };
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i) (i == j ? diag : off) += a(i, j) * a(i, j);
+        if (off <= 1e-32 * (diag + 1e-300)) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a(p, q);
+                if (apq == 0.0) continue;
+                const double theta = (a(q, q) - a(p, p)) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = a(k, p), akq = a(k, q);
+                    a(k, p) = c * akp - s * akq;
+                    a(k, q) = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = a(p, k), aqk = a(q, k);
+                    a(p, k) = c * apk - s * aqk;
+                    a(q, k) = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = V[k + (size_t)p * n], vkq = V[k + (size_t)q * n];
+                    V[k + (size_t)p * n] = c * vkp - s * vkq;
+                    V[k + (size_t)q * n] = s * vkp + c * vkq;
+                }
+            }
+    }
+    w.resize(n);
+    std::vector<int> ord(n);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::sort(ord.begin(), ord.end(), [&](int x, int y) { return a(x, x) < a(y, y); });
+    std::vector<double> V2((size_t)n * n);
+    for (int k = 0; k < n; ++k) {
+        w[k] = a(ord[k], ord[k]);
+        for (int i = 0; i < n; ++i) V2[i + (size_t)k * n] = V[i + (size_t)ord[k] * n];
+    }
+    V.swap(V2);
+}
+// f(A) = V diag(f(w)) V'
+template <typename F>
+static void sym_function(int n, const std::vector<double>& w, const std::vector<double>& V, F f, double* out, int ldo) {
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i < n; ++i) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc += V[i + (size_t)k * n] * f(w[k]) * V[j + (size_t)k * n];
+            out[i + (size_t)j * ldo] = acc;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------------
+constexpr int GSTEP_THREADS = 512;
+constexpr int GSTEP_WARPS = GSTEP_THREADS / 32;
+
+// state[] layout
+enum : int { ST_OBJ = 0, ST_OBJ_NEW = 1, ST_MAXD = 2, ST_CONV = 3, ST_ACCEPTED = 4, ST_STEPS = 5, ST_LAST = 8 };
+
+struct GroupDev {
+    int p, ng, gmax, nv, method;
+    long ld;
+    double m, eps, tol;
+    double* MD;             // D^{-1}, p x p, fully stored
+    const int* goff;        // ng + 1 group offsets (contiguous groups)
+    double* Sblk;           // ng blocks, stride gmax*gmax, ld gmax: S_GG
+    double* MSblk;          // S_GG^{-1}
+    const double* SigBlk;   // Σ_GG (correlation scale)
+    const int* vgrp;        // nv: group of PCA direction
+    const double* vvec;     // nv x gmax: entries of the direction inside its group
+    double* W;              // 2 x ld: MD v (and MD e_j for off-diagonal steps)
+    double* coef;           // [0..2] = q11, q12, q22 of the pending MD update
+    double* state;
+    double* gobj;           // ng: per-group SDP objective (group.jl:976-983)
+};
+
+template <typename F>
+__device__ void brent_min(F f, double x_lower, double x_upper, double& xmin, double& fmin) {
+    // Optim.jl Brent(), abs_tol = 1e-4, rel_tol = sqrt(eps), 1000 iterations (group.jl:1303-1309, 1419-1422, 1624-1627)
+    const double abs_tol = 1e-4, rel_tol = 1.4901161193847656e-08;
+    const double golden = 0.5 * (3.0 - sqrt(5.0));
+    double x = x_lower + golden * (x_upper - x_lower);
+    double fx = f(x);
+    double step = 0.0, old_step = 0.0;
+    double x1 = x, x2 = x, f1 = fx, f2 = fx;
+    for (int it = 0; it < 1000;) {
+        double p = 0.0, q = 0.0;
+        const double x_tol = rel_tol * fabs(x) + abs_tol;
+        const double mid = (x_upper + x_lower) / 2;
+        if (fabs(x - mid) <= 2 * x_tol - (x_upper - x_lower) / 2) break;
+        ++it;
+        if (fabs(old_step) > x_tol) {
+            const double r = (x - x1) * (fx - f2);
+            q = (x - x2) * (fx - f1);
+            p = (x - x2) * q - (x - x1) * r;
+            q = 2 * (q - r);
+            if (q > 0) p = -p; else q = -q;
+        }
+        if (fabs(p) < fabs(q * old_step / 2) && p < q * (x_upper - x) && p < q * (x - x_lower)) {
+            old_step = step;
+            step = p / q;
+            const double xt = x + step;
+            if ((xt - x_lower) < 2 * x_tol || (x_upper - xt) < 2 * x_tol) step = (x < mid) ? x_tol : -x_tol;
+        } else {
+            old_step = (x < mid) ? (x_upper - x) : (x_lower - x);
+            step = golden * old_step;
+        }
+        const double xn = (fabs(step) >= x_tol) ? x + step : x + ((step > 0) ? x_tol : -x_tol);
+        const double fn = f(xn);
+        if (fn < fx) {
+            if (xn < x) x_upper = x; else x_lower = x;
+            x2 = x1; f2 = f1; x1 = x; f1 = fx; x = xn; fx = fn;
+        } else {
+            if (xn < x) x_lower = xn; else x_upper = xn;
+            if (fn <= f1 || x1 == x) { x2 = x1; f2 = f1; x1 = xn; f1 = fn; }
+            else if (fn <= f2 || x2 == x || x2 == x1) { x2 = xn; f2 = fn; }
+        }
+    }
+    xmin = x;
+    fmin = fx;
+}
+
+__device__ __forceinline__ bool bad_delta(double d) { return fabs(d) < 1e-15 || isnan(d) || isinf(d); }
+__device__ __forceinline__ double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// diag_mvr_obj_root, group.jl:1708-1716
+__device__ __forceinline__ void diag_mvr_roots(double m, double ajj, double bjj, double cjj, double djj, double& x1, double& x2) {
+    const double a = -ajj * ajj * m * m * cjj + bjj * bjj * djj;
+    const double b = 2 * ajj * m * m * cjj + 2 * bjj * djj;
+    const double c = djj - m * m * cjj;
+    if (a == 0.0 && c == 0.0) { x1 = 0.0; x2 = 0.0; return; }
+    const double disc = sqrt(b * b - 4 * a * c);
+    x1 = (-b + disc) / (2 * a);
+    x2 = (-b - disc) / (2 * a);
+}
+
+// step types
+enum : int { STEP_PCA = 0, STEP_DIAG = 1, STEP_OFFDIAG = 2 };
+
+__global__ void __launch_bounds__(GSTEP_THREADS, 1)
+group_step_kernel(const GroupDev G, const int type, const int g, const int ia, const int ib) {
+    extern __shared__ double gsm[];
+    const int gmax = G.gmax;
+    double* sh_v = gsm;                  // direction inside the group (PCA)
+    double* sh_u1 = gsm + gmax;          // S^{-1} v   (or column i of the block)
+    double* sh_u2 = gsm + 2 * gmax;      // column j of the block (off-diagonal)
+    double* red = gsm + 3 * gmax;        // 3 x GSTEP_WARPS
+    __shared__ double sh_dec[8];         // decision broadcast: [0] accept, [1] delta, [2..4] t11,t12,t22 for MS
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = G.p;
+    const long ld = G.ld;
+    const int o = G.goff[g], gs = G.goff[g + 1] - o;
+    double* w1 = G.W;
+    double* w2 = G.W + ld;
+    const double* __restrict__ MD = G.MD;
+    double* MS = G.MSblk + (size_t)g * gmax * gmax;
+    double* Sb = G.Sblk + (size_t)g * gmax * gmax;
+    const double* Sg = G.SigBlk + (size_t)g * gmax * gmax;
+
+    if (type == STEP_PCA) {
+        for (int k = tid; k < gs; k += GSTEP_THREADS) sh_v[k] = G.vvec[(size_t)ia * gmax + k];
+        __syncthreads();
+    }
+    // ---- MD v (columns of the group are contiguous) and the column-norm scalars ----
+    double s11 = 0.0, s12 = 0.0, s22 = 0.0;
+    for (int r = tid; r < p; r += GSTEP_THREADS) {
+        double x1, x2 = 0.0;
+        if (type == STEP_PCA) {
+            x1 = 0.0;
+            for (int k = 0; k < gs; ++k) x1 = fma(sh_v[k], MD[r + (long)(o + k) * ld], x1);
+        } else if (type == STEP_DIAG) {
+            x1 = MD[r + (long)(o + ia) * ld];
+        } else {
+            x1 = MD[r + (long)(o + ia) * ld];
+            x2 = MD[r + (long)(o + ib) * ld];
+        }
+        w1[r] = x1;
+        if (type == STEP_OFFDIAG) w2[r] = x2;
+        s11 = fma(x1, x1, s11);
+        s12 = fma(x1, x2, s12);
+        s22 = fma(x2, x2, s22);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s11 += __shfl_xor_sync(0xffffffffu, s11, off);
+        s12 += __shfl_xor_sync(0xffffffffu, s12, off);
+        s22 += __shfl_xor_sync(0xffffffffu, s22, off);
+    }
+    if (lane == 0) { red[warp] = s11; red[GSTEP_WARPS + warp] = s12; red[2 * GSTEP_WARPS + warp] = s22; }
+    // ---- S^{-1} side: u = MS v or the block's columns ----
+    if (type == STEP_PCA) {
+        for (int k = tid; k < gs; k += GSTEP_THREADS) {
+            double acc = 0.0;
+            for (int l = 0; l < gs; ++l) acc = fma(MS[k + (size_t)l * gmax], sh_v[l], acc);
+            sh_u1[k] = acc;
+        }
+    } else {
+        for (int k = tid; k < gs; k += GSTEP_THREADS) {
+            sh_u1[k] = MS[k + (size_t)ia * gmax];
+            if (type == STEP_OFFDIAG) sh_u2[k] = MS[k + (size_t)ib * gmax];
+        }
+    }
+    __syncthreads();
+
+    // ---- line search (thread 0) ----
+    if (tid == 0) {
+        double d11 = 0.0, d12 = 0.0, d22 = 0.0;
+        for (int w = 0; w < GSTEP_WARPS; ++w) { d11 += red[w]; d12 += red[GSTEP_WARPS + w]; d22 += red[2 * GSTEP_WARPS + w]; }
+        const double m = G.m, eps = G.eps;
+        const int method = G.method;
+        double delta = 0.0, change = 0.0;
+        bool accept = false;
+        double q11 = 0.0, q12 = 0.0, q22 = 0.0, t11 = 0.0, t12 = 0.0, t22 = 0.0;
+        if (type != STEP_OFFDIAG) {
+            // a = v'D^{-1}v, b = v'S^{-1}v, c = |S^{-1}v|^2, d = |D^{-1}v|^2
+            double a = 0.0, b = 0.0, c = 0.0;
+            if (type == STEP_PCA) {
+                for (int k = 0; k < gs; ++k) {
+                    a = fma(sh_v[k], w1[o + k], a);
+                    b = fma(sh_v[k], sh_u1[k], b);
+                    c = fma(sh_u1[k], sh_u1[k], c);
+                }
+            } else {
+                a = w1[o + ia];
+                b = sh_u1[ia];
+                for (int k = 0; k < gs; ++k) c = fma(sh_u1[k], sh_u1[k], c);
+            }
+            const double d = d11;
+            const double lb = -1.0 / b + eps, ub = 1.0 / a - eps;
+            if (!(lb >= ub)) {
+                if (method == KB_METHOD_MAXENT) {
+                    // group.jl:1391-1404 / :1483-1490
+                    delta = clampd((m * b - a) / ((m + 1) * a * b), lb, ub);
+                    change = log(1.0 - delta * a) + m * log(1.0 + delta * b);
+                    accept = !(change < 0.0 || bad_delta(delta));
+                } else if (method == KB_METHOD_MVR) {
+                    // group.jl:1253-1259 / :1555-1563
+                    double x1, x2;
+                    diag_mvr_roots(m, a, b, c, d, x1, x2);
+                    delta = (lb < x1 && x1 < ub) ? x1 : ((lb < x2 && x2 < ub) ? x2 : NAN);
+                    change = -m * m * delta * c / (1.0 + delta * b) + delta * d / (1.0 - delta * a);
+                    accept = !(change > 0.0 || bad_delta(delta));
+                } else if (type == STEP_DIAG) {
+                    // SDP diagonal, group.jl:1136-1141
+                    const double gap = Sg[ia + (size_t)ia * gmax] - Sb[ia + (size_t)ia * gmax];
+                    delta = clampd(gap, lb, ub);
+                    change = (fabs(gap - delta) - fabs(gap)) / ((double)gs * gs);
+                    accept = !(bad_delta(delta) || change > 0.01);
+                } else {
+                    // SDP PCA direction: Brent on the group's block objective, group.jl:1619-1634
+                    auto f = [&](double t) {
+                        double acc = 0.0;
+                        for (int j = 0; j < gs; ++j)
+                            for (int i = 0; i < gs; ++i)
+                                acc += fabs(Sg[i + (size_t)j * gmax] - Sb[i + (size_t)j * gmax] - t * sh_v[i] * sh_v[j]);
+                        return acc / ((double)gs * gs);
+                    };
+                    double xm, fm;
+                    brent_min(f, lb, ub, xm, fm);
+                    delta = clampd(xm, lb, ub);
+                    change = fm - G.gobj[g];
+                    accept = !(bad_delta(delta) || change > 0.01);
+                    if (accept) G.gobj[g] = fm;
+                }
+            }
+            if (accept) {
+                q11 = delta / (1.0 - delta * a);          // D -> D - δ vv'
+                t11 = delta / (1.0 + delta * b);          // S -> S + δ vv'
+            }
+        } else {
+            // off-diagonal (i, j) = (ia, ib): group.jl:1151-1193, 1267-1322, 1392-1436
+            const double aii = w1[o + ia], aij = w1[o + ib], ajj = w2[o + ib];
+            const double bii = sh_u1[ia], bij = sh_u1[ib], bjj = sh_u2[ib];
+            double cii = 0.0, cij = 0.0, cjj = 0.0;
+            for (int k = 0; k < gs; ++k) {
+                cii = fma(sh_u1[k], sh_u1[k], cii);
+                cij = fma(sh_u1[k], sh_u2[k], cij);
+                cjj = fma(sh_u2[k], sh_u2[k], cjj);
+            }
+            const double dii = d11, dij = d12, djj = d22;
+            double s1 = (aij - sqrt(aii * ajj)) / (aij * aij - aii * ajj);
+            double s2 = (aij + sqrt(aii * ajj)) / (aij * aij - aii * ajj);
+            double e1 = (-bij - sqrt(bii * bjj)) / (bij * bij - bii * bjj);
+            double e2 = (-bij + sqrt(bii * bjj)) / (bij * bij - bii * bjj);
+            if (s1 > s2) { const double t = s1; s1 = s2; s2 = t; }
+            if (e1 > e2) { const double t = e1; e1 = e2; e2 = t; }
+            double lb, ub;
+            if (method == KB_METHOD_SDP_CCD) {          // ε outside max/min (quirk Q4), group.jl:1176-1177
+                lb = fmax(fmax(s1, e1), -2.0 / (bii + 2 * bij + bjj)) + eps;
+                ub = fmin(fmin(s2, e2), 2.0 / (aii + 2 * aij + ajj)) - eps;
+            } else {                                    // group.jl:1299-1300, 1415-1416
+                lb = fmax(fmax(s1, e1), -2.0 / (bii + 2 * bij + bjj) + eps);
+                ub = fmin(fmin(s2, e2), 2.0 / (aii + 2 * aij + ajj) - eps);
+            }
+            if (!(lb >= ub)) {
+                if (method == KB_METHOD_SDP_CCD) {
+                    const double gap = Sg[ia + (size_t)ib * gmax] - Sb[ia + (size_t)ib * gmax];
+                    delta = clampd(gap, lb, ub);
+                    change = (2 * fabs(gap - delta) - 2 * fabs(gap)) / ((double)gs * gs);
+                    accept = !(bad_delta(delta) || change > 0.01);
+                } else if (method == KB_METHOD_MAXENT) {
+                    auto f = [&](double t) {              // offdiag_maxent_obj, group.jl:1695-1700 (quirk Q5)
+                        const double in1 = (1 - t * aij) * (1 - t * aij) - t * t * aii * ajj;
+                        const double in2 = (1 + t * bij) * (1 + t * bij) - t * t * bjj * bii;
+                        if (in1 <= 0.0) return (double)NAN;
+                        if (in2 <= 0.0) return -(double)INFINITY;
+                        return -log(in1) - m * log(in2);
+                    };
+                    double xm, fm;
+                    brent_min(f, lb, ub, xm, fm);
+                    delta = clampd(xm, lb, ub);
+                    change = -fm;
+                    accept = !(change < 0.0 || bad_delta(delta));
+                } else {
+                    auto f = [&](double t) {              // offdiag_mvr_obj, group.jl:1701-1707
+                        const double denom1 = (1 + t * bij) * (1 + t * bij) - t * t * bii * bjj;
+                        const double denom2 = (1 - t * aij) * (1 - t * aij) - t * t * aii * ajj;
+                        const double numer1 = -m * m * t * ((cij * bij - cjj * bii - cii * bjj + cij * bij) * t + 2 * cij);
+                        const double numer2 = t * ((-dij * aij + djj * aii + dii * ajj - dij * aij) * t + 2 * dij);
+                        return numer1 / denom1 + numer2 / denom2;
+                    };
+                    double xm, fm;
+                    brent_min(f, lb, ub, xm, fm);
+                    delta = clampd(xm, lb, ub);
+                    change = fm;
+                    accept = !(change > 0.0 || bad_delta(delta));
+                }
+            }
+            if (accept) {
+                // D -> D − U K U',  U = [e_i e_j], K = δ [[0,1],[1,0]]:  MD += [w_i w_j] (K^{-1} − A2)^{-1} [w_i w_j]'
+                const double k = 1.0 / delta;
+                {   // Q = inv([[-aii, k - aij], [k - aij, -ajj]])
+                    const double m11 = -aii, m12 = k - aij, m22 = -ajj;
+                    const double det = m11 * m22 - m12 * m12;
+                    q11 = m22 / det; q12 = -m12 / det; q22 = m11 / det;
+                }
+                {   // S -> S + U K U':  MS −= [u_i u_j] (K^{-1} + B2)^{-1} [u_i u_j]'
+                    const double m11 = bii, m12 = k + bij, m22 = bjj;
+                    const double det = m11 * m22 - m12 * m12;
+                    t11 = m22 / det; t12 = -m12 / det; t22 = m11 / det;
+                }
+            }
+        }
+        if (accept) {
+            G.state[ST_OBJ_NEW] += change;
+            if (fabs(delta) > G.state[ST_MAXD]) G.state[ST_MAXD] = fabs(delta);
+            G.state[ST_ACCEPTED] += 1.0;
+        }
+        G.state[ST_STEPS] += 1.0;
+        G.coef[0] = q11; G.coef[1] = q12; G.coef[2] = q22;
+        sh_dec[0] = accept ? 1.0 : 0.0;
+        sh_dec[1] = delta;
+        sh_dec[2] = t11; sh_dec[3] = t12; sh_dec[4] = t22;
+    }
+    __syncthreads();
+    if (sh_dec[0] == 0.0) return;
+    // ---- accepted: update the g x g blocks S_GG and S_GG^{-1} ----
+    const double delta = sh_dec[1], t11 = sh_dec[2], t12 = sh_dec[3], t22 = sh_dec[4];
+    for (int e = tid; e < gs * gs; e += GSTEP_THREADS) {
+        const int k = e % gs, l = e / gs;
+        double ms = MS[k + (size_t)l * gmax];
+        if (type == STEP_OFFDIAG) {
+            ms -= t11 * sh_u1[k] * sh_u1[l] + t12 * (sh_u1[k] * sh_u2[l] + sh_u2[k] * sh_u1[l]) + t22 * sh_u2[k] * sh_u2[l];
+        } else {
+            ms -= t11 * sh_u1[k] * sh_u1[l];
+        }
+        MS[k + (size_t)l * gmax] = ms;
+        double add = 0.0;
+        if (type == STEP_PCA) add = delta * sh_v[k] * sh_v[l];
+        else if (type == STEP_DIAG) add = (k == ia && l == ia) ? delta : 0.0;
+        else add = ((k == ia && l == ib) || (k == ib && l == ia)) ? delta : 0.0;
+        if (add != 0.0) Sb[k + (size_t)l * gmax] += add;
+    }
+}
+
+// MD(r,c) += q11 w1_r w1_c + q12 (w1_r w2_c + w2_r w1_c) + q22 w2_r w2_c over the full matrix
+constexpr int GAPPLY_COLS = 8;
+__global__ void __launch_bounds__(256) group_apply_kernel(const GroupDev G) {
+    const double q11 = G.coef[0], q12 = G.coef[1], q22 = G.coef[2];
+    if (q11 == 0.0 && q12 == 0.0 && q22 == 0.0) return;      // step rejected
+    const int p = G.p;
+    const long ld = G.ld;
+    const double* w1 = G.W;
+    const double* w2 = G.W + ld;
+    const int r = (blockIdx.x * 256 + threadIdx.x) * 2;
+    if (r >= p) return;
+    const bool two = r + 1 < p;
+    const double a0 = w1[r], a1 = two ? w1[r + 1] : 0.0;
+    const double b0 = w2[r], b1 = two ? w2[r + 1] : 0.0;
+    const bool rank2 = (q12 != 0.0 || q22 != 0.0);
+    const int c0 = blockIdx.y * GAPPLY_COLS;
+#pragma unroll
+    for (int cc = 0; cc < GAPPLY_COLS; ++cc) {
+        const int c = c0 + cc;
+        if (c >= p) break;
+        const double wc1 = w1[c];
+        double f1 = q11 * wc1, f2 = 0.0;           // coefficient of w1_r and of w2_r
+        if (rank2) {
+            const double wc2 = w2[c];
+            f1 = fma(q12, wc2, f1);
+            f2 = fma(q12, wc1, q22 * wc2);
+        }
+        double* ptr = G.MD + r + (long)c * ld;
+        if (two) {
+            double2 v = *reinterpret_cast<double2*>(ptr);
+            v.x = fma(f1, a0, v.x); v.y = fma(f1, a1, v.y);
+            if (rank2) { v.x = fma(f2, b0, v.x); v.y = fma(f2, b1, v.y); }
+            *reinterpret_cast<double2*>(ptr) = v;
+        } else {
+            double v = *ptr;
+            v = fma(f1, a0, v);
+            if (rank2) v = fma(f2, b0, v);
+            *ptr = v;
+        }
+    }
+}
+
+__global__ void group_sweep_begin_kernel(const GroupDev G) {
+    G.state[ST_OBJ_NEW] = G.state[ST_OBJ];
+    G.state[ST_MAXD] = 0.0;
+}
+// group.jl:1207-1212 and twins: change = |(obj_new − obj)/obj|; obj = obj_new; converged if change < tol or maxδ < 1e-4
+__global__ void group_sweep_end_kernel(const GroupDev G) {
+    const double obj = G.state[ST_OBJ], obj_new = G.state[ST_OBJ_NEW];
+    const double change = fabs((obj_new - obj) / obj);
+    G.state[ST_OBJ] = obj_new;
+    G.state[ST_CONV] = (change < G.tol || G.state[ST_MAXD] < 1e-4) ? 1.0 : 0.0;
+}
+// per-group SDP objectives from the current blocks, group.jl:1015-1020
+__global__ void group_sdp_objectives_kernel(const GroupDev G) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G.ng) return;
+    const int gs = G.goff[g + 1] - G.goff[g];
+    const double* Sg = G.SigBlk + (size_t)g * G.gmax * G.gmax;
+    const double* Sb = G.Sblk + (size_t)g * G.gmax * G.gmax;
+    double acc = 0.0;
+    for (int j = 0; j < gs; ++j)
+        for (int i = 0; i < gs; ++i) acc += fabs(Sg[i + (size_t)j * G.gmax] - Sb[i + (size_t)j * G.gmax]);
+    G.gobj[g] = acc / ((double)gs * gs);
+}
+
+// Y = A * blockdiag(B) (side = 0) or blockdiag(B) * A (side = 1); A, Y p x p (ld), B ng blocks (stride gmax², ld gmax)
+__global__ void blockdiag_mul_kernel(const double* A, long ld, int p, const double* B, const int* goff, const int* gid,
+                                     int gmax, int side, double* Y) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)p * p;
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % p), j = (int)(idx / p);
+        double acc = 0.0;
+        if (side == 0) {            // Y(i,j) = sum_{k in G(j)} A(i,k) B(k,j)
+            const int g = gid[j], o = goff[g], gs = goff[g + 1] - o;
+            const double* Bg = B + (size_t)g * gmax * gmax;
+            for (int k = 0; k < gs; ++k) acc = fma(A[i + (long)(o + k) * ld], Bg[k + (size_t)(j - o) * gmax], acc);
+        } else {                    // Y(i,j) = sum_{k in G(i)} B(i,k) A(k,j)
+            const int g = gid[i], o = goff[g], gs = goff[g + 1] - o;
+            const double* Bg = B + (size_t)g * gmax * gmax;
+            for (int k = 0; k < gs; ++k) acc = fma(Bg[(i - o) + (size_t)k * gmax], A[(o + k) + (long)j * ld], acc);
+        }
+        Y[i + (long)j * ld] = acc;
+    }
+}
+// D (lower, ld) = kappa * Sig (full, ld) − blockdiag(S)
+__global__ void build_D_lower_kernel(const double* Sig, long ld, int p, double kappa, const double* Sblk, const int* goff,
+                                     const int* gid, int gmax, double* D) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)p * p;
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % p), j = (int)(idx / p);
+        if (i < j) { D[i + (long)j * ld] = 0.0; continue; }
+        double v = kappa * Sig[i + (long)j * ld];
+        if (gid[i] == gid[j]) {
+            const int g = gid[i], o = goff[g];
+            v -= Sblk[(size_t)g * gmax * gmax + (i - o) + (size_t)(j - o) * gmax];
+        }
+        D[i + (long)j * ld] = v;
+    }
+}
+__global__ void extract_diag_kernel(const double* A, long ld, int p, double* d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p) d[i] = A[i + (long)i * ld];
+}
+
+static inline int ewg3(kb_ctx* ctx, long total) {
+    long g = (total + 255) / 256, cap = (long)ctx->num_sms * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+void default_group_opts(kb_group_opts* o) {
+    o->outer_iter = 100; o->inner_pca_iter = 1; o->inner_ccd_iter = 1; o->tol = 1e-4; o->eps = 1e-6;
+    o->robust = 0; o->verbose = 0;
+}
+
+// Σcor: host, p x p column-major, symmetric, unit diagonal, groups CONTIGUOUS (goff).  Vperm: p x nv host or null.
+// Sblocks_out: ng blocks (stride gmax², ld gmax) on the host.
+int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, const std::vector<int>& goff, int method,
+                           double m, const kb_group_opts& opts, const double* Vperm, int nv_in,
+                           std::vector<double>& Sblocks_out, int* gmax_out, double* obj_out, kb_group_info* info) {
+    const int ng = (int)goff.size() - 1;
+    int gmax = 1;
+    for (int g = 0; g < ng; ++g) gmax = std::max(gmax, goff[g + 1] - goff[g]);
+    *gmax_out = gmax;
+    const size_t bs = (size_t)gmax * gmax;
+    const double kappa = (m + 1.0) / m;
+    const long ld = (p + 1) & ~1L;
+    std::vector<int> gid(p);
+    for (int g = 0; g < ng; ++g)
+        for (int i = goff[g]; i < goff[g + 1]; ++i) gid[i] = g;
+
+    // ---- per-group eigen-decompositions of Σ_GG (host, g x g): inverse square roots + PCA directions ----
+    std::vector<double> SigBlk(bs * ng, 0.0), Db(bs * ng, 0.0), evecs(bs * ng, 0.0), evals((size_t)gmax * ng, 0.0);
+    for (int g = 0; g < ng; ++g) {
+        const int o = goff[g], gs = goff[g + 1] - o;
+        std::vector<double> A((size_t)gs * gs), w, V;
+        for (int j = 0; j < gs; ++j)
+            for (int i = 0; i < gs; ++i) {
+                A[i + (size_t)j * gs] = Scor[(o + i) + (size_t)(o + j) * p];
+                SigBlk[g * bs + i + (size_t)j * gmax] = A[i + (size_t)j * gs];
+            }
+        jacobi_eigh(gs, A, w, V);
+        // inverse_mat_sqrt, group.jl:448-454 (eigenvalues clipped at 1e-6)
+        sym_function(gs, w, V, [](double x) { return 1.0 / std::sqrt(x < 1e-6 ? 1e-6 : x); }, &Db[g * bs], gmax);
+        for (int k = 0; k < gs; ++k) {
+            evals[(size_t)g * gmax + k] = w[k];
+            for (int i = 0; i < gs; ++i) evecs[g * bs + i + (size_t)k * gmax] = V[i + (size_t)k * gs];
+        }
+    }
+    // ---- PCA direction set (get_PCA_vectors, group.jl:2161-2187) ----
+    std::vector<int> vgrp;
+    std::vector<double> vvec;
+    if (Vperm) {
+        for (int j = 0; j < nv_in; ++j) {
+            const double* v = Vperm + (size_t)j * p;
+            int first = -1;
+            for (int i = 0; i < p; ++i)
+                if (v[i] != 0.0) { first = i; break; }
+            if (first < 0) return set_error(ctx, KB_ERR_INVALID, "V column %d is zero", j + 1);
+            const int g = gid[first];
+            for (int i = 0; i < p; ++i)
+                if (v[i] != 0.0 && gid[i] != g)
+                    return set_error(ctx, KB_ERR_INVALID, "V column %d is not supported on a single group", j + 1);
+            vgrp.push_back(g);
+            const size_t base = vvec.size();
+            vvec.resize(base + gmax, 0.0);
+            for (int i = goff[g]; i < goff[g + 1]; ++i) vvec[base + (i - goff[g])] = v[i];
+        }
+    } else {
+        // block by block, eigenvalues ascending, then the unit vectors; duplicates (singleton groups) dropped
+        for (int g = 0; g < ng; ++g) {
+            const int gs = goff[g + 1] - goff[g];
+            for (int k = 0; k < gs; ++k) {
+                vgrp.push_back(g);
+                const size_t base = vvec.size();
+                vvec.resize(base + gmax, 0.0);
+                for (int i = 0; i < gs; ++i) vvec[base + i] = evecs[g * bs + i + (size_t)k * gmax];
+            }
+        }
+        for (int g = 0; g < ng; ++g) {
+            const int gs = goff[g + 1] - goff[g];
+            if (gs == 1 && evecs[g * bs] == 1.0) continue;
+            for (int k = 0; k < gs; ++k) {
+                vgrp.push_back(g);
+                const size_t base = vvec.size();
+                vvec.resize(base + gmax, 0.0);
+                vvec[base + k] = 1.0;
+            }
+        }
+    }
+    const int nv = (int)vgrp.size();
+
+    // ---- device buffers ----
+    Scope sc(ctx);
+    double *dSig, *dA, *dB, *dW2, *dwork, *dinvdiag, *dDb, *dSblk, *dMSblk, *dSigBlk, *dvvec, *dWv, *dcoef, *dstate, *dgobj, *ddiag;
+    int *dgoff, *dgid, *dvgrp, *d_fail;
+    KB_TRY(sc.alloc(&dSig, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dA, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dB, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dW2, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dwork, (size_t)ld * p / 2 + 2 * ld + 64));
+    KB_TRY(sc.alloc(&dinvdiag, potrf_invdiag_doubles(p)));
+    KB_TRY(sc.alloc(&dDb, bs * ng));
+    KB_TRY(sc.alloc(&dSblk, bs * ng));
+    KB_TRY(sc.alloc(&dMSblk, bs * ng));
+    KB_TRY(sc.alloc(&dSigBlk, bs * ng));
+    KB_TRY(sc.alloc(&dvvec, (size_t)std::max(nv, 1) * gmax));
+    KB_TRY(sc.alloc(&dWv, (size_t)2 * ld));
+    KB_TRY(sc.alloc(&dcoef, 8));
+    KB_TRY(sc.alloc(&dstate, 16));
+    KB_TRY(sc.alloc(&dgobj, ng));
+    KB_TRY(sc.alloc(&ddiag, p));
+    KB_TRY(sc.alloc(&dgoff, ng + 1));
+    KB_TRY(sc.alloc(&dgid, p));
+    KB_TRY(sc.alloc(&dvgrp, std::max(nv, 1)));
+    KB_TRY(sc.alloc(&d_fail, 4));
+    cudaStream_t st = ctx->stream;
+    KB_CUDA(ctx, cudaMemcpy2DAsync(dSig, ld * sizeof(double), Scor.data(), (size_t)p * sizeof(double), (size_t)p * sizeof(double), p,
+                                   cudaMemcpyHostToDevice, st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dDb, Db.data(), sizeof(double) * bs * ng, cudaMemcpyHostToDevice, st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dSigBlk, SigBlk.data(), sizeof(double) * bs * ng, cudaMemcpyHostToDevice, st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dgoff, goff.data(), sizeof(int) * (ng + 1), cudaMemcpyHostToDevice, st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dgid, gid.data(), sizeof(int) * p, cudaMemcpyHostToDevice, st));
+    if (nv > 0) {
+        KB_CUDA(ctx, cudaMemcpyAsync(dvvec, vvec.data(), sizeof(double) * (size_t)nv * gmax, cudaMemcpyHostToDevice, st));
+        KB_CUDA(ctx, cudaMemcpyAsync(dvgrp, vgrp.data(), sizeof(int) * nv, cudaMemcpyHostToDevice, st));
+    }
+
+    // ---- solve_group_equi (group.jl:479-495): γ = min(1, κ λmin(Db Σ Db)) ----
+    const int eg = ewg3(ctx, (long)p * p);
+    blockdiag_mul_kernel<<<eg, 256, 0, st>>>(dSig, ld, p, dDb, dgoff, dgid, gmax, 0, dA);      // A = Σ Db
+    blockdiag_mul_kernel<<<eg, 256, 0, st>>>(dA, ld, p, dDb, dgoff, dgid, gmax, 1, dB);        // B = Db Σ Db
+    ctx->launches += 2;
+    KB_CUDA(ctx, cudaGetLastError());
+    double lam = 0.0;
+    KB_TRY(eigmin_lower_dev(ctx, dB, ld, p, dA, dinvdiag, d_fail, &lam));
+    const double gamma = std::min(1.0, kappa * lam);
+    // ---- initialize_S (group.jl:432-443): S = γ Σ_GG, eigenvalues clipped at 1e-8, halved ----
+    std::vector<double> Sblk(bs * ng, 0.0), MSblk(bs * ng, 0.0);
+    double logdetS = 0.0, trSinv = 0.0;
+    for (int g = 0; g < ng; ++g) {
+        const int gs = goff[g + 1] - goff[g];
+        std::vector<double> V((size_t)gs * gs), w(gs);
+        for (int k = 0; k < gs; ++k) {
+            double e = gamma * evals[(size_t)g * gmax + k];
+            if (e < 1e-8) e = 1e-8;
+            w[k] = e / 2.0;
+            for (int i = 0; i < gs; ++i) V[i + (size_t)k * gs] = evecs[g * bs + i + (size_t)k * gmax];
+        }
+        sym_function(gs, w, V, [](double x) { return x; }, &Sblk[g * bs], gmax);
+        sym_function(gs, w, V, [](double x) { return 1.0 / x; }, &MSblk[g * bs], gmax);
+        for (int k = 0; k < gs; ++k) { logdetS += std::log(w[k]); trSinv += 1.0 / w[k]; }
+    }
+    KB_CUDA(ctx, cudaMemcpyAsync(dSblk, Sblk.data(), sizeof(double) * bs * ng, cudaMemcpyHostToDevice, st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dMSblk, MSblk.data(), sizeof(double) * bs * ng, cudaMemcpyHostToDevice, st));
+    // ---- MD = (κΣ − S)^{-1} on the tensor-core Cholesky / inverse; logdet and trace for the objectives ----
+    build_D_lower_kernel<<<eg, 256, 0, st>>>(dSig, ld, p, kappa, dSblk, dgoff, dgid, gmax, dA);
+    ctx->launches++;
+    KB_CUDA(ctx, cudaMemsetAsync(d_fail, 0, sizeof(int), st));
+    KB_TRY(potrf_lower(ctx, dA, ld, p, dinvdiag, d_fail));
+    {
+        int f = 0;
+        KB_CUDA(ctx, cudaMemcpyAsync(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st));
+        KB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (f != 0)
+            return set_error(ctx, KB_ERR_NOT_PD, "PosDefException: (m+1)/m*Sigma - S is not positive definite at "
+                                                 "initialisation; Cholesky factorization failed at pivot %d.", f);
+    }
+    std::vector<double> hdiag(p);
+    extract_diag_kernel<<<ceil_div(p, 256), 256, 0, st>>>(dA, ld, p, ddiag);
+    ctx->launches++;
+    KB_CUDA(ctx, cudaMemcpyAsync(hdiag.data(), ddiag, sizeof(double) * p, cudaMemcpyDeviceToHost, st));
+    KB_TRY(trtri_lower(ctx, dA, ld, p, dinvdiag, dW2, ld, dwork));
+    double* dMD = dB;
+    KB_TRY(fill_zero(ctx, dMD, (size_t)ld * p));
+    KB_TRY(syrk_WtW_lower(ctx, dW2, ld, p, dMD, ld));
+    KB_TRY(mirror_lower_to_upper(ctx, dMD, ld, p));
+    extract_diag_kernel<<<ceil_div(p, 256), 256, 0, st>>>(dMD, ld, p, ddiag);
+    ctx->launches++;
+    std::vector<double> hdiagM(p);
+    KB_CUDA(ctx, cudaMemcpyAsync(hdiagM.data(), ddiag, sizeof(double) * p, cudaMemcpyDeviceToHost, st));
+    KB_CUDA(ctx, cudaStreamSynchronize(st));
+    double logdetD = 0.0, trDinv = 0.0;
+    for (int i = 0; i < p; ++i) { logdetD += 2.0 * std::log(hdiag[i]); trDinv += hdiagM[i]; }
+
+    // ---- initial objective (group.jl:887, :975-984, :1078) ----
+    double obj0 = 0.0;
+    std::vector<double> gobj(ng, 0.0);
+    if (method == KB_METHOD_MAXENT) obj0 = logdetD + m * logdetS;                 // group_maxent_obj :1678-1680
+    else if (method == KB_METHOD_MVR) obj0 = m * m * trSinv + trDinv;             // group_block_objective :27
+    else {
+        for (int g = 0; g < ng; ++g) {
+            const int gs = goff[g + 1] - goff[g];
+            double acc = 0.0;
+            for (int j = 0; j < gs; ++j)
+                for (int i = 0; i < gs; ++i) acc += std::fabs(SigBlk[g * bs + i + (size_t)j * gmax] - Sblk[g * bs + i + (size_t)j * gmax]);
+            gobj[g] = acc / ((double)gs * gs);
+            obj0 += gobj[g];
+        }
+    }
+    if (info) { info->obj_init = obj0; info->gamma_equi = gamma; info->n_directions = nv; }
+    *obj_out = obj0;
+    Sblocks_out = Sblk;
+    if (method == KB_METHOD_SDP_CCD && obj0 < opts.eps) return KB_OK;              // quick return, group.jl:982-984
+
+    GroupDev G{};
+    G.p = p; G.ng = ng; G.gmax = gmax; G.nv = nv; G.method = method; G.ld = ld; G.m = m; G.eps = opts.eps; G.tol = opts.tol;
+    G.MD = dMD; G.goff = dgoff; G.Sblk = dSblk; G.MSblk = dMSblk; G.SigBlk = dSigBlk; G.vgrp = dvgrp; G.vvec = dvvec;
+    G.W = dWv; G.coef = dcoef; G.state = dstate; G.gobj = dgobj;
+    double hstate[16] = {0};
+    hstate[ST_OBJ] = obj0;
+    KB_CUDA(ctx, cudaMemcpyAsync(dstate, hstate, sizeof(hstate), cudaMemcpyHostToDevice, st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dgobj, gobj.data(), sizeof(double) * ng, cudaMemcpyHostToDevice, st));
+    KB_TRY(fill_zero(ctx, dcoef, 8));
+    KB_TRY(fill_zero(ctx, dWv, (size_t)2 * ld));
+
+    const size_t step_smem = (size_t)(3 * gmax + 3 * GSTEP_WARPS + 8) * sizeof(double);
+    if (step_smem > 200 * 1024) return set_error(ctx, KB_ERR_INVALID, "group size %d too large", gmax);
+    KB_CUDA(ctx, cudaFuncSetAttribute(group_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
+    const dim3 agrid(ceil_div(ceil_div(p, 2), 256), ceil_div(p, GAPPLY_COLS));
+    auto step = [&](int type, int g, int ia, int ib) {
+        group_step_kernel<<<1, GSTEP_THREADS, step_smem, st>>>(G, type, g, ia, ib);
+        group_apply_kernel<<<agrid, 256, 0, st>>>(G);
+        ctx->launches += 2;
+    };
+    int inner_sweeps = 0, outer_done = 0;
+    auto end_sweep = [&](int kind, bool* conv) -> int {
+        group_sweep_end_kernel<<<1, 1, 0, st>>>(G);
+        ctx->launches++;
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_CUDA(ctx, cudaMemcpyAsync(hstate, dstate, sizeof(hstate), cudaMemcpyDeviceToHost, st));
+        KB_CUDA(ctx, cudaStreamSynchronize(st));
+        *conv = hstate[ST_CONV] != 0.0;
+        if (info && inner_sweeps < KB_MAX_TRACE) {
+            info->trace_obj[inner_sweeps] = hstate[ST_OBJ];
+            info->trace_delta[inner_sweeps] = hstate[ST_MAXD];
+            info->trace_kind[inner_sweeps] = kind;
+        }
+        ++inner_sweeps;
+        return KB_OK;
+    };
+    KB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    for (int it = 0; it < opts.outer_iter; ++it) {
+        ++outer_done;
+        bool conv1 = opts.inner_pca_iter == 0, conv2 = opts.inner_ccd_iter == 0;
+        for (int l = 0; l < opts.inner_pca_iter; ++l) {                       // _X_pca_ccd_iter!
+            group_sweep_begin_kernel<<<1, 1, 0, st>>>(G);
+            ctx->launches++;
+            for (int jv = 0; jv < nv; ++jv) step(STEP_PCA, vgrp[jv], jv, 0);
+            bool c = false;
+            KB_TRY(end_sweep(0, &c));
+            if (c) { conv1 = true; break; }
+        }
+        for (int l = 0; l < opts.inner_ccd_iter; ++l) {                       // _X_ccd_iter!
+            group_sweep_begin_kernel<<<1, 1, 0, st>>>(G);
+            ctx->launches++;
+            for (int g = 0; g < ng; ++g) {
+                const int gs = goff[g + 1] - goff[g];
+                for (int j = 0; j < gs; ++j) step(STEP_DIAG, g, j, 0);
+                for (int i1 = 0; i1 < gs; ++i1)
+                    for (int i2 = i1 + 1; i2 < gs; ++i2) step(STEP_OFFDIAG, g, i2, i1);   // (i, j) = (idx2, idx1)
+            }
+            bool c = false;
+            KB_TRY(end_sweep(1, &c));
+            if (c) { conv2 = true; break; }
+        }
+        if (method == KB_METHOD_SDP_CCD && opts.inner_pca_iter > 0) {             // group.jl:1015-1020
+            group_sdp_objectives_kernel<<<ceil_div(ng, 128), 128, 0, st>>>(G);
+            ctx->launches++;
+        }
+        if (conv1 && conv2) break;
+    }
+    KB_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    Sblocks_out.resize(bs * ng);
+    KB_CUDA(ctx, cudaMemcpyAsync(Sblocks_out.data(), dSblk, sizeof(double) * bs * ng, cudaMemcpyDeviceToHost, st));
+    KB_CUDA(ctx, cudaMemcpyAsync(hstate, dstate, sizeof(hstate), cudaMemcpyDeviceToHost, st));
+    KB_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    KB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *obj_out = hstate[ST_OBJ];
+    if (info) {
+        info->obj = hstate[ST_OBJ];
+        info->outer_iters = outer_done;
+        info->inner_sweeps = inner_sweeps;
+        info->steps = hstate[ST_STEPS];
+        info->accepted = hstate[ST_ACCEPTED];
+        info->solve_ms = ms;
+        // bytes the reference's formulation moves for the same steps: per accepted rank-1 step two
+        // factor updates + the solves; reported as the bytes THIS kernel moves: 16 p² per accepted step
+        info->touched_bytes = 16.0 * (double)p * (double)p * hstate[ST_ACCEPTED];
+    }
+    return KB_OK;
+}
+
+
+int solve_s_group_host(kb_ctx* ctx, const double* Sigma, int p, const int64_t* groups, int method, double m,
+                       const kb_group_opts* opts_in, const double* V, int nv, double* S_out, double* obj_out,
+                       kb_group_info* info) {
+    kb_group_opts opts;
+    if (opts_in) opts = *opts_in; else default_group_opts(&opts);
+    if (info) memset(info, 0, sizeof(*info));
+    if (!(m >= 1.0)) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %g.", m);
+    if (method != KB_METHOD_MVR && method != KB_METHOD_MAXENT && method != KB_METHOD_SDP_CCD && method != KB_METHOD_EQUI)
+        return set_error(ctx, KB_ERR_INVALID, "Method must be one of the group knockoff methods (mvr, maxent, sdp, equi)");
+    // Symmetric(Σ): upper triangle; σ = sqrt(diag); Σcor = cov2cor (group.jl:366-368)
+    std::vector<double> sig(p);
+    for (int i = 0; i < p; ++i) {
+        const double d = Sigma[i + (size_t)i * p];
+        if (!(d > 0.0)) return set_error(ctx, KB_ERR_NOT_PD, "Sigma has a non-positive diagonal entry at %d", i + 1);
+        sig[i] = std::sqrt(d);
+    }
+    // sortperm(groups) (stable), group.jl:370-377
+    std::vector<int> perm(p);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return groups[a] < groups[b]; });
+    std::vector<double> Scor((size_t)p * p);
+    for (int jj = 0; jj < p; ++jj) {
+        const int j = perm[jj];
+        for (int ii = 0; ii < p; ++ii) {
+            const int i = perm[ii];
+            double v;
+            if (i == j) v = 1.0;
+            else {
+                const double raw = (i < j) ? Sigma[i + (size_t)j * p] : Sigma[j + (size_t)i * p];
+                v = raw / (sig[i] * sig[j]);
+                v = v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v);
+            }
+            Scor[ii + (size_t)jj * p] = v;
+        }
+    }
+    std::vector<int> goff{0};
+    for (int ii = 1; ii < p; ++ii)
+        if (groups[perm[ii]] != groups[perm[ii - 1]]) goff.push_back(ii);
+    goff.push_back(p);
+    const int ng = (int)goff.size() - 1;
+    std::vector<double> Sperm((size_t)p * p, 0.0);
+    double obj = 0.0;
+    if (ng == p) {
+        // all singletons: the ungrouped problem (group.jl:378-386); group :sdp maps to the CCD solver
+        Scope sc(ctx);
+        double *dS, *ds;
+        KB_TRY(sc.alloc(&dS, (size_t)p * p));
+        KB_TRY(sc.alloc(&ds, p));
+        KB_CUDA(ctx, cudaMemcpyAsync(dS, Scor.data(), sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+        KB_TRY(solve_s_dev(ctx, dS, p, p, method, m, nullptr, nullptr, ds, nullptr));
+        std::vector<double> s(p);
+        KB_CUDA(ctx, cudaMemcpyAsync(s.data(), ds, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < p; ++i) Sperm[i + (size_t)i * p] = s[i];
+    } else {
+        std::vector<double> Vperm;
+        if (V && nv > 0) {
+            Vperm.resize((size_t)p * nv);
+            for (int j = 0; j < nv; ++j)
+                for (int ii = 0; ii < p; ++ii) Vperm[ii + (size_t)j * p] = V[perm[ii] + (size_t)j * p];
+        }
+        std::vector<double> Sblk;
+        int gmax = 1;
+        kb_group_opts o2 = opts;
+        if (method == KB_METHOD_EQUI) { o2.outer_iter = 0; }      // solve_group_equi only (S = γ Σ_GG)
+        KB_TRY(group_solve_contiguous(ctx, Scor, p, goff, method == KB_METHOD_EQUI ? KB_METHOD_MAXENT : method, m, o2,
+                                      Vperm.empty() ? nullptr : Vperm.data(), nv, Sblk, &gmax, &obj, info));
+        const size_t bs = (size_t)gmax * gmax;
+        const double scale = (method == KB_METHOD_EQUI) ? 2.0 : 1.0;   // initialize_S halves the equi solution
+        for (int g = 0; g < ng; ++g) {
+            const int o = goff[g], gs = goff[g + 1] - o;
+            for (int j = 0; j < gs; ++j)
+                for (int i = 0; i < gs; ++i) Sperm[(o + i) + (size_t)(o + j) * p] = scale * Sblk[g * bs + i + (size_t)j * gmax];
+        }
+        if (method == KB_METHOD_EQUI) {
+            // objective of the equi solution is the SDP block objective (group.jl:493)
+            obj = 0.0;
+            for (int g = 0; g < ng; ++g) {
+                const int o = goff[g], gs = goff[g + 1] - o;
+                double acc = 0.0;
+                for (int j = 0; j < gs; ++j)
+                    for (int i = 0; i < gs; ++i)
+                        acc += std::fabs(Scor[(o + i) + (size_t)(o + j) * p] - Sperm[(o + i) + (size_t)(o + j) * p]);
+                obj += acc / ((double)gs * gs);
+            }
+        }
+    }
+    // un-permute (group.jl:414-418) and cor2cov! (:420)
+    for (int jj = 0; jj < p; ++jj)
+        for (int ii = 0; ii < p; ++ii) {
+            const int i = perm[ii], j = perm[jj];
+            S_out[i + (size_t)j * p] = Sperm[ii + (size_t)jj * p] * sig[i] * sig[j];
+        }
+    // iscor: the reference skips the rescale when all σ ≈ 1; multiplying by σ_i σ_j ≈ 1 would perturb S at 1e-8,
+    // so do exactly what it does
+    bool iscor = true;
+    for (int i = 0; i < p; ++i)
+        if (!(std::fabs(sig[i] - 1.0) <= 1.4901161193847656e-08 * std::fmax(std::fabs(sig[i]), 1.0))) iscor = false;
+    if (iscor)
+        for (int jj = 0; jj < p; ++jj)
+            for (int ii = 0; ii < p; ++ii) S_out[perm[ii] + (size_t)perm[jj] * p] = Sperm[ii + (size_t)jj * p];
+    if (obj_out) *obj_out = obj;
+    if (info) info->status = KB_OK;
+    return KB_OK;
+}
+
+}  // namespace kb

@@ -15,7 +15,7 @@ METHODS = {"mvr": 0, "maxent": 1, "sdp_ccd": 2}
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libko_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("ccd_oracle.c", "group_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("ccd_oracle.c",)]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libko_oracle.so"])
     return so

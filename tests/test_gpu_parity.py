@@ -294,3 +294,80 @@ def test_row_sharded_sampling_equals_single(kb, ctx):
         lo, hi = kb.dist.shard_rows(n, 2, r)
         parts.append(kb.sample(np.asfortranarray(X[lo:hi]), mu, SiS, Lb, m=m, Z=None, seed=77, row_offset=lo, ctx=ctx))
     assert np.array_equal(np.vstack(parts), full)
+
+
+# ---- group knockoffs ----------------------------------------------------------
+def _group_problem(ngroups=10, gsize=5, rho=0.4, gamma=0.2):
+    groups = np.repeat(np.arange(1, ngroups + 1), gsize)
+    return np.asfortranarray(ko.simulate_block_covariance(groups, rho, gamma)), groups
+
+
+@pytest.mark.parametrize("method", ["maxent", "mvr", "sdp"])
+@pytest.mark.parametrize("pca,ccd", [(1, 1), (1, 0), (10, 5)])
+def test_group_solver_matches_oracle_and_reference_properties(kb, ctx, method, pca, ccd):
+    """runtests.jl:546-625 configuration (10 groups x 5, rho 0.4, gamma 0.2, m = 5, tol 0.01): parity with the
+    oracle on a shared direction set V, plus the reference's own property tests."""
+    from oracle import group_oracle as go
+    Sigma, groups = _group_problem()
+    m = 5
+    V = go.get_PCA_vectors(Sigma, list(groups))
+    want_S, _, want_obj = go.solve_s_group(Sigma, groups, method, m=m, V=V, tol=0.01, inner_pca_iter=pca,
+                                           inner_ccd_iter=ccd)
+    keep = Sigma.copy()
+    S, gam, obj, info = kb.solve_s_group(Sigma, groups, method, m=m, V=V, tol=0.01, inner_pca_iter=pca,
+                                         inner_ccd_iter=ccd, ctx=ctx, return_info=True)
+    assert np.array_equal(Sigma, keep)                                  # inputs not mutated (runtests.jl:582-583)
+    assert np.max(np.abs(S - want_S)) / np.max(np.abs(want_S)) < 1e-8
+    assert abs(obj - want_obj) <= 1e-8 * max(1.0, abs(want_obj))
+    assert np.linalg.eigvalsh((S + S.T) / 2).min() > -1e-7              # runtests.jl:579-581
+    assert np.linalg.eigvalsh((m + 1) / m * Sigma - S).min() > -1e-7
+    mask = groups[:, None] == groups[None, :]
+    assert np.all(S[~mask] == 0.0)                                      # block diagonal (runtests.jl:584-589)
+    assert gam.size == 0
+
+
+def test_group_solver_default_V_noncontiguous_groups_and_covariance_scale(kb, ctx):
+    """groups given out of order (sortperm path, group.jl:370-377, 414-418) on a covariance (cor2cov!, :420);
+    the library's own direction set equals the oracle's (per-group eigenvectors)."""
+    from oracle import group_oracle as go
+    rng = np.random.default_rng(3)
+    Sigma, groups = _group_problem(8, 4, 0.5, 0.3)
+    p = Sigma.shape[0]
+    shuffle = rng.permutation(p)
+    d = np.linspace(0.7, 1.9, p)
+    Cov = np.asfortranarray((Sigma * np.outer(d, d))[np.ix_(shuffle, shuffle)])
+    g2 = groups[shuffle]
+    S, _, obj = kb.solve_s_group(Cov, g2, "maxent", m=2, ctx=ctx)
+    mask = g2[:, None] == g2[None, :]
+    assert np.all(S[~mask] == 0.0)
+    assert np.linalg.eigvalsh(1.5 * Cov - S).min() > -1e-7 and np.linalg.eigvalsh(S).min() > -1e-7
+    # objective-level agreement with the oracle run on the same problem (direction bases may differ by sign/rotation)
+    want_S, _, want_obj = go.solve_s_group(Cov, g2, "maxent", m=2)
+    assert abs(obj - want_obj) < 1e-3 * abs(want_obj)
+    assert np.max(np.abs(S - want_S)) < 5e-3
+
+
+def test_group_singletons_fall_back_to_single_solver(kb, ctx):
+    Sigma = toeplitz(60, 0.4)
+    groups = np.arange(1, 61)
+    S, _, obj = kb.solve_s_group(Sigma, groups, "mvr", m=1, ctx=ctx)
+    s = kb.solve_s(Sigma, "mvr", m=1, ctx=ctx)
+    assert np.array_equal(np.diag(S), s) and obj == 0.0 and np.count_nonzero(S - np.diag(s)) == 0
+
+
+def test_modelX_group_one_shot(kb, ctx):
+    from oracle import group_oracle as go
+    rng = np.random.default_rng(4)
+    Sigma, groups = _group_problem(6, 5, 0.5, 0.2)
+    p, n, m = Sigma.shape[0], 300, 2
+    X = np.asfortranarray(rng.standard_normal((n, p)) @ np.linalg.cholesky(Sigma).T)
+    Z = np.asfortranarray(rng.standard_normal((n, m * p)))
+    V = go.get_PCA_vectors(Sigma, list(groups))
+    res = kb.modelX_gaussian_group_knockoffs(X, "maxent", groups, np.zeros(p), Sigma, m=m, V=V, Z=Z, ctx=ctx)
+    want_S, _, want_obj = go.solve_s_group(Sigma, groups, "maxent", m=m, V=V)
+    want_X = ko.condition(X, np.zeros(p), Sigma, want_S, m=m, Z=Z)
+    assert np.max(np.abs(res.S - want_S)) < 1e-8 and abs(res.obj - want_obj) < 1e-8 * abs(want_obj)
+    assert np.max(np.abs(res.Xko - want_X)) < 1e-8
+    assert res.Xko.shape == (n, m * p)
+    with pytest.raises(kb.KnockoffsError):                              # group.jl:119-120
+        kb.modelX_gaussian_group_knockoffs(X, "maxent", groups[:-1], np.zeros(p), Sigma, ctx=ctx)
