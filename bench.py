@@ -31,7 +31,12 @@ METRIC = "knockoff rows/s (solve_s :mvr + conditional factor + sampling, p=5000,
 UNIT = "rows/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
 # ncu --set full capture (profiles/); None until a capture of this exact configuration exists.
-NCU_TRAFFIC_BYTES = {"ccd_stream_kernel": None, "dgemm_dmma_kernel": None}
+NCU_TRAFFIC_BYTES = {
+    # profiles/r01_ccd_stream_kernel_ncu_raw.csv: 375.47 GB read + 494.29 GB written per sweep launch (p = 5000)
+    "ccd_stream_kernel": 869.76e9,
+    # profiles/r01_dgemm_dmma_kernel_sampling_ncu_raw.csv: one 4096-row chunk GEMM (2 segments): 1.015 GB + 0.138 GB
+    "dgemm_dmma_kernel": 1.153e9,
+}
 
 
 def parse():

@@ -137,109 +137,236 @@ int fill_zero(kb_ctx* ctx, double* A, size_t count) {
 constexpr int DIAG_PITCH = POTRF_NB + 1;
 constexpr int DIAG_THREADS = 512;
 constexpr int DIAG_PANEL = 16;     // columns factored per panel step
-constexpr size_t DIAG_SMEM = (size_t)(POTRF_NB * DIAG_PITCH + POTRF_NB) * sizeof(double);
+constexpr int DIAG_NPANEL = POTRF_NB / DIAG_PANEL;
+// T (128 x 129) + W (inverse, lower triangle folded into a 129 x 64 rectangle) + 16 x 17 scratch for the panel's
+// diagonal block and its inverse: 132 + 66 + 4 KB
+constexpr size_t DIAG_SMEM = (size_t)(POTRF_NB * DIAG_PITCH + DIAG_PITCH * (POTRF_NB / 2) + 2 * DIAG_PANEL * (DIAG_PANEL + 1)) * sizeof(double);
+// folded lower-triangular storage: (i, k), i >= k.  Columns k < 64 keep rows k..127 at row i + 1; columns k >= 64 go
+// to column 127 - k, row 127 - i (the part of that column the first half leaves free).
+__device__ __forceinline__ int wfold(int i, int k) {
+    return (k < POTRF_NB / 2) ? (k * DIAG_PITCH + i + 1) : ((POTRF_NB - 1 - k) * DIAG_PITCH + (POTRF_NB - 1 - i));
+}
 
-// One CTA factors an nb x nb (<= 128) diagonal block held in shared memory, writes L back and then
-// inv(L) to `inv`.  Blocked right-looking inside the CTA: a 16-column panel is factored by its own
-// 128 x 16 thread strip (one thread per row, columns swept with CTA barriers), then the trailing
-// matrix gets ONE rank-16 update with 4 x 4 register tiles (no integer division in any loop).
+// C(i0.., j0..) (+)= sign * A(i0.., k-range) * B(j0.., k-range)'  over a rows x cols output block, 4 x 4 register
+// tiles dealt round-robin to the CTA's threads.  All operands in shared memory with pitch DIAG_PITCH (column-major),
+// element (i, k) of X at X[k * DIAG_PITCH + i].  lower_only: skip tiles strictly above the diagonal of the output.
+template <bool ACCUM, bool LOWER_ONLY>
+__device__ __forceinline__ void smem_tile_gemm_nt(double* C, int ci0, int cj0, int rows, int cols, const double* A, int ai0,
+                                                  int ak0, const double* B, int bj0, int bk0, int kk, double sign, int tid) {
+    const int tr = (rows + 3) >> 2, tc = (cols + 3) >> 2;
+    for (int tile = tid; tile < tr * tc; tile += DIAG_THREADS) {
+        const int ti = (tile % tr) * 4, tj = (tile / tr) * 4;
+        if (LOWER_ONLY && ci0 + ti + 3 < cj0 + tj) continue;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int k = 0; k < kk; ++k) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                av[a] = (ti + a < rows) ? A[(ak0 + k) * DIAG_PITCH + ai0 + ti + a] : 0.0;
+                bv[a] = (tj + a < cols) ? B[(bk0 + k) * DIAG_PITCH + bj0 + tj + a] : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (ti + a < rows && tj + b < cols && (!LOWER_ONLY || ci0 + ti + a >= cj0 + tj + b)) {
+                    double* c = &C[(cj0 + tj + b) * DIAG_PITCH + ci0 + ti + a];
+                    *c = ACCUM ? (*c + sign * acc[a][b]) : sign * acc[a][b];
+                }
+            }
+    }
+}
+
+// One CTA factors an nb x nb (<= 128) diagonal block held in shared memory, writes L back and then inv(L) to `inv`.
+// Blocked right-looking inside the CTA with 16-column panels:
+//   (a) warp 0 factors the 16 x 16 diagonal block and inverts it (warp-synchronous, no CTA barrier per column),
+//   (b) the panel below it is multiplied by that inverse (TRSM as a small GEMM),
+//   (c) the trailing matrix gets one rank-16 update with 4 x 4 register tiles.
+// The triangular inverse is blocked the same way: 16 x 16 diagonal inverses from (a), then recursive doubling
+// W21 = -W22 (L21 W11) at block sizes 16, 32, 64.
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
 potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) {
     extern __shared__ double dsm[];
-    double* T = dsm;                              // T(i,k) at k*DIAG_PITCH + i
-    double* xv = dsm + POTRF_NB * DIAG_PITCH;
-    const int tid = threadIdx.x;
+    double* T = dsm;                                   // T(i,k) at k*DIAG_PITCH + i
+    double* W = dsm + POTRF_NB * DIAG_PITCH;           // inverse being assembled (lower)
+    double* D16 = W + DIAG_PITCH * (POTRF_NB / 2);     // 16 x 17: factored diagonal block of the current panel
+    double* I16 = D16 + DIAG_PANEL * (DIAG_PANEL + 1); // 16 x 17: its inverse
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #define T_(i, k) T[(k) * DIAG_PITCH + (i)]
+#define W_(i, k) W[wfold((i), (k))]
+#define WG_(i, k) (((i) >= (k)) ? W[wfold((i), (k))] : 0.0)
+#define D_(i, k) D16[(k) * (DIAG_PANEL + 1) + (i)]
+#define I_(i, k) I16[(k) * (DIAG_PANEL + 1) + (i)]
     {
         const int i = tid & (POTRF_NB - 1);
-        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB)
+        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB) {
             T_(i, k) = (i < nb && k < nb) ? ((i >= k) ? A[i + (long)k * ld] : 0.0) : (i == k ? 1.0 : 0.0);
+            if (i >= k) W_(i, k) = 0.0;
+        }
     }
     __syncthreads();
-    for (int j0 = 0; j0 < nb; j0 += DIAG_PANEL) {
-        const int jb = min(DIAG_PANEL, nb - j0);
-        // ---- panel: columns j0 .. j0+jb-1, rows j0 .. nb-1; thread `tid` < 128 owns row tid ----
-        for (int j = j0; j < j0 + jb; ++j) {
-            double d = T_(j, j);
-            if (!(d > 0.0)) {                      // also catches NaN
-                if (tid == 0) atomicCAS(fail, 0, base + j + 1);
-                d = 1.0;
+    for (int jb = 0; jb < DIAG_NPANEL; ++jb) {
+        const int j0 = jb * DIAG_PANEL;
+        // ---- (a) warp 0: 16 x 16 Cholesky + inverse, lane r owns row r (lanes 16..31 idle) ----
+        if (warp == 0) {
+            const int r = lane;
+            double row[DIAG_PANEL];
+#pragma unroll
+            for (int c = 0; c < DIAG_PANEL; ++c) row[c] = (r < DIAG_PANEL && c <= r) ? T_(j0 + r, j0 + c) : 0.0;
+#pragma unroll
+            for (int c = 0; c < DIAG_PANEL; ++c) {
+                double d = __shfl_sync(0xffffffffu, row[c], c);          // pivot (row c, column c)
+                if (!(d > 0.0)) {                                         // also catches NaN
+                    if (lane == 0 && j0 + c < nb) atomicCAS(fail, 0, base + j0 + c + 1);
+                    d = 1.0;
+                }
+                const double ljj = sqrt(d);
+                row[c] = (r == c) ? ljj : row[c] / ljj;                   // column c scaled (rows > c meaningful)
+#pragma unroll
+                for (int k = c + 1; k < DIAG_PANEL; ++k) {
+                    const double lkc = __shfl_sync(0xffffffffu, row[c], k);   // L(k, c)
+                    if (r >= k) row[k] = fma(-row[c], lkc, row[k]);
+                }
             }
-            const double ljj = sqrt(d);
-            __syncthreads();
-            if (tid < nb && tid >= j) {
-                const double v = (tid == j) ? ljj : T_(tid, j) / ljj;
-                T_(tid, j) = v;
+            if (r < DIAG_PANEL) {
+#pragma unroll
+                for (int c = 0; c < DIAG_PANEL; ++c) {
+                    const double lv = (c <= r) ? row[c] : 0.0;
+                    T_(j0 + r, j0 + c) = lv;
+                    D_(r, c) = lv;
+                }
             }
-            __syncthreads();
-            // update the remaining panel columns k = j+1 .. j0+jb-1 of rows >= k
-            if (tid < nb && tid > j) {
-                const double lij = T_(tid, j);
-                for (int k = j + 1; k < j0 + jb; ++k)
-                    if (tid >= k) T_(tid, k) -= lij * T_(k, j);
-            }
-            __syncthreads();
-        }
-        // ---- trailing update: T(i,k) -= sum_{c in panel} T(i,c) T(k,c) for i >= k >= j0+jb ----
-        const int t0 = j0 + jb;
-        if (t0 < nb) {
-            // 4x4 tiles over the trailing square; 32 x 32 tile grid covers 128 x 128, 512 threads -> 2 tiles each
-            for (int tile = tid; tile < 32 * 32; tile += DIAG_THREADS) {
-                const int ti = t0 + (tile & 31) * 4, tk = t0 + (tile >> 5) * 4;
-                if (ti >= nb || tk >= nb || ti + 3 < tk) continue;
-                double acc[4][4];
+            __syncwarp();
+            // inverse: lane c computes COLUMN c of inv(L) by forward substitution (L read from shared memory,
+            // all lanes read the same address -> broadcast)
+            if (r < DIAG_PANEL) {
+                const int c = r;
+                double x[DIAG_PANEL];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int i = 0; i < DIAG_PANEL; ++i) {
+                    double acc = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-                for (int c = j0; c < t0; ++c) {
-                    double li[4], lk[4];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) { li[a] = T_(ti + a, c); lk[a] = T_(tk + a, c); }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) acc[a][b] = fma(li[a], lk[b], acc[a][b]);
+                    for (int k = 0; k < DIAG_PANEL; ++k)
+                        if (k < i) acc = fma(-D_(i, k), (k >= c) ? x[k] : 0.0, acc);
+                    x[i] = (i >= c) ? acc / D_(i, i) : 0.0;
                 }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b)
-                        if (ti + a < nb && tk + b < nb && ti + a >= tk + b) T_(ti + a, tk + b) -= acc[a][b];
+                for (int i = 0; i < DIAG_PANEL; ++i) {
+                    I_(i, c) = x[i];
+                    if (i >= c) W_(j0 + i, j0 + c) = x[i];
+                }
             }
         }
         __syncthreads();
+        const int t0 = j0 + DIAG_PANEL;
+        if (t0 < POTRF_NB) {
+            // ---- (b) panel rows below: P <- P * inv(D)'   (P(i, c) = sum_k Pold(i, k) I(c, k), k <= c) ----
+            // each thread owns whole rows so that the in-place product needs no second buffer
+            for (int i = t0 + tid; i < POTRF_NB; i += DIAG_THREADS) {
+                double pr[DIAG_PANEL];
+#pragma unroll
+                for (int k = 0; k < DIAG_PANEL; ++k) pr[k] = T_(i, j0 + k);
+#pragma unroll
+                for (int c = 0; c < DIAG_PANEL; ++c) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIAG_PANEL; ++k)
+                        if (k <= c) acc = fma(pr[k], I_(c, k), acc);
+                    T_(i, j0 + c) = acc;
+                }
+            }
+            __syncthreads();
+            // ---- (c) trailing update T(t0.., t0..) -= P P' (lower tiles) ----
+            smem_tile_gemm_nt<true, true>(T, t0, t0, POTRF_NB - t0, POTRF_NB - t0, T, t0, j0, T, t0, j0, DIAG_PANEL, -1.0, tid);
+            __syncthreads();
+        }
     }
     {
         const int i = tid & (POTRF_NB - 1);
         if (i < nb)
             for (int k = tid >> 7; k < nb; k += DIAG_THREADS / POTRF_NB)
-                A[i + (long)k * ld] = T_(i, k);    // strict upper of the block becomes 0
+                A[i + (long)k * ld] = T_(i, k);        // strict upper of the block becomes 0
     }
-    __syncthreads();
-    // in-place inverse of lower-triangular T (dtrti2, columns from the right)
-    const int part = tid & 3, row = tid >> 2;      // 4 threads per row
-    for (int j = nb - 1; j >= 0; --j) {
-        const double ljj = T_(j, j);
-        for (int i = j + 1 + tid; i < nb; i += DIAG_THREADS) xv[i] = T_(i, j);
+    // ---- blocked triangular inverse: W holds inv of the 16 x 16 diagonal blocks; merge pairs 16 -> 32 -> 64 -> 128.
+    //      X = L21 * W11 goes through the (now free) strict upper part of T: block (o.., o+b..)  ----
+    for (int b = DIAG_PANEL; b < POTRF_NB; b *= 2) {
+        // X(o+b.., o..) = L21 * W11 for every pair, stored transposed-free in T's upper block region (rows o.., cols o+b..)
+        for (int o = 0; o + b < POTRF_NB; o += 2 * b) {
+            // Xt(c, r) := X(r, c) cannot alias the lower part; keep X in T(o + c, o + b + r) = upper block (o.., o+b..)
+            // computed as Xt = W11' * L21'  ==  C(i = c, j = r) = sum_k W11(k, c) L21(r, k): NT form needs A(i,k) = W11(k,i).
+            // Simpler: compute X directly into the upper block with a plain loop tiling over (r, c).
+            const int tr = b >> 2, tc = b >> 2;
+            for (int tile = tid; tile < tr * tc; tile += DIAG_THREADS) {
+                const int r0 = (tile % tr) * 4, c0 = (tile / tr) * 4;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.0;
+                for (int k = c0; k < b; ++k) {                       // W11(k, c) = 0 for k < c
+                    double lv[4], wv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { lv[a] = T_(o + b + r0 + a, o + k); wv[a] = WG_(o + k, o + c0 + a); }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(lv[a], wv[bb], acc[a][bb]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) T_(o + c0 + bb, o + b + r0 + a) = acc[a][bb];   // X(r, c) kept at T(c, b + r)
+            }
+        }
         __syncthreads();
-        double acc = 0.0;
-        if (row > j && row < nb)
-            for (int k = j + 1 + part; k <= row; k += 4) acc += T_(row, k) * xv[k];
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (part == 0) {
-            if (row > j && row < nb) T_(row, j) = -acc / ljj;
-            else if (row == j) T_(j, j) = 1.0 / ljj;
+        for (int o = 0; o + b < POTRF_NB; o += 2 * b) {
+            // W21(r, c) = - sum_k W22(r, k) X(k, c),  W22(r, k) = 0 for k > r
+            const int tr = b >> 2, tc = b >> 2;
+            for (int tile = tid; tile < tr * tc; tile += DIAG_THREADS) {
+                const int r0 = (tile % tr) * 4, c0 = (tile / tr) * 4;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.0;
+                for (int k = 0; k < r0 + 4; ++k) {
+                    double wv[4], xv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { wv[a] = WG_(o + b + r0 + a, o + b + k); xv[a] = T_(o + c0 + a, o + b + k); }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(wv[a], xv[bb], acc[a][bb]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) W_(o + b + r0 + a, o + c0 + bb) = -acc[a][bb];
+            }
         }
         __syncthreads();
     }
     {
         const int i = tid & (POTRF_NB - 1);
         for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB)
-            inv[i + (long)k * POTRF_NB] = (i < nb && k < nb && i >= k) ? T_(i, k) : 0.0;
+            inv[i + (long)k * POTRF_NB] = (i < nb && k < nb && i >= k) ? W_(i, k) : 0.0;
+    }
+#undef WG_
+    {
     }
 #undef T_
+#undef W_
+#undef D_
+#undef I_
 }
 
 int potrf_lower(kb_ctx* ctx, double* A, long ld, int p, double* invdiag, int* d_fail) {

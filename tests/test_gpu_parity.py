@@ -376,3 +376,50 @@ def test_modelX_group_one_shot(kb, ctx):
     assert res.Xko.shape == (n, m * p)
     with pytest.raises(kb.KnockoffsError):                              # group.jl:119-120
         kb.modelX_gaussian_group_knockoffs(X, "maxent", groups[:-1], np.zeros(p), Sigma, ctx=ctx)
+
+
+# ---- BASELINE-size cases ---------------------------------------------------------------------------------
+def test_config2_maxent_p2000_matches_oracle(kb, ctx):
+    """BASELINE configs[1]: AR(1) rho = 0.5, p = 2000, :maxent, m = 1 -- full solve against the C oracle."""
+    Sigma = kb.harness.ar1_sigma(2000, 0.5)
+    s0 = ko.solve_equi(Sigma, 1)
+    want = c_oracle.solve_ccd(Sigma, "maxent", m=1, s_init=s0, lapack_init=True)
+    got, info = kb.solve_s(Sigma, "maxent", m=1, s_init=s0, ctx=ctx, return_info=True)
+    assert info["sweeps"] == want["sweeps"] and rel(got, want["s"]) < S_RTOL
+    # K4 anchor (test/compare_knockpy.ipynb cell 9): interior value of the rho = 0.5 ME solution is p-independent
+    assert abs(got[1000] - 0.485332) < 2e-6
+
+
+def test_config3_full_size_properties(kb, ctx):
+    """BASELINE configs[2] at full size (block-equicorrelated, p = 5000, m = 5): too large for the oracle's full
+    solve in a test, so size-independent properties: feasibility (PSD of kappa*Sigma - S, 0 <= s <= 1), exchangeability
+    of the solution under the block symmetry, first-sweep agreement with the oracle on a bounded number of
+    coordinates, and the objective ordering MVR(obj at s_mvr) <= MVR(obj at s_equi)."""
+    p, m = 5000, 5
+    kap = (m + 1) / m
+    Sigma = kb.harness.block_sigma(p, 10, 0.5, 0.25)
+    s0 = np.full(p, min(1.0, kap * 0.5))                         # lambda_min of this family is 1 - rho = 0.5
+    s, info = kb.solve_s(Sigma, "mvr", m=m, s_init=s0, ctx=ctx, return_info=True)
+    assert np.all(s > 0) and np.all(s <= 1)
+    assert np.linalg.eigvalsh(kap * Sigma - np.diag(s)).min() > -1e-8
+    # all variables are exchangeable up to sweep-order effects: at convergence (tol 1e-6) the entries agree to ~1e-5
+    assert s.max() - s.min() < 1e-4
+    # bounded oracle sample: the first 300 coordinates of sweep 1 (reference arithmetic) vs the GPU's first sweep
+    want = c_oracle.solve_ccd(Sigma, "mvr", m=m, s_init=s0, max_coords=300, lapack_init=True)
+    got1 = kb.solve_s(Sigma, "mvr", m=m, s_init=s0, niter=1, ctx=ctx)
+    assert rel(got1[:300], want["s"][:300]) < S_RTOL
+
+    def mvr_obj(sv):
+        # m^2 tr(S^-1) + tr((kappa Sigma - S)^-1)   (group.jl:27)
+        return m * m * np.sum(1.0 / sv) + np.trace(np.linalg.inv(kap * Sigma - np.diag(sv)))
+    assert mvr_obj(s) < mvr_obj(s0 * 0.999)
+
+
+def test_gram_on_dosage_data(kb, ctx):
+    """config-5 style input: 0/1/2 dosages (integers in FP64): the Gram of integers is exact up to the final division."""
+    X = kb.harness.dosage_X(6000, 300, 20260005)
+    G, mu = kb.gram(X, center=False, denom=1.0, ctx=ctx)
+    assert np.array_equal(G, X.T @ X)                          # integer sums < 2^53: bit-exact
+    Gc, mu = kb.gram(X, center=True, ctx=ctx)
+    Xc = X - X.mean(0)
+    assert np.max(np.abs(Gc - Xc.T @ Xc / X.shape[0])) < 1e-12
