@@ -167,6 +167,13 @@ int kb_gram_partial_dev(kb_ctx* ctx, const double* dX, int64_t n_local, int64_t 
 int kb_gram_finish_dev(kb_ctx* ctx, double* dG, double* dcolsum, int64_t n_total, int64_t p,
                        int32_t center, double denom);
 
+/* Σ̂ = cov(LinearShrinkage(DiagonalUnequalVariance(), :lw), X) and μ̂ = mean(X, dims=1) -- the default
+ * covariance_approximator of the 2-argument entry (modelX.jl:43-50; CovarianceEstimation.jl is not vendored:
+ * restated from the published Ledoit-Wolf / Schäfer-Strimmer target-D formula).
+ * shrinkage_out receives the intensity λ. */
+int kb_cov_shrink_lw(kb_ctx* ctx, const double* X, int64_t n, int64_t p, double* Sigma_out, double* colmean_out,
+                     double* shrinkage_out);
+
 /* ---- (3) conditional-covariance factor ------------------------------------------------------
  * Replaces modelX.jl:106-120: ΣinvS = inv(Symmetric Σ)·S, C = 2S − S·ΣinvS and the Cholesky factor
  * used for the noise.  S is a length-p vector (Diagonal(s)) if s_is_diag, else dense p x p.

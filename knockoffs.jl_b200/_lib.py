@@ -69,6 +69,7 @@ SIGNATURES = {
     "kb_gram": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _d, _vp, _vp]),
     "kb_gram_partial_dev": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "kb_gram_finish_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i32, _d]),
+    "kb_cov_shrink_lw": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, c_double_p]),
     "kb_cond_factor": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "kb_cond_factor_dev": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "kb_sample": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _u64, _i64, _vp]),

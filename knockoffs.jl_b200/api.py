@@ -168,6 +168,19 @@ def gram(X, center=True, denom=None, ctx: Optional[Context] = None):
     return G, mu
 
 
+def cov_shrink_lw(X, ctx: Optional[Context] = None):
+    """``cov(LinearShrinkage(DiagonalUnequalVariance(), :lw), X)`` and ``vec(mean(X, dims=1))`` -- the default
+    covariance_approximator of the 2-argument entry (src/modelX.jl:43-50).  Returns (Sigma, mu, lambda)."""
+    ctx = ctx or default_context()
+    X = _f(X)
+    n, p = X.shape
+    Sig = np.empty((p, p), order="F")
+    mu = np.empty(p)
+    lam = C.c_double()
+    check(ctx.h, ctx._lib.kb_cov_shrink_lw(ctx.h, _ptr(X), n, p, _ptr(Sig), _ptr(mu), C.byref(lam)))
+    return Sig, mu, lam.value
+
+
 def cond_factor(Sigma, S, m=1, ctx: Optional[Context] = None):
     """ΣinvS and the factor blocks of src/modelX.jl:106-120.  ``S`` is a vector (``Diagonal(s)``) or a
     dense p x p matrix.  Returns (SigmaInvS, Lblocks) with Lblocks of shape (p, p, 2m-1):
@@ -242,8 +255,8 @@ def modelX_gaussian_knockoffs(X, method, mu=None, Sigma=None, m=1, Z=None, seed=
                               ctx: Optional[Context] = None, **kwargs) -> GaussianKnockoff:
     """``modelX_gaussian_knockoffs(X, method, μ, Σ; m, kwargs...)`` -- src/modelX.jl:53-66: one library call
     (solve_s -> conditional factor -> sampling; intermediates never leave the device).
-    With ``mu``/``Sigma`` omitted this is the 2-argument entry (src/modelX.jl:39-51) with the sample
-    covariance computed on the device."""
+    With ``mu``/``Sigma`` omitted this is the 2-argument entry (src/modelX.jl:39-51): Σ̂ is the Ledoit-Wolf
+    linear-shrinkage estimate (two device Grams) and μ̂ the column means."""
     ctx = ctx or default_context()
     X = _f(X)
     n, p = X.shape
@@ -253,7 +266,7 @@ def modelX_gaussian_knockoffs(X, method, mu=None, Sigma=None, m=1, Z=None, seed=
     if (mu is None) != (Sigma is None):
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "give both mu and Sigma, or neither")
     if Sigma is None:
-        Sigma, mu = gram(X, center=True, ctx=ctx)
+        Sigma, mu, _ = cov_shrink_lw(X, ctx=ctx)                    # modelX.jl:47-49
     Sigma = _f(Sigma)
     mu = np.ascontiguousarray(mu, dtype=np.float64)
     if Sigma.shape != (p, p) or mu.shape != (p,):

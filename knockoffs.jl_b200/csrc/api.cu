@@ -315,6 +315,54 @@ int kb_gram(kb_ctx* ctx, const double* X, int64_t n, int64_t p, int32_t center, 
     return KB_OK;
 }
 
+// Σ̂ = cov(LinearShrinkage(DiagonalUnequalVariance(), :lw), X), μ̂ = column means  (modelX.jl:43-50).  Two passes
+// over the host matrix: (1) column sums + raw Gram, (2) Gram of the squared centred entries.
+int kb_cov_shrink_lw(kb_ctx* ctx, const double* X, int64_t n, int64_t p, double* Sigma_out, double* colmean_out,
+                     double* shrinkage_out) {
+    if (!ctx) return bad_ctx();
+    if (!X || !Sigma_out || p < 1 || n < 2) return set_error(ctx, KB_ERR_INVALID, "cov_shrink_lw: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const long ld = (p + 1) & ~1L;
+    long chunk = 32768;
+    if (chunk > n) chunk = (n + 1) & ~1L;
+    double *dG, *dG2, *dcs, *dXc[2], *dY;
+    KB_TRY(sc.alloc(&dG, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dG2, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dcs, p));
+    KB_TRY(sc.alloc(&dY, (size_t)chunk * p));
+    for (int b = 0; b < 2; ++b) KB_TRY(sc.alloc(&dXc[b], (size_t)chunk * p));
+    KB_TRY(fill_zero(ctx, dG, (size_t)ld * p));
+    KB_TRY(fill_zero(ctx, dG2, (size_t)ld * p));
+    KB_TRY(fill_zero(ctx, dcs, p));
+    cudaEvent_t* ev_h2d = ctx->pipe_ev;
+    cudaEvent_t* ev_comp = ctx->pipe_ev + 2;
+    for (int pass = 0; pass < 2; ++pass) {
+        long i = 0;
+        for (long r0 = 0; r0 < n; r0 += chunk, ++i) {
+            const int b = (int)(i & 1);
+            const long rows = std::min(chunk, (long)n - r0);
+            if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
+            KB_TRY(h2d_matrix(ctx, X + r0, n, dXc[b], chunk, rows, p, ctx->stream_h2d));
+            KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
+            KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
+            if (pass == 0) KB_TRY(gram_partial_dev(ctx, dXc[b], rows, chunk, (int)p, dG, ld, dcs, 1));
+            else KB_TRY(gram_sq_partial_dev(ctx, dXc[b], rows, chunk, (int)p, dcs, dY, chunk, dG2, ld, 1));
+            KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
+        }
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (pass == 0) KB_TRY(gram_finish_dev(ctx, dG, ld, dcs, (long)n, (int)p, 1, (double)n));   // S = Xc'Xc/n, dcs -> means
+    }
+    double lam = 0.0;
+    KB_TRY(lw_finish_dev(ctx, dG, ld, dG2, ld, (int)p, (long)n, &lam));
+    KB_TRY(d2h_matrix(ctx, dG, ld, Sigma_out, p, p, p, ctx->stream));
+    if (colmean_out) KB_CUDA(ctx, cudaMemcpyAsync(colmean_out, dcs, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (shrinkage_out) *shrinkage_out = lam;
+    return KB_OK;
+}
+
 // ---- (3) conditional factor -----------------------------------------------------------------------
 int kb_cond_factor_dev(kb_ctx* ctx, const double* dSigma, int64_t p, const double* dS, int32_t s_is_diag, int32_t m,
                        double* dSigmaInvS, double* dLblocks) {

@@ -4,6 +4,7 @@
 #include "linalg.cuh"
 #include <algorithm>
 #include <cmath>
+#include <vector>
 
 namespace kb {
 
@@ -471,6 +472,84 @@ int gram_finish_dev(kb_ctx* ctx, double* dG, long ldg, double* dcolsum, long n_t
         ctx->launches++;
     }
     KB_CUDA(ctx, cudaGetLastError());
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ledoit-Wolf linear shrinkage toward diag(S)  (CovarianceEstimation.jl LinearShrinkage(DiagonalUnequalVariance(), :lw),
+// the default covariance_approximator of the 2-argument entry, modelX.jl:43-50).  Restated from the published
+// algorithm (the package is not under /root/reference: parity unpinned):
+//   S = Xc'Xc / n,  pi_ij = (1/n) sum_k (x_ki x_kj)^2 − S_ij^2,  lambda = clamp( (sum_{i≠j} pi_ij / n) / sum_{i≠j} S_ij^2, 0, 1 ),
+//   Sigma = (1 − lambda) S + lambda diag(S).
+// Both Grams (of Xc and of Xc∘Xc) run on the DMMA GEMM and shard by rows like kb_gram.
+// ------------------------------------------------------------------------------------------------
+// Y = (X − mean)^2 for a row slab
+__global__ void centered_square_kernel(const double* X, long n, long ldx, int p, const double* mean, double* Y, long ldy) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = n * p;
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long i = idx % n, c = idx / n;
+        const double d = X[i + c * ldx] - mean[c];
+        Y[i + c * ldy] = d * d;
+    }
+}
+int gram_sq_partial_dev(kb_ctx* ctx, const double* dX, long n, long ldx, int p, const double* dmean, double* dY, long ldy,
+                        double* dG2, long ldg, int accumulate) {
+    if (n <= 0) return KB_OK;
+    centered_square_kernel<<<ew_grid2(ctx, n * p), 256, 0, ctx->stream>>>(dX, n, ldx, p, dmean, dY, ldy);
+    ctx->launches++;
+    KB_CUDA(ctx, cudaGetLastError());
+    return gemm1(ctx, A_KCONTIG, B_KCONTIG, p, p, (int)n, 1.0, dY, ldy, dY, ldy, accumulate ? 1.0 : 0.0, dG2, ldg, 0, 1, 0);
+}
+// sums over the strict lower triangle: out[0] += sum (G2_ij / n − S_ij^2), out[1] += sum S_ij^2
+__global__ void lw_sums_kernel(const double* S, long lds, const double* G2, long ldg, int p, double n, double* out) {
+    __shared__ double r0[256], r1[256];
+    double a = 0.0, b = 0.0;
+    const long total = (long)p * p;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % p), k = (int)(idx / p);
+        if (i > k) {
+            const double s = S[i + (long)k * lds];
+            a += G2[i + (long)k * ldg] / n - s * s;
+            b += s * s;
+        }
+    }
+    r0[threadIdx.x] = a; r1[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[2 * blockIdx.x] = r0[0]; out[2 * blockIdx.x + 1] = r1[0]; }
+}
+__global__ void lw_shrink_kernel(double* S, long lds, int p, double lambda) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)p * p;
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % p), k = (int)(idx / p);
+        if (i != k) S[i + (long)k * lds] *= (1.0 - lambda);
+    }
+}
+// dS: finished covariance (full symmetric, kb_gram_finish_dev output); dG2: raw sums of the squared-centred Gram
+// (lower triangle valid).  Writes the shrunk covariance into dS and returns lambda.
+int lw_finish_dev(kb_ctx* ctx, double* dS, long lds, const double* dG2, long ldg, int p, long n_total, double* lambda_out) {
+    Scope sc(ctx);
+    const int nb = 256;
+    double* dout;
+    KB_TRY(sc.alloc(&dout, 2 * nb));
+    lw_sums_kernel<<<nb, 256, 0, ctx->stream>>>(dS, lds, dG2, ldg, p, (double)n_total, dout);
+    ctx->launches++;
+    std::vector<double> h(2 * nb);
+    KB_CUDA(ctx, cudaMemcpyAsync(h.data(), dout, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double num = 0.0, den = 0.0;
+    for (int i = 0; i < nb; ++i) { num += h[2 * i]; den += h[2 * i + 1]; }
+    double lam = (den > 0.0) ? (num / (double)n_total) / den : 0.0;     // the factor 2 of (i,j)/(j,i) cancels
+    lam = lam < 0.0 ? 0.0 : (lam > 1.0 ? 1.0 : lam);
+    lw_shrink_kernel<<<ew_grid2(ctx, (long)p * p), 256, 0, ctx->stream>>>(dS, lds, p, lam);
+    ctx->launches++;
+    KB_CUDA(ctx, cudaGetLastError());
+    *lambda_out = lam;
     return KB_OK;
 }
 

@@ -49,6 +49,11 @@ int gram_partial_dev(kb_ctx* ctx, const double* dX, long n, long ldx, int p, dou
                      int accumulate);
 int gram_finish_dev(kb_ctx* ctx, double* dG, long ldg, double* dcolsum, long n_total, int p, int center, double denom);
 
+// Ledoit-Wolf shrinkage pieces (pipeline.cu)
+int gram_sq_partial_dev(kb_ctx* ctx, const double* dX, long n, long ldx, int p, const double* dmean, double* dY, long ldy,
+                        double* dG2, long ldg, int accumulate);
+int lw_finish_dev(kb_ctx* ctx, double* dS, long lds, const double* dG2, long ldg, int p, long n_total, double* lambda_out);
+
 // dense helpers on matrices given by their upper triangle (Symmetric(.), uplo = :U)
 int spd_inverse_dev(kb_ctx* ctx, const double* dA_upper, long lda, int p, double* dOut, long ldo);
 int potrf_dev(kb_ctx* ctx, const double* dA_upper, long lda, int p, double* dL, long ldl);

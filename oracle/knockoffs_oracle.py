@@ -329,6 +329,22 @@ def condition(X, mu, Sigma, S, m=1, Z=None, rng=None):
     return np.tile(mui, (1, m)) + Z @ L                  # :118-121
 
 
+def cov_shrink_lw(X):
+    """cov(LinearShrinkage(DiagonalUnequalVariance(), :lw), X) as used at src/modelX.jl:43,47.  CovarianceEstimation.jl
+    is NOT under /root/reference (parity unpinned): restated from the published Ledoit-Wolf formula with the
+    diagonal (unequal variance) target, uncorrected S = Xc'Xc/n:
+    lambda = clamp( sum_{i!=j} Var^(s_ij) / sum_{i!=j} s_ij^2, 0, 1 ),  Var^(s_ij) = ((1/n) sum_k (x_ki x_kj)^2 - s_ij^2) / n."""
+    n, p = X.shape
+    mu = X.mean(0)
+    Xc = X - mu
+    S = Xc.T @ Xc / n
+    pi = (Xc ** 2).T @ (Xc ** 2) / n - S ** 2
+    off = ~np.eye(p, dtype=bool)
+    lam = float(np.clip(pi[off].sum() / n / np.sum(S[off] ** 2), 0.0, 1.0))
+    Sig = (1 - lam) * S + lam * np.diag(np.diag(S))
+    return Sig, mu, lam
+
+
 def modelX_gaussian_knockoffs(X, method, mu, Sigma, m=1, Z=None, **kw):
     """src/modelX.jl:53-66.  Returns (Xko, s)."""
     s = solve_s(Sigma, method, m=m, **kw)

@@ -423,3 +423,21 @@ def test_gram_on_dosage_data(kb, ctx):
     Gc, mu = kb.gram(X, center=True, ctx=ctx)
     Xc = X - X.mean(0)
     assert np.max(np.abs(Gc - Xc.T @ Xc / X.shape[0])) < 1e-12
+
+
+def test_ledoit_wolf_shrinkage_and_two_argument_entry(kb, ctx):
+    """2-argument entry (modelX.jl:39-51): LW-shrunk covariance (row N1) + column means on the device."""
+    rng = np.random.default_rng(21)
+    n, p = 150, 200                                            # p > n: the case the reference's docs motivate
+    Sigma = toeplitz(p, 0.5)
+    X = np.asfortranarray(rng.standard_normal((n, p)) @ np.linalg.cholesky(Sigma).T + rng.standard_normal(p))
+    want_S, want_mu, want_lam = ko.cov_shrink_lw(X)
+    S, mu, lam = kb.cov_shrink_lw(X, ctx=ctx)
+    assert abs(lam - want_lam) < 1e-10 and 0 < lam < 1
+    assert np.max(np.abs(S - want_S)) < 1e-10 and np.max(np.abs(mu - want_mu)) < 1e-12
+    assert np.linalg.eigvalsh(S).min() > 0                      # the point of shrinking (runtests.jl:118-154)
+    Z = np.asfortranarray(rng.standard_normal((n, p)))
+    res = kb.modelX_gaussian_knockoffs(X, "maxent", Z=Z, ctx=ctx)
+    want_X, want_s = ko.modelX_gaussian_knockoffs(X, "maxent", want_mu, want_S, Z=Z)
+    assert rel(res.s, want_s) < 1e-7 and np.max(np.abs(res.Xko - want_X)) < 1e-7
+    assert np.all(res.s >= 0) and np.linalg.eigvalsh(2 * res.Sigma - np.diag(res.s)).min() > -1e-8
