@@ -144,6 +144,19 @@ void kb_default_group_opts(kb_group_opts* opts);
 int kb_solve_s_group(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups, int32_t method, double m,
                      const kb_group_opts* opts, const double* V, int64_t nv, double* S_out, double* obj_out,
                      kb_group_info* info);
+/* Multi-GPU form for a BLOCK-DIAGONAL Σ (BASELINE configs[3]): each rank passes its own diagonal
+ * block(s) (no group straddles ranks).  All ranks sweep in lockstep and call `reduce` -- an all-reduce of a few
+ * doubles (NCCL / MPI / anything) -- where the reference takes a GLOBAL decision: the shared equi γ
+ * (min of the blocks' λmin, group.jl:490-491), the per-sweep convergence test on the summed objective and the
+ * overall max δ (group.jl:1207-1212 ...), the SDP quick return (group.jl:982-984).  The union of the ranks'
+ * S blocks equals the single-GPU solution of the whole matrix; obj_local_out is this shard's part of the objective. */
+#define KB_REDUCE_MIN 0
+#define KB_REDUCE_SUM 1
+#define KB_REDUCE_MAX 2
+typedef int (*kb_reduce_fn)(void* user, int32_t op, double* vals, int32_t n);   /* in place; 0 = ok */
+int kb_solve_s_group_sharded(kb_ctx* ctx, const double* Sigma_block, int64_t p, const int64_t* groups, int32_t method,
+                             double m, const kb_group_opts* opts, const double* V, int64_t nv, kb_reduce_fn reduce,
+                             void* user, double* S_out, double* obj_local_out, kb_group_info* info);
 /* `modelX_gaussian_group_knockoffs(X, method, groups, μ, Σ; m, kwargs...)` (group.jl:109-127):
  * S = solve_s_group(...), X̃ = condition(X, μ, Σ, S; m). */
 int kb_modelx_gaussian_group_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* groups,

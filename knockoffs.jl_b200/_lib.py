@@ -63,6 +63,8 @@ SIGNATURES = {
     "kb_default_group_opts": (None, [C.POINTER(GroupOpts)]),
     "kb_solve_s_group": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _d, C.POINTER(GroupOpts), _vp, _i64, _vp, c_double_p,
                                    C.POINTER(GroupInfo)]),
+    "kb_solve_s_group_sharded": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _d, C.POINTER(GroupOpts), _vp, _i64, _vp, _vp,
+                                           _vp, c_double_p, C.POINTER(GroupInfo)]),
     "kb_modelx_gaussian_group_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32,
                                                      C.POINTER(GroupOpts), _vp, _i64, _vp, _u64, _i64, _vp, _vp,
                                                      c_double_p, C.POINTER(GroupInfo)]),
@@ -81,6 +83,9 @@ SIGNATURES = {
     "kb_test_spd_inverse": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_randn": (C.c_int, [_vp, _u64, _i64, _i64, _i64, _vp]),
 }
+
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32)
+KB_REDUCE_MIN, KB_REDUCE_SUM, KB_REDUCE_MAX = 0, 1, 2
 
 _lib = None
 

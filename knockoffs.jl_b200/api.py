@@ -361,6 +361,38 @@ def solve_s_group(Sigma, groups, method, m=1, V=None, ctx: Optional[Context] = N
     return out + (d,) if return_info else out
 
 
+def solve_s_group_sharded(Sigma_block, groups, method, reduce, m=1, V=None, ctx: Optional[Context] = None, **kwargs):
+    """One rank's part of ``solve_s_group`` on a block-diagonal Σ (kb_solve_s_group_sharded).
+    ``reduce(op, values)`` must all-reduce the numpy array ``values`` IN PLACE across the ranks holding the other
+    diagonal blocks (op: 0 = min, 1 = sum, 2 = max).  Returns (S_block, obj_local, info)."""
+    ctx = ctx or default_context()
+    Sigma_block = _f(Sigma_block)
+    p = Sigma_block.shape[0]
+    groups = np.ascontiguousarray(groups, dtype=np.int64)
+    opts = make_group_opts(**kwargs)
+    info = GroupInfo()
+    Vf = None if V is None else _f(V)
+
+    def _hook(user, op, vals, n):
+        try:
+            arr = np.ctypeslib.as_array(vals, shape=(n,))
+            reduce(int(op), arr)
+            return 0
+        except Exception:                       # never let an exception cross the C boundary
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    cb = _lib.REDUCE_FN(_hook)
+    S = np.empty((p, p), order="F")
+    obj = C.c_double()
+    rc = ctx._lib.kb_solve_s_group_sharded(ctx.h, _ptr(Sigma_block), p, _ptr(groups), _group_method_id(method), float(m),
+                                           C.byref(opts), _ptr(Vf), 0 if Vf is None else Vf.shape[1],
+                                           C.cast(cb, C.c_void_p), None, _ptr(S), C.byref(obj), C.byref(info))
+    check(ctx.h, rc)
+    return S, obj.value, _group_info_dict(info, str(method).lstrip(":"))
+
+
 @dataclass
 class GaussianGroupKnockoff:
     """src/struct.jl:24-34."""

@@ -223,7 +223,18 @@ int kb_solve_s_group(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t*
     if (!Sigma || !groups || !S_out || p < 1 || p > 46000 || nv < 0 || nv > 0x3fffffff)
         return set_error(ctx, KB_ERR_INVALID, "solve_s_group: bad arguments");
     DeviceGuard g(ctx->device);
-    return solve_s_group_host(ctx, Sigma, (int)p, groups, method, m, opts, V, (int)nv, S_out, obj_out, info);
+    return solve_s_group_host(ctx, Sigma, (int)p, groups, method, m, opts, V, (int)nv, nullptr, nullptr, S_out, obj_out, info);
+}
+
+int kb_solve_s_group_sharded(kb_ctx* ctx, const double* Sigma_block, int64_t p, const int64_t* groups, int32_t method,
+                             double m, const kb_group_opts* opts, const double* V, int64_t nv, kb_reduce_fn reduce,
+                             void* user, double* S_out, double* obj_local_out, kb_group_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma_block || !groups || !S_out || !reduce || p < 1 || p > 46000 || nv < 0 || nv > 0x3fffffff)
+        return set_error(ctx, KB_ERR_INVALID, "solve_s_group_sharded: bad arguments");
+    DeviceGuard g(ctx->device);
+    return solve_s_group_host(ctx, Sigma_block, (int)p, groups, method, m, opts, V, (int)nv, reduce, user, S_out,
+                              obj_local_out, info);
 }
 
 int kb_modelx_gaussian_group_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* groups,
@@ -237,7 +248,8 @@ int kb_modelx_gaussian_group_knockoffs(kb_ctx* ctx, const double* X, int64_t n, 
     if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
     DeviceGuard g(ctx->device);
     // (S, γs, obj) = solve_s_group(Symmetric(Σ), groups, method; m, kwargs...)      (group.jl:123)
-    KB_TRY(solve_s_group_host(ctx, Sigma, (int)p, groups, method, (double)m, opts, V, (int)nv, S_out, obj_out, info));
+    KB_TRY(solve_s_group_host(ctx, Sigma, (int)p, groups, method, (double)m, opts, V, (int)nv, nullptr, nullptr, S_out,
+                              obj_out, info));
     // X̃ = condition(X, μ, Σ, S; m)                                                  (group.jl:125)
     Scope sc(ctx);
     const size_t pp = (size_t)p * p;

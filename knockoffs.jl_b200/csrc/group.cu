@@ -460,13 +460,8 @@ __global__ void group_sweep_begin_kernel(const GroupDev G) {
     G.state[ST_OBJ_NEW] = G.state[ST_OBJ];
     G.state[ST_MAXD] = 0.0;
 }
-// group.jl:1207-1212 and twins: change = |(obj_new − obj)/obj|; obj = obj_new; converged if change < tol or maxδ < 1e-4
-__global__ void group_sweep_end_kernel(const GroupDev G) {
-    const double obj = G.state[ST_OBJ], obj_new = G.state[ST_OBJ_NEW];
-    const double change = fabs((obj_new - obj) / obj);
-    G.state[ST_OBJ] = obj_new;
-    G.state[ST_CONV] = (change < G.tol || G.state[ST_MAXD] < 1e-4) ? 1.0 : 0.0;
-}
+// obj = obj_new (the convergence test of group.jl:1207-1212 runs on the host, where sharded solves reduce it)
+__global__ void group_sweep_end_kernel(const GroupDev G) { G.state[ST_OBJ] = G.state[ST_OBJ_NEW]; }
 // per-group SDP objectives from the current blocks, group.jl:1015-1020
 __global__ void group_sdp_objectives_kernel(const GroupDev G) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -534,8 +529,18 @@ void default_group_opts(kb_group_opts* o) {
 // Σcor: host, p x p column-major, symmetric, unit diagonal, groups CONTIGUOUS (goff).  Vperm: p x nv host or null.
 // Sblocks_out: ng blocks (stride gmax², ld gmax) on the host.
 int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, const std::vector<int>& goff, int method,
-                           double m, const kb_group_opts& opts, const double* Vperm, int nv_in,
-                           std::vector<double>& Sblocks_out, int* gmax_out, double* obj_out, kb_group_info* info) {
+                           double m, const kb_group_opts& opts, const double* Vperm, int nv_in, kb_reduce_fn reduce,
+                           void* user, std::vector<double>& Sblocks_out, int* gmax_out, double* obj_out,
+                           kb_group_info* info) {
+    // Sharded block-diagonal problems: `reduce` combines a few doubles across the ranks that hold the
+    // other diagonal blocks, so every rank takes the reference's GLOBAL decisions (shared equi γ, convergence on the
+    // summed objective and the overall max δ, the SDP quick return).  reduce == NULL: single problem.
+    auto allreduce = [&](int op, double* vals, int n) -> int {
+        if (!reduce) return KB_OK;
+        const int rc = reduce(user, op, vals, n);
+        if (rc != 0) return set_error(ctx, KB_ERR_CUDA, "group solve: the reduce hook failed (%d)", rc);
+        return KB_OK;
+    };
     const int ng = (int)goff.size() - 1;
     int gmax = 1;
     for (int g = 0; g < ng; ++g) gmax = std::max(gmax, goff[g + 1] - goff[g]);
@@ -652,6 +657,7 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
     KB_CUDA(ctx, cudaGetLastError());
     double lam = 0.0;
     KB_TRY(eigmin_lower_dev(ctx, dB, ld, p, dA, dinvdiag, d_fail, &lam));
+    KB_TRY(allreduce(KB_REDUCE_MIN, &lam, 1));                 // λmin of a block-diagonal matrix = min over its blocks
     const double gamma = std::min(1.0, kappa * lam);
     // ---- initialize_S (group.jl:432-443): S = γ Σ_GG, eigenvalues clipped at 1e-8, halved ----
     std::vector<double> Sblk(bs * ng, 0.0), MSblk(bs * ng, 0.0);
@@ -719,7 +725,11 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
     if (info) { info->obj_init = obj0; info->gamma_equi = gamma; info->n_directions = nv; }
     *obj_out = obj0;
     Sblocks_out = Sblk;
-    if (method == KB_METHOD_SDP_CCD && obj0 < opts.eps) return KB_OK;              // quick return, group.jl:982-984
+    {
+        double tot = obj0;
+        KB_TRY(allreduce(KB_REDUCE_SUM, &tot, 1));
+        if (method == KB_METHOD_SDP_CCD && tot < opts.eps) return KB_OK;           // quick return, group.jl:982-984
+    }
 
     GroupDev G{};
     G.p = p; G.ng = ng; G.gmax = gmax; G.nv = nv; G.method = method; G.ld = ld; G.m = m; G.eps = opts.eps; G.tol = opts.tol;
@@ -743,12 +753,19 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
     };
     int inner_sweeps = 0, outer_done = 0;
     auto end_sweep = [&](int kind, bool* conv) -> int {
-        group_sweep_end_kernel<<<1, 1, 0, st>>>(G);
-        ctx->launches++;
         KB_CUDA(ctx, cudaGetLastError());
         KB_CUDA(ctx, cudaMemcpyAsync(hstate, dstate, sizeof(hstate), cudaMemcpyDeviceToHost, st));
         KB_CUDA(ctx, cudaStreamSynchronize(st));
-        *conv = hstate[ST_CONV] != 0.0;
+        // group.jl:1207-1212 and twins: change = |(obj_new − obj)/obj|, converged if change < tol or max δ < 1e-4 --
+        // on the sums / max over all shards when the problem is sharded
+        double sums[2] = {hstate[ST_OBJ], hstate[ST_OBJ_NEW]}, maxd = hstate[ST_MAXD];
+        KB_TRY(allreduce(KB_REDUCE_SUM, sums, 2));
+        KB_TRY(allreduce(KB_REDUCE_MAX, &maxd, 1));
+        const double change = std::fabs((sums[1] - sums[0]) / sums[0]);
+        *conv = (change < opts.tol || maxd < 1e-4);
+        group_sweep_end_kernel<<<1, 1, 0, st>>>(G);              // obj <- obj_new on the device
+        ctx->launches++;
+        hstate[ST_OBJ] = hstate[ST_OBJ_NEW];
         if (info && inner_sweeps < KB_MAX_TRACE) {
             info->trace_obj[inner_sweeps] = hstate[ST_OBJ];
             info->trace_delta[inner_sweeps] = hstate[ST_MAXD];
@@ -812,8 +829,8 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
 
 
 int solve_s_group_host(kb_ctx* ctx, const double* Sigma, int p, const int64_t* groups, int method, double m,
-                       const kb_group_opts* opts_in, const double* V, int nv, double* S_out, double* obj_out,
-                       kb_group_info* info) {
+                       const kb_group_opts* opts_in, const double* V, int nv, kb_reduce_fn reduce, void* user,
+                       double* S_out, double* obj_out, kb_group_info* info) {
     kb_group_opts opts;
     if (opts_in) opts = *opts_in; else default_group_opts(&opts);
     if (info) memset(info, 0, sizeof(*info));
@@ -853,6 +870,8 @@ int solve_s_group_host(kb_ctx* ctx, const double* Sigma, int p, const int64_t* g
     const int ng = (int)goff.size() - 1;
     std::vector<double> Sperm((size_t)p * p, 0.0);
     double obj = 0.0;
+    if (ng == p && reduce)
+        return set_error(ctx, KB_ERR_INVALID, "sharded group solve needs at least one non-singleton group per shard");
     if (ng == p) {
         // all singletons: the ungrouped problem (group.jl:378-386); group :sdp maps to the CCD solver
         Scope sc(ctx);
@@ -877,7 +896,7 @@ int solve_s_group_host(kb_ctx* ctx, const double* Sigma, int p, const int64_t* g
         kb_group_opts o2 = opts;
         if (method == KB_METHOD_EQUI) { o2.outer_iter = 0; }      // solve_group_equi only (S = γ Σ_GG)
         KB_TRY(group_solve_contiguous(ctx, Scor, p, goff, method == KB_METHOD_EQUI ? KB_METHOD_MAXENT : method, m, o2,
-                                      Vperm.empty() ? nullptr : Vperm.data(), nv, Sblk, &gmax, &obj, info));
+                                      Vperm.empty() ? nullptr : Vperm.data(), nv, reduce, user, Sblk, &gmax, &obj, info));
         const size_t bs = (size_t)gmax * gmax;
         const double scale = (method == KB_METHOD_EQUI) ? 2.0 : 1.0;   // initialize_S halves the equi solution
         for (int g = 0; g < ng; ++g) {

@@ -69,6 +69,37 @@ def solve_many(problems: Sequence, solve_one: Callable, group=None):
     return [out[i] for i in range(len(problems))]
 
 
+def torch_reduce_hook(group=None, device=None):
+    """reduce(op, values) for api.solve_s_group_sharded backed by torch.distributed (NCCL on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    ops = {0: dist.ReduceOp.MIN, 1: dist.ReduceOp.SUM, 2: dist.ReduceOp.MAX}
+
+    def reduce(op, values):
+        t = torch.from_numpy(values.copy())
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=ops[op], group=group)
+        values[:] = t.cpu().numpy()
+    return reduce
+
+
+def solve_s_group_blockdiag(ctx, Sigma_blocks, groups_blocks, method, m=1, group=None, device=None, **kwargs):
+    """Block-diagonal Σ = blockdiag(Sigma_blocks[0], Sigma_blocks[1], ...) with one (or more) diagonal block per
+    rank: this rank solves `Sigma_blocks[rank]` in lockstep with the others.  Returns
+    (S_block_of_this_rank, total_objective)."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    hook = torch_reduce_hook(group, device) if dist.is_initialized() and dist.get_world_size(group) > 1 \
+        else (lambda op, values: None)
+    S, obj, info = api.solve_s_group_sharded(Sigma_blocks[rank], groups_blocks[rank], method, hook, m=m, ctx=ctx, **kwargs)
+    tot = np.array([obj])
+    hook(1, tot)
+    return S, float(tot[0]), info
+
+
 def gram_reference_numpy(X_shards: Sequence[np.ndarray], center=True):
     """Host restatement of the sharded Gram algebra (used by the gloo tests to check the partition logic)."""
     n = sum(x.shape[0] for x in X_shards)

@@ -441,3 +441,61 @@ def test_ledoit_wolf_shrinkage_and_two_argument_entry(kb, ctx):
     want_X, want_s = ko.modelX_gaussian_knockoffs(X, "maxent", want_mu, want_S, Z=Z)
     assert rel(res.s, want_s) < 1e-7 and np.max(np.abs(res.Xko - want_X)) < 1e-7
     assert np.all(res.s >= 0) and np.linalg.eigvalsh(2 * res.Sigma - np.diag(res.s)).min() > -1e-8
+
+
+def _blockdiag(mats):
+    n = sum(a.shape[0] for a in mats)
+    out = np.zeros((n, n), order="F")
+    o = 0
+    for a in mats:
+        out[o:o + a.shape[0], o:o + a.shape[0]] = a
+        o += a.shape[0]
+    return out
+
+
+@pytest.mark.parametrize("method", ["maxent", "mvr", "sdp"])
+def test_sharded_group_solve_equals_full_solve(kb, method):
+    """BASELINE configs[3] logic: block-diagonal Sigma, one LD block per rank, sweeps in lockstep with the reduce hook
+    (global equi gamma, global convergence test).  Two ranks are emulated by two host threads with their own contexts
+    on this GPU; the union of their S blocks must equal the single-context solve of the whole matrix."""
+    import threading
+    from oracle import group_oracle as go
+    (S1, g1), (S2, g2) = _group_problem(6, 5, 0.4, 0.2), _group_problem(5, 4, 0.6, 0.3)
+    full = _blockdiag([S1, S2])
+    groups_full = np.concatenate([g1, g2 + g1.max()])
+    V1, V2 = go.get_PCA_vectors(S1, list(g1)), go.get_PCA_vectors(S2, list(g2))
+    Vfull = _blockdiag_rect(V1, V2)
+    m = 3
+    want_S, _, want_obj = kb.solve_s_group(full, groups_full, method, m=m, V=Vfull, tol=1e-3, ctx=kb.Context(0))
+    slots = [None, None]
+    bar = threading.Barrier(2)
+    out = [None, None]
+
+    def worker(rank, Sig, grp, V):
+        def reduce(op, vals):
+            slots[rank] = vals.copy()
+            bar.wait()
+            both = np.stack(slots)
+            res = both.min(0) if op == 0 else (both.sum(0) if op == 1 else both.max(0))
+            bar.wait()
+            vals[:] = res
+        out[rank] = kb.solve_s_group_sharded(Sig, grp, method, reduce, m=m, V=V, tol=1e-3, ctx=kb.Context(0))
+
+    th = [threading.Thread(target=worker, args=(0, S1, g1, V1)), threading.Thread(target=worker, args=(1, S2, g2, V2))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(120)
+    assert out[0] is not None and out[1] is not None
+    p1 = S1.shape[0]
+    assert np.max(np.abs(out[0][0] - want_S[:p1, :p1])) < 1e-9
+    assert np.max(np.abs(out[1][0] - want_S[p1:, p1:])) < 1e-9
+    assert abs(out[0][1] + out[1][1] - want_obj) < 1e-8 * max(1.0, abs(want_obj))
+    assert out[0][2]["inner_sweeps"] == out[1][2]["inner_sweeps"]
+
+
+def _blockdiag_rect(V1, V2):
+    out = np.zeros((V1.shape[0] + V2.shape[0], V1.shape[1] + V2.shape[1]), order="F")
+    out[:V1.shape[0], :V1.shape[1]] = V1
+    out[V1.shape[0]:, V1.shape[1]:] = V2
+    return out
