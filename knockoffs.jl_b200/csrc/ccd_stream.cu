@@ -437,7 +437,7 @@ static int ccd_stream_launch(kb_ctx* ctx, const CcdParams& P, int* nctas_out) {
         const long per_cta = (total_slots + g - 1) / g + 1;
         const size_t need = base_smem + (size_t)per_cta * sizeof(int2);
         if (need > 227 * 1024) continue;
-        KB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        KB_CUDA(ctx, raise_max_dynamic_smem((const void*)kern, need));
         int per_sm = 0;
         KB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, need));
         if (per_sm >= want || g <= (long)ctx->num_sms * per_sm) { nctas = g; smem = need; }

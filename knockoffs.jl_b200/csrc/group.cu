@@ -744,7 +744,7 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
 
     const size_t step_smem = (size_t)(3 * gmax + 3 * GSTEP_WARPS + 8) * sizeof(double);
     if (step_smem > 200 * 1024) return set_error(ctx, KB_ERR_INVALID, "group size %d too large", gmax);
-    KB_CUDA(ctx, cudaFuncSetAttribute(group_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem));
+    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)group_step_kernel, step_smem));
     const dim3 agrid(ceil_div(ceil_div(p, 2), 256), ceil_div(p, GAPPLY_COLS));
     auto step = [&](int type, int g, int ia, int ib) {
         group_step_kernel<<<1, GSTEP_THREADS, step_smem, st>>>(G, type, g, ia, ib);

@@ -112,4 +112,9 @@ struct Scope {
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per-function state shared by every host thread / context on the
+// device: raise it monotonically under a lock so concurrent contexts (different p, different group sizes) never
+// lower each other's limit between the attribute call and the launch.
+cudaError_t raise_max_dynamic_smem(const void* func, size_t bytes);
+
 }  // namespace kb

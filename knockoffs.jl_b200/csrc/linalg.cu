@@ -1,6 +1,8 @@
 // Dense FP64 building blocks: GEMM launcher, blocked Cholesky, triangular inverse.
 #include "linalg.cuh"
 #include <cstdarg>
+#include <map>
+#include <mutex>
 
 namespace kb {
 
@@ -14,17 +16,24 @@ int set_error(kb_ctx* ctx, int code, const char* fmt, ...) {
     return code;
 }
 
+cudaError_t raise_max_dynamic_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> current;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = current[func];
+    if (bytes <= cur || bytes <= 48 * 1024) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
+
 // ------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------
 template <int AL, int BL, bool VEC>
 static int launch_gemm_t(kb_ctx* ctx, const GemmParams& P) {
-    static bool configured = false;
     auto kern = dgemm_dmma_kernel<AL, BL, VEC>;
-    if (!configured) {
-        KB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
-        configured = true;
-    }
+    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)kern, GEMM_SMEM_BYTES));
     dim3 grid(ceil_div(P.M, GEMM_BM), ceil_div(P.N, GEMM_BN));
     kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(P);
     ctx->launches++;
@@ -370,12 +379,7 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
 }
 
 int potrf_lower(kb_ctx* ctx, double* A, long ld, int p, double* invdiag, int* d_fail) {
-    static bool configured = false;
-    if (!configured) {
-        KB_CUDA(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)DIAG_SMEM));
-        configured = true;
-    }
+    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)potrf_diag_kernel, DIAG_SMEM));
     int blk = 0;
     for (int r0 = 0; r0 < p; r0 += POTRF_NB, ++blk) {
         const int nb = (p - r0 < POTRF_NB) ? p - r0 : POTRF_NB;
