@@ -41,7 +41,10 @@ if rank == 0:
             gfull[b * pb:(b + 1) * pb] = groups[b] + b * (pb // 5)
         t = time.time()
         Sf, _, objf = kb.solve_s_group(full, gfull, method, ctx=ctx)
+        # exactly equicorrelated groups are degenerate: accept/reject ties flip on summation order, so shards other
+        # than the first agree with the full solve at the solver tolerance (objective), not bit for bit
         print(f"single GPU full matrix: obj = {objf:.8g}, wall = {time.time() - t:.2f} s, max|S_shard0 - S_full| = "
-              f"{np.max(np.abs(S - Sf[:pb, :pb])):.3g}, |obj diff| = {abs(obj - objf):.3g}", flush=True)
+              f"{np.max(np.abs(S - Sf[:pb, :pb])):.3g}, rel |obj diff| = {abs(obj - objf) / abs(objf):.3g} (tol 1e-4)", flush=True)
+        assert abs(obj - objf) <= 1e-4 * abs(objf)
 dist.barrier()
 dist.destroy_process_group()
