@@ -228,7 +228,7 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
         // ---- (a) warp 0: 16 x 16 Cholesky + inverse, lane r owns row r (lanes 16..31 idle) ----
         if (warp == 0) {
             const int r = lane;
-            double row[DIAG_PANEL];
+            double row[DIAG_PANEL], dinv[DIAG_PANEL];
 #pragma unroll
             for (int c = 0; c < DIAG_PANEL; ++c) row[c] = (r < DIAG_PANEL && c <= r) ? T_(j0 + r, j0 + c) : 0.0;
 #pragma unroll
@@ -238,8 +238,10 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
                     if (lane == 0 && j0 + c < nb) atomicCAS(fail, 0, base + j0 + c + 1);
                     d = 1.0;
                 }
-                const double ljj = sqrt(d);
-                row[c] = (r == c) ? ljj : row[c] / ljj;                   // column c scaled (rows > c meaningful)
+                // 1/sqrt(d) once (no FP64 divide, no FP64 sqrt sequence on the serial chain); L_cc = d * rsqrt(d)
+                const double rinv = rsqrt(d);
+                dinv[c] = rinv;
+                row[c] = (r == c) ? d * rinv : row[c] * rinv;             // column c scaled (rows > c meaningful)
 #pragma unroll
                 for (int k = c + 1; k < DIAG_PANEL; ++k) {
                     const double lkc = __shfl_sync(0xffffffffu, row[c], k);   // L(k, c)
@@ -266,7 +268,7 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
 #pragma unroll
                     for (int k = 0; k < DIAG_PANEL; ++k)
                         if (k < i) acc = fma(-D_(i, k), (k >= c) ? x[k] : 0.0, acc);
-                    x[i] = (i >= c) ? acc / D_(i, i) : 0.0;
+                    x[i] = (i >= c) ? acc * dinv[i] : 0.0;
                 }
 #pragma unroll
                 for (int i = 0; i < DIAG_PANEL; ++i) {
