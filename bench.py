@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="rows per sampling chunk (0 = library default)")
-    ap.add_argument("--refresh-every", type=int, default=1)
+    ap.add_argument("--refresh-every", type=int, default=-1)
     return ap.parse_args()
 
 

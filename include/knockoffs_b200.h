@@ -42,6 +42,7 @@ extern "C" {
 /* solver execution modes (same mathematics, different kernels) */
 #define KB_MODE_AUTO 0
 #define KB_MODE_STREAM 1  /* persistent kernel, one rank-1 streaming pass over the resident triangle per coordinate */
+#define KB_MODE_BLOCK 2   /* delayed updates: 64 coordinates per rank-64 tensor-core pass over the triangle (AUTO picks this) */
 
 #define KB_MAX_TRACE 128
 
@@ -59,7 +60,7 @@ typedef struct {
     int32_t verbose;     /* per-sweep trace is always returned in kb_solve_info */
     int32_t mode;        /* KB_MODE_* */
     int32_t refresh_every; /* rebuild the device-resident inverse from the current diagonal every k sweeps
-                              (1 = default; 0 = never: the whole solve is ONE kernel launch) */
+                              (-1 = default: 1 in KB_MODE_STREAM, 4 in KB_MODE_BLOCK; 0 = never) */
 } kb_solve_opts;
 
 typedef struct {

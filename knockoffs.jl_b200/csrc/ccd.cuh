@@ -5,6 +5,7 @@
 namespace kb {
 
 constexpr int CCD_SLOT_ROWS = 64;   // rows per slot; the M buffer's leading dimension is a multiple of this
+constexpr int CCD_BLOCK_WIDTH = 64; // coordinates per delayed-update block (ccd_block.cu)
 
 struct CcdParams {
     int p;
@@ -33,5 +34,9 @@ size_t ccd_stream_colbuf_doubles(int p);
 static inline long ccd_stream_ld(int p) { return ((long)p + CCD_SLOT_ROWS - 1) / CCD_SLOT_ROWS * CCD_SLOT_ROWS; }
 // one launch = init kernel + persistent cooperative kernel running P.nsweeps sweeps
 int ccd_stream_run(kb_ctx* ctx, const CcdParams& P, int* nctas_out);
+
+// Blocked (delayed rank-64 update) variant, ccd_block.cu: ONE sweep per call on the same resident inverse.
+size_t ccd_block_work_doubles(int p);
+int ccd_block_run(kb_ctx* ctx, const CcdParams& P, double* work);
 
 }  // namespace kb

@@ -200,6 +200,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmP
 
     const int lr = lane >> 2, lc = lane & 3;
 
+    // beta * Cin enters through the accumulators: all of a thread's Cin loads are issued here, back to back and
+    // ahead of the first k-tile (they overlap the cp.async prologue).  Loading in the epilogue instead serialises
+    // one DRAM round trip per element, because Cin may alias C and every load would have to wait for the
+    // previous store -- that made short-K updates (rank-64/128 passes, Cholesky trailing updates) latency-bound.
+    const bool preload = (P.beta != 0.0 && P.alpha != 0.0);
+    if (preload) {
+        const double r = P.beta / P.alpha;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + wm * 64 + i * 8 + lr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
+                    if (m < P.M && n < P.N && !(P.store_mode == 1 && m < n))
+                        acc[i][j][e] = r * P.Cin[(long)m + (long)n * P.ldcin];
+                }
+            }
+        }
+    }
+
     for (int s = 0; s < P.nseg; ++s) {
         const GemmSeg sg = P.seg[s];
         int kbeg = 0, kend = sg.K;
@@ -274,7 +296,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmP
                 if (n >= P.N) continue;
                 if (P.store_mode == 1 && m < n) continue;
                 double v = P.alpha * acc[i][j][e];
-                if (P.beta != 0.0) v += P.beta * P.Cin[(long)m + (long)n * P.ldcin];
+                if (!preload && P.beta != 0.0) v += P.beta * P.Cin[(long)m + (long)n * P.ldcin];
                 if (P.bias_n) v += P.bias_n[n];
                 P.C[(long)m + (long)n * P.ldc] = v;
             }

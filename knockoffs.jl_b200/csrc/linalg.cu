@@ -1,6 +1,7 @@
 // Dense FP64 building blocks: GEMM launcher, blocked Cholesky, triangular inverse.
 #include "linalg.cuh"
 #include <cstdarg>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -203,7 +204,7 @@ __device__ __forceinline__ void smem_tile_gemm_nt(double* C, int ci0, int cj0, i
 // The triangular inverse is blocked the same way: 16 x 16 diagonal inverses from (a), then recursive doubling
 // W21 = -W22 (L21 W11) at block sizes 16, 32, 64.
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
-potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) {
+potrf_diag_kernel_v1(double* A, long ld, int nb, double* inv, int* fail, int base) {
     extern __shared__ double dsm[];
     double* T = dsm;                                   // T(i,k) at k*DIAG_PITCH + i
     double* W = dsm + POTRF_NB * DIAG_PITCH;           // inverse being assembled (lower)
@@ -380,14 +381,184 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
 #undef I_
 }
 
+// 1/sqrt(d) for d > 0 without the library's FP64 rsqrt/div sequences on the serial pivot chain:
+// single-precision MUFU.RSQ seed (22 bits) + two Newton steps in double (-> < 1 ulp).
+__device__ __forceinline__ double rsqrt_pivot(double d) {
+    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+    double r = (double)rsqrtf((float)d);
+    const double h = 0.5 * d;
+    double e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    e = fma(-h * r, r, 0.5);
+    r = fma(r, e, r);
+    return r;
+}
+
+// v2 of the diagonal-block kernel.  Same contract as v1 (factor nb x nb <= 128 in shared memory, write L back, write
+// inv(L) to `inv`), restructured so the serial chain is ~250 cycles per column instead of ~2500:
+//  * 16-column panels; inside a panel thread i (< 128) owns ROW i of the panel in registers and ALL rows below the
+//    pivot take part in the column-by-column elimination (the panel's TRSM is folded into its factorisation -- no
+//    per-panel 16 x 16 inverse on the chain).  Per column the 16 diagonal-block rows publish their unscaled entries
+//    u_k = T(j0+k, j0+c) (one 128-thread named barrier), every row derives 1/sqrt(u_c) itself and applies
+//    row[k] -= (row[c] r)(u_k r).
+//  * rank-16 trailing update with 4 x 4 register tiles on all 16 warps (as v1).
+//  * inverse afterwards: the eight 16 x 16 diagonal inverses in parallel (one warp each), then the recursive doubling of v1.
+__global__ void __launch_bounds__(DIAG_THREADS, 1)
+potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) {
+    extern __shared__ double dsm[];
+    double* T = dsm;                                   // T(i,k) at k*DIAG_PITCH + i
+    double* W = dsm + POTRF_NB * DIAG_PITCH;           // inverse being assembled (lower, folded)
+    double* ubuf = W + DIAG_PITCH * (POTRF_NB / 2);    // 2 x 16 published column entries
+    double* dinv = ubuf + 2 * DIAG_PANEL;              // 128 reciprocal diagonal entries of L
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#define T_(i, k) T[(k) * DIAG_PITCH + (i)]
+#define W_(i, k) W[wfold((i), (k))]
+#define WG_(i, k) (((i) >= (k)) ? W[wfold((i), (k))] : 0.0)
+    {
+        const int i = tid & (POTRF_NB - 1);
+        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB) {
+            T_(i, k) = (i < nb && k < nb) ? ((i >= k) ? A[i + (long)k * ld] : 0.0) : (i == k ? 1.0 : 0.0);
+            if (i >= k) W_(i, k) = 0.0;
+        }
+    }
+    __syncthreads();
+    for (int jb = 0; jb < DIAG_NPANEL; ++jb) {
+        const int j0 = jb * DIAG_PANEL;
+        if (tid < POTRF_NB) {
+            // ---- panel factorisation + TRSM: thread i owns row i (rows < j0 only keep the barrier count) ----
+            const int i = tid;
+            const int rl = i - j0;                       // row inside the panel's diagonal block if 0 <= rl < 16
+            const bool active = i >= j0;
+            double row[DIAG_PANEL];
+#pragma unroll
+            for (int c = 0; c < DIAG_PANEL; ++c) row[c] = (active && (rl >= DIAG_PANEL || c <= rl)) ? T_(i, j0 + c) : 0.0;
+#pragma unroll
+            for (int c = 0; c < DIAG_PANEL; ++c) {
+                double* ub = ubuf + (c & 1) * DIAG_PANEL;
+                if (rl >= c && rl < DIAG_PANEL) ub[rl] = row[c];          // u_k, k = c..15 (row k of the diagonal block)
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                double d = ub[c];
+                if (!(d > 0.0)) {                                         // also catches NaN
+                    if (i == j0 + c && j0 + c < nb) atomicCAS(fail, 0, base + j0 + c + 1);
+                    d = 1.0;
+                }
+                const double r = rsqrt_pivot(d);
+                if (i == j0 + c) dinv[j0 + c] = r;
+                const double lc = (rl == c) ? d * r : row[c] * r;         // L(i, j0+c)
+                row[c] = lc;
+#pragma unroll
+                for (int k = c + 1; k < DIAG_PANEL; ++k) row[k] = fma(-lc, ub[k] * r, row[k]);
+            }
+            if (active) {
+#pragma unroll
+                for (int c = 0; c < DIAG_PANEL; ++c) T_(i, j0 + c) = (rl >= DIAG_PANEL || c <= rl) ? row[c] : 0.0;
+            }
+        }
+        __syncthreads();
+        const int t0 = j0 + DIAG_PANEL;
+        if (t0 < POTRF_NB) {
+            // ---- trailing update T(t0.., t0..) -= P P' (lower tiles) ----
+            smem_tile_gemm_nt<true, true>(T, t0, t0, POTRF_NB - t0, POTRF_NB - t0, T, t0, j0, T, t0, j0, DIAG_PANEL, -1.0, tid);
+            __syncthreads();
+        }
+    }
+    {
+        const int i = tid & (POTRF_NB - 1);
+        if (i < nb)
+            for (int k = tid >> 7; k < nb; k += DIAG_THREADS / POTRF_NB)
+                A[i + (long)k * ld] = T_(i, k);        // strict upper of the block becomes 0
+    }
+    // ---- 16 x 16 diagonal inverses: warp w < 8 takes block w, lane c < 16 computes column c by forward substitution ----
+    if (warp < DIAG_NPANEL && lane < DIAG_PANEL) {
+        const int j0 = warp * DIAG_PANEL, c = lane;
+        double x[DIAG_PANEL];
+#pragma unroll
+        for (int i = 0; i < DIAG_PANEL; ++i) {
+            double acc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = 0; k < DIAG_PANEL; ++k)
+                if (k < i) acc = fma(-T_(j0 + i, j0 + k), (k >= c) ? x[k] : 0.0, acc);
+            x[i] = (i >= c) ? acc * dinv[j0 + i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < DIAG_PANEL; ++i)
+            if (i >= c) W_(j0 + i, j0 + c) = x[i];
+    }
+    __syncthreads();
+    // ---- blocked triangular inverse: merge pairs 16 -> 32 -> 64 -> 128 (X = L21 W11 parked in T's free upper part) ----
+    for (int b = DIAG_PANEL; b < POTRF_NB; b *= 2) {
+        for (int o = 0; o + b < POTRF_NB; o += 2 * b) {
+            const int tr = b >> 2, tc = b >> 2;
+            for (int tile = tid; tile < tr * tc; tile += DIAG_THREADS) {
+                const int r0 = (tile % tr) * 4, c0 = (tile / tr) * 4;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.0;
+                for (int k = c0; k < b; ++k) {                       // W11(k, c) = 0 for k < c
+                    double lv[4], wv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { lv[a] = T_(o + b + r0 + a, o + k); wv[a] = WG_(o + k, o + c0 + a); }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(lv[a], wv[bb], acc[a][bb]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) T_(o + c0 + bb, o + b + r0 + a) = acc[a][bb];   // X(r, c) kept at T(c, b + r)
+            }
+        }
+        __syncthreads();
+        for (int o = 0; o + b < POTRF_NB; o += 2 * b) {
+            const int tr = b >> 2, tc = b >> 2;
+            for (int tile = tid; tile < tr * tc; tile += DIAG_THREADS) {
+                const int r0 = (tile % tr) * 4, c0 = (tile / tr) * 4;
+                double acc[4][4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.0;
+                for (int k = 0; k < r0 + 4; ++k) {
+                    double wv[4], xv[4];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) { wv[a] = WG_(o + b + r0 + a, o + b + k); xv[a] = T_(o + c0 + a, o + b + k); }
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(wv[a], xv[bb], acc[a][bb]);
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb) W_(o + b + r0 + a, o + c0 + bb) = -acc[a][bb];
+            }
+        }
+        __syncthreads();
+    }
+    {
+        const int i = tid & (POTRF_NB - 1);
+        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB)
+            inv[i + (long)k * POTRF_NB] = (i < nb && k < nb && i >= k) ? W_(i, k) : 0.0;
+    }
+#undef WG_
+#undef T_
+#undef W_
+}
+
 int potrf_lower(kb_ctx* ctx, double* A, long ld, int p, double* invdiag, int* d_fail) {
+    static const bool use_v1 = [] { const char* e = getenv("KB_POTRF_DIAG"); return e && e[0] == '1'; }();
     KB_CUDA(ctx, raise_max_dynamic_smem((const void*)potrf_diag_kernel, DIAG_SMEM));
+    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)potrf_diag_kernel_v1, DIAG_SMEM));
     int blk = 0;
     for (int r0 = 0; r0 < p; r0 += POTRF_NB, ++blk) {
         const int nb = (p - r0 < POTRF_NB) ? p - r0 : POTRF_NB;
         double* Abb = A + r0 + (long)r0 * ld;
         double* inv = invdiag + (size_t)blk * POTRF_NB * POTRF_NB;
-        potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0);
+        if (use_v1) potrf_diag_kernel_v1<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0);
+        else potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0);
         ctx->launches++;
         KB_CUDA(ctx, cudaGetLastError());
         const int rem = p - r0 - nb;

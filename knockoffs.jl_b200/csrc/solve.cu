@@ -116,9 +116,34 @@ static inline int ewg(kb_ctx* ctx, long total) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-// λmin of the symmetric matrix B (lower triangle, ld) by bisection on positive definiteness:
-// B − σI ≻ 0  <=>  σ < λmin, tested with the blocked DMMA Cholesky.  Bracket: Gershgorin bound
-// (or 0 if B ≻ 0) below, min diagonal above.  ~45 factorisations, no host LAPACK anywhere.
+// Root λ of the power-law model h(σ) = C (λ − σ)^α through three points σ0 < σ1 < σ2 with h0 > h1 > h2 > 0
+// (α = 1: an isolated smallest eigenvalue, the last pivot is a simple pole's reciprocal; α = 1/2: the edge of a
+// near-continuous spectrum such as AR(1)).  Returns NaN when the points do not fit the model.
+static double powerlaw_root(const double x[3], const double y[3]) {
+    if (!(y[0] > y[1] && y[1] > y[2] && y[2] > 0.0)) return NAN;
+    const double R = (log(y[0]) - log(y[1])) / (log(y[1]) - log(y[2]));
+    auto F = [&](double lam) { return (log(lam - x[0]) - log(lam - x[1])) / (log(lam - x[1]) - log(lam - x[2])) - R; };
+    double a = x[2] + (x[2] - x[1]) * 1e-12, b = x[2] + (x[2] - x[0]) * 1e6;
+    double fa = F(a);
+    const double fb = F(b);
+    if (!(fa == fa) || !(fb == fb) || fa * fb > 0.0) return NAN;
+    for (int it = 0; it < 200; ++it) {
+        const double mid = x[2] + sqrt((a - x[2]) * (b - x[2]));     // bisection on the log of the distance
+        const double fm = F(mid);
+        if (!(fm == fm)) return NAN;
+        if (fa * fm <= 0.0) b = mid; else { a = mid; fa = fm; }
+        if (b - a <= 1e-15 * fabs(b)) break;
+    }
+    return 0.5 * (a + b);
+}
+
+// λmin of the symmetric matrix B (lower triangle, ld): B − σI ≻ 0  <=>  σ < λmin, tested with the blocked DMMA
+// Cholesky, so every probe is rigorous; the bracket [lo (PD), hi (not PD)] is closed to 2e-13 relative.
+// Probes are placed by extrapolating the LAST PIVOT h(σ) = L_pp(σ)² = 1/[(B − σI)⁻¹]_pp of the successful
+// factorisations (concave, decreasing, zero at λmin): a power-law / secant root estimate is probed just above
+// (expect failure -> hi) or just below (expect success -> lo) by the change of the estimate; any probe that fails
+// to halve the bracket is followed by a plain bisection step, so the worst case is ~bisection (≈ 45
+// factorisations) and isolated / multiple smallest eigenvalues take ≈ 13.  No host LAPACK anywhere.
 int eigmin_lower_dev(kb_ctx* ctx, const double* B, long ld, int p, double* work_A, double* invdiag, int* d_fail,
                      double* lambda_out) {
     double* d_g = nullptr;
@@ -132,31 +157,73 @@ int eigmin_lower_dev(kb_ctx* ctx, const double* B, long ld, int p, double* work_
     double lb = INFINITY, dmin = INFINITY;
     for (int i = 0; i < 64; ++i) { lb = fmin(lb, hg[2 * i]); dmin = fmin(dmin, hg[2 * i + 1]); }
     if (!std::isfinite(lb) || !std::isfinite(dmin)) return set_error(ctx, KB_ERR_NAN, "eigmin: non-finite matrix");
-    auto is_pd = [&](double sigma, bool* pd) -> int {
+    // probe: pd = (B − σI ≻ 0); h = last pivot (valid when pd)
+    auto is_pd = [&](double sigma, bool* pd, double* h) -> int {
         shift_copy_lower_kernel<<<ewg(ctx, (long)p * p), 256, 0, ctx->stream>>>(B, ld, p, sigma, work_A);
         ctx->launches++;
         KB_CUDA(ctx, cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
         KB_TRY(potrf_lower(ctx, work_A, ld, p, invdiag, d_fail));
         int f = 0;
+        double lpp = 0.0;
         KB_CUDA(ctx, cudaMemcpyAsync(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(&lpp, work_A + (size_t)(p - 1) + (size_t)(p - 1) * ld, sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *pd = (f == 0);
+        *h = lpp * lpp;
         return KB_OK;
     };
+    const double tol = 2e-13;
+    static const bool trace_probes = getenv("KB_EIGMIN_TRACE") != nullptr;
     double lo, hi = dmin;   // λmin <= min diagonal
+    double px[3] = {0, 0, 0}, py[3] = {0, 0, 0};   // last PD probes, ascending σ
+    int npts = 0;
+    auto push = [&](double x, double y) {
+        if (npts == 3) { px[0] = px[1]; py[0] = py[1]; px[1] = px[2]; py[1] = py[2]; npts = 2; }
+        px[npts] = x; py[npts] = y; ++npts;
+    };
     bool pd = false;
-    if (lb > 0.0) lo = lb;
-    else {
-        KB_TRY(is_pd(0.0, &pd));
-        lo = pd ? 0.0 : lb - 1e-12 * fabs(lb) - 1e-300;
+    double h = 0.0;
+    if (lb > 0.0) {
+        lo = lb;                                    // Gershgorin: B − lb I is PSD; probe it for h
+        KB_TRY(is_pd(lo, &pd, &h));
+        if (pd) push(lo, h); else lo = lb - 1e-12 * fabs(lb) - 1e-300;
+    } else {
+        KB_TRY(is_pd(0.0, &pd, &h));
+        if (pd) { lo = 0.0; push(0.0, h); }
+        else { lo = lb - 1e-12 * fabs(lb) - 1e-300; hi = fmin(hi, 0.0); }
     }
     if (hi <= lo) { *lambda_out = hi; return KB_OK; }
+    double est_prev = NAN;
+    bool force_bisect = false;
     for (int it = 0; it < 200; ++it) {
+        if (hi - lo <= tol * fmax(fabs(lo), fabs(hi))) break;
+        const double w0 = hi - lo;
         const double mid = 0.5 * (lo + hi);
         if (!(mid > lo && mid < hi)) break;
-        if (hi - lo <= 2e-13 * fmax(fabs(lo), fabs(hi))) break;
-        KB_TRY(is_pd(mid, &pd));
-        if (pd) lo = mid; else hi = mid;
+        double est = NAN;
+        if (npts == 3) est = powerlaw_root(px, py);
+        if (!(est == est) && npts >= 2) {
+            const double a = px[npts - 2], ha = py[npts - 2], b = px[npts - 1], hb = py[npts - 1];
+            if (ha > hb && hb > 0.0) est = b + hb * (b - a) / (ha - hb);       // secant root (>= λmin for concave h)
+        }
+        double sigma = mid;
+        bool guided = false;
+        if (est == est && est >= hi && est - hi <= 0.01 * w0) est = hi;   // root modelled at a known failure: aim just below it
+        if (est == est && est > lo && est <= hi && !force_bisect) {
+            double unc = (est_prev == est_prev) ? fabs(est - est_prev) : 0.25 * (est - lo);
+            unc = fmax(unc, 0.25 * tol * fabs(est));
+            sigma = (hi - est > 4.0 * unc) ? est + 2.0 * unc : est - 2.0 * unc;
+            guided = (sigma > lo && sigma < hi);
+            if (!guided) sigma = mid;
+        }
+        if (est == est) est_prev = est;
+        KB_TRY(is_pd(sigma, &pd, &h));
+        if (pd) { lo = sigma; push(sigma, h); } else hi = sigma;
+        force_bisect = guided && (hi - lo) > 0.5 * w0;
+        if (trace_probes)
+            fprintf(stderr, "[eigmin %2d] %s sigma=%.17g %s h=%.6e est=%.17g width=%.3e\n", it, guided ? "guided" : "bisect", sigma,
+                    pd ? "PD" : "no", pd ? h : 0.0, est, hi - lo);
     }
     *lambda_out = 0.5 * (lo + hi);
     return KB_OK;
@@ -181,7 +248,7 @@ int eigmin_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, double* lambd
 
 void default_solve_opts(kb_solve_opts* o) {
     o->niter = 100; o->tol = 1e-6; o->lambda_min = 1e-6; o->sdp_lambda = 0.5; o->sdp_mu = 0.8;
-    o->robust = 0; o->verbose = 0; o->mode = KB_MODE_AUTO; o->refresh_every = 1;
+    o->robust = 0; o->verbose = 0; o->mode = KB_MODE_AUTO; o->refresh_every = -1;
 }
 
 // dSigma: p x p, leading dimension lds, upper triangle trusted.  d_s_init may be NULL.  d_s_out: p.
@@ -268,17 +335,32 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
         KB_TRY(sc.alloc(&W, (size_t)ld * p));
         KB_TRY(sc.alloc(&Mbuf, (size_t)ld * p));
         KB_TRY(sc.alloc(&work, (size_t)ld * p / 2 + 2 * ld + 64));
-        KB_TRY(sc.alloc(&colbuf, ccd_stream_colbuf_doubles(p)));
+        // execution mode: AUTO = the blocked (delayed rank-64 update) kernels; KB_MODE_STREAM = the persistent
+        // rank-1 streaming kernel.  KB_CCD_MODE=stream|block overrides AUTO (experiments).
+        int mode = (opts.mode == KB_MODE_STREAM) ? KB_MODE_STREAM : KB_MODE_BLOCK;
+        if (opts.mode == KB_MODE_AUTO) {
+            const char* e = getenv("KB_CCD_MODE");
+            if (e && e[0] == 's') mode = KB_MODE_STREAM;
+        }
+        double* blockwork = nullptr;
+        if (mode == KB_MODE_STREAM) KB_TRY(sc.alloc(&colbuf, ccd_stream_colbuf_doubles(p)));
+        else KB_TRY(sc.alloc(&blockwork, ccd_block_work_doubles(p)));
         KB_TRY(fill_zero(ctx, trace, KB_MAX_TRACE));
         KB_TRY(fill_zero(ctx, counters, 8));
         const double shift = (method == KB_METHOD_SDP_CCD) ? 0.0 : opts.lambda_min;
         const double pd = (double)p;
-        const int refresh_every = opts.refresh_every < 0 ? 1 : opts.refresh_every;
+        // rebuild cadence of the resident inverse.  Default: every sweep for the streaming kernel (p rank-1
+        // passes per sweep); for the blocked one (p/64 rank-64 passes per sweep) after the FIRST sweep -- the equi
+        // starting point makes the initial A nearly singular (λmin(A) = λmin option), the inverse built there is the
+        // least accurate one of the whole solve -- and then every 4th sweep.
+        const bool auto_block = (opts.refresh_every < 0 && mode == KB_MODE_BLOCK);
+        const int refresh_every = opts.refresh_every < 0 ? (mode == KB_MODE_STREAM ? 1 : 4) : opts.refresh_every;
         double lam = opts.sdp_lambda;
         double init_ms = 0.0, solve_ms = 0.0;
         int sweeps_done = 0;
         std::vector<double> hs(p);
         bool converged = false;
+        double block_touched = 0.0;
 
         // (re)build M = A^{-1}; first == true also initialises ksig / adiag from s (utilities.jl:140, :237, :309)
         auto build_inverse = [&](bool first, bool* ok) -> int {
@@ -319,12 +401,23 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
         P.status = d_status; P.sweeps_out = d_sweeps; P.trace = trace; P.counters = counters;
 
         while (sweeps_done < opts.niter && !converged && status == KB_OK) {
-            const int chunk = (refresh_every == 0) ? (opts.niter - sweeps_done)
-                                                   : std::min(refresh_every, opts.niter - sweeps_done);
-            if (sweeps_done > 0 && refresh_every > 0) KB_TRY(build_inverse(false, &ok));
+            const int chunk = (mode == KB_MODE_BLOCK) ? 1
+                              : (refresh_every == 0) ? (opts.niter - sweeps_done)
+                                                     : std::min(refresh_every, opts.niter - sweeps_done);
+            if (sweeps_done > 0 && refresh_every > 0 && (sweeps_done % refresh_every == 0 || (auto_block && sweeps_done == 1)))
+                KB_TRY(build_inverse(false, &ok));
             P.nsweeps = chunk; P.sweep0 = sweeps_done; P.sdp_lambda = lam;
             KB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-            KB_TRY(ccd_stream_run(ctx, P, nullptr));
+            if (mode == KB_MODE_STREAM) {
+                KB_TRY(ccd_stream_run(ctx, P, nullptr));
+            } else {
+                KB_CUDA(ctx, cudaMemsetAsync(d_status, 0, sizeof(int), ctx->stream));
+                KB_CUDA(ctx, cudaMemsetAsync(d_sweeps, 0, sizeof(int), ctx->stream));
+                KB_TRY(ccd_block_run(ctx, P, blockwork));
+                // bytes the rank-64 passes move: every block reads + writes the lower 128 x 128 tiles once
+                const double nt = (double)((p + 127) / 128);
+                block_touched += (double)((p + CCD_BLOCK_WIDTH - 1) / CCD_BLOCK_WIDTH) * (nt * (nt + 1) / 2) * 128.0 * 128.0 * 16.0;
+            }
             KB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
             int hsweeps = 0;
             double hcount[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -348,7 +441,7 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
             if (info) {
                 for (int l = 0; l < sweeps_done && l < KB_MAX_TRACE; ++l) info->trace[l] = htrace[l];
                 info->updates = hcount[1];
-                info->touched_bytes = 16.0 * CCD_SLOT_ROWS * hcount[0];
+                info->touched_bytes = (mode == KB_MODE_STREAM) ? 16.0 * CCD_SLOT_ROWS * hcount[0] : block_touched;
                 if (getenv("KB_CCD_PHASES"))
                     fprintf(stderr, "[ccd launch %d: %.2f ms; phases, Mcycles summed over CTAs so far] wait=%.1f stage=%.1f "
                                     "publish=%.1f stream=%.1f slots=%.0f\n", sweeps_done, ms,
@@ -371,7 +464,7 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
             info->init_ms = init_ms;
             info->solve_ms = solve_ms;
             info->sweeps = sweeps_done;
-            info->mode = KB_MODE_STREAM;
+            info->mode = mode;
             // full-sweep algorithmic bytes of the reference's solves + update
             const double per_sweep = (method == KB_METHOD_SDP_CCD) ? (20.0 / 3.0) * pd * pd * pd : 8.0 * pd * (pd + 1) * (pd + 1);
             info->ref_bytes = per_sweep * sweeps_done;

@@ -10,9 +10,9 @@ ctx = kb.Context(0)
 for rep in range(2):
     t = time.time()
     s, info = kb.solve_s(Sigma, os.environ.get("METHOD", "mvr"), m=m, s_init=s0, ctx=ctx, return_info=True,
-                         refresh_every=int(os.environ.get("REFRESH", "1")), niter=int(os.environ.get("NITER", "100")))
+                         refresh_every=int(os.environ.get("REFRESH", "-1")), mode=os.environ.get("MODE", "auto"), niter=int(os.environ.get("NITER", "100")))
     wall = time.time() - t
     per = info["solve_ms"] / max(1, info["sweeps"])
-    print(f"shape={os.environ.get('KB_CCD_SHAPE','2x256')} l2={os.environ.get('KB_CCD_L2_PERSIST','0')} p={p} sweeps={info['sweeps']} "
+    print(f"mode={info['mode']} shape={os.environ.get('KB_CCD_SHAPE','2x256')} l2={os.environ.get('KB_CCD_L2_PERSIST','0')} p={p} sweeps={info['sweeps']} "
           f"ccd_ms/sweep={per:.2f} GB/s={info['ref_bytes']/max(1,info['sweeps'])/per/1e6:.0f} init_ms={info['init_ms']:.1f} wall={wall:.2f}s "
           f"s[:3]={s[:3]}", flush=True)

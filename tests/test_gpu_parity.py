@@ -71,16 +71,21 @@ def _sigma(kind, p):
     ("ar1", 63, "mvr", 1), ("ar1", 64, "maxent", 2), ("ar1", 65, "sdp_ccd", 1), ("ar1", 1, "maxent", 1),
     ("ar1", 2, "maxent", 1), ("block", 130, "mvr", 3),
 ])
-@pytest.mark.parametrize("refresh", [1, 0])
-def test_solve_s_matches_oracle(kb, ctx, kind, p, method, m, refresh):
+@pytest.mark.parametrize("mode,refresh", [("block", -1), ("block", 1), ("block", 0), ("stream", 1), ("stream", 0)])
+def test_solve_s_matches_oracle(kb, ctx, kind, p, method, m, mode, refresh):
+    """Both kernels (blocked rank-64 delayed updates = AUTO, rank-1 streaming) against the C oracle."""
     Sigma = _sigma(kind, p)
     s0 = ko.solve_equi(Sigma, m)
     want = c_oracle.solve_ccd(Sigma, method, m=m, s_init=s0)
-    got, info = kb.solve_s(Sigma, method, m=m, s_init=s0, ctx=ctx, return_info=True, refresh_every=refresh)
+    got, info = kb.solve_s(Sigma, method, m=m, s_init=s0, ctx=ctx, return_info=True, refresh_every=refresh, mode=mode)
+    assert info["mode"] == mode
     assert info["sweeps"] == want["sweeps"]
     assert rel(got, want["s"]) < S_RTOL
     if method != "sdp_ccd":
-        assert np.allclose(info["trace"], want["trace"], rtol=1e-6, atol=1e-12)
+        # per-sweep max|δ|: the equi starting point makes the first factorisation nearly singular (λmin(A) = 1e-6), so
+        # implementations that differ in rounding leave sweep 1 ~1e-9 apart in s and re-converge (an every-sweep
+        # float64 numpy restatement shows the same 1e-5 relative spread on the late, tiny δ's)
+        assert np.allclose(info["trace"], want["trace"], rtol=1e-4, atol=1e-8)
     assert info["updates"] == want["n_updates"]
 
 
