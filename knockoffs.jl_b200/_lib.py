@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libknockoffs_b200.so")
+LIB_PATH = os.environ.get("KB_LIB_PATH") or os.path.join(_HERE, "libknockoffs_b200.so")   # KB_LIB_PATH: A/B builds
 
 KB_OK, KB_ERR_INVALID, KB_ERR_NOT_PD, KB_ERR_NAN, KB_ERR_CUDA = 0, -1, -2, -3, -4
 KB_MAX_TRACE = 128

@@ -10,11 +10,13 @@
 //     D ← D + c·w wᵀ,     G ← G + c·(g wᵀ + w gᵀ) + c²·G_jj·w wᵀ.
 // The current panel is M[:, J] = P₀·T with P₀ the panel at block entry and T (b x b) following T ← T + c·T[:, j]·wᵀ,
 // so u_j = P₀·T[:, j] (snapshot at step j) and the whole block amounts to the rank-b update
-//     M ← M + U·diag(c)·Uᵀ,   U = P₀·[t_0 … t_{b-1}],
-// i.e. one p x b x b GEMM and one SYRK-shaped p x p x b GEMM on the FP64 tensor cores per block: the
-// triangle is read and written ONCE per 64 coordinates instead of once per coordinate.
-// Per block: gather (panel + partial Grams, all SMs) → sequential (one CTA, b line searches, registers +
-// shared memory only) → U = P₀·T (DMMA GEMM) → rank-b update of the lower tiles (DMMA GEMM).
+//     M ← M + U·diag(c)·Uᵀ,   U = P₀·[t_0 … t_{b-1}].
+// Two levels: an OUTER block of up to 4 inner blocks (256 coordinates) keeps a gathered full-height copy PO of its
+// columns; after each inner block only PO's later columns are brought up to date (p x ≤192 x 64 GEMM), and the
+// triangle itself is read and written ONCE per outer block by a SYRK-shaped p x p x 256 GEMM on the FP64 tensor
+// cores -- instead of once per coordinate.
+// Per inner block: [Gram partials (MVR)] → sequential kernel (one CTA, 64 line searches, registers + shared memory
+// only) → [U | U diag(c)] = P₀·[T | T diag(c)] (DMMA GEMM) → update of PO's later columns (DMMA GEMM).
 // The coordinate order, the line search (ccd_device.cuh) and every skip / clip / error decision are the
 // reference's; only the order in which the mathematically identical updates reach memory differs.
 #include "kb_common.cuh"
@@ -26,87 +28,102 @@
 
 namespace kb {
 
-constexpr int BW = CCD_BLOCK_WIDTH;    // coordinates per block (= slot rows, 64)
-constexpr int SLAB = 128;              // rows per gather CTA
+constexpr int BW = CCD_BLOCK_WIDTH;    // coordinates per inner block (= slot rows, 64)
+constexpr int MAX_NIN = 8;             // inner blocks per outer block: at most 8 (512 coordinates)
+constexpr int SLAB = 128;              // rows per gather / Gram CTA
 constexpr int GPITCH = SLAB + 1;       // shared-memory pitch of one panel column
 constexpr int BLK_THREADS = 256;
 static_assert(BW == 64 && SLOT_ROWS == 64, "ownership maps below assume 64-wide blocks");
 
 // Thread t of the 256 owns the 4 x 4 entries (tr + 16a, tc + 16b), tr = t & 15, tc = t >> 4, of every 64 x 64
-// block matrix (D, G, T) -- in the gather kernel's partial Grams and in the sequential kernel alike, so partial
+// block matrix (D, G, T) -- in the Gram kernel's partials and in the sequential kernel alike, so partial
 // Grams are exchanged as [slab][a*4+b][t] (coalesced).
 
-// Panel P₀ = M[:, j0 .. j0+63] (full height, from the lower triangle + symmetric diagonal blocks), written to
-// Pbuf (ld x 64, rows >= p zero), and -- WITH_GRAM -- this slab's partial Gram.
-template <bool WITH_GRAM>
-__global__ void __launch_bounds__(BLK_THREADS) ccd_block_gather_kernel(const double* __restrict__ M, long ld, int p, int j0,
-                                                                      double* __restrict__ Pbuf, double* __restrict__ Gpart) {
-    extern __shared__ double gsm[];          // [64][GPITCH]: column c of the slab at gsm + c * GPITCH
+// PO[:, 64 cb .. 64 cb + 63] = M[:, j0 .. j0 + 63], j0 = o0 + 64 cb (full height, from the lower triangle + the
+// symmetric diagonal blocks; rows >= p and columns >= p are zero).  grid = (row slabs, inner blocks).
+__global__ void __launch_bounds__(BLK_THREADS) ccd_block_gather_kernel(const double* __restrict__ M, long ld, int p, int o0,
+                                                                      double* __restrict__ PO) {
+    __shared__ double tile[BW][BW + 1];
     const int tid = threadIdx.x;
-    const int r0 = blockIdx.x * SLAB;
+    const int j0 = o0 + (int)blockIdx.y * BW;
     const int jb = j0 / BW;
+    double* Pk = PO + (size_t)blockIdx.y * BW * ld;
 #pragma unroll
     for (int h = 0; h < SLAB / BW; ++h) {
-        const int rbase = r0 + h * BW;
+        const int rbase = (int)blockIdx.x * SLAB + h * BW;
+        if (rbase >= ld) break;
         const int rb = rbase / BW;
-        if (rbase >= ld) {
-            for (int e = tid; e < BW * BW; e += BLK_THREADS) gsm[(e >> 6) * GPITCH + h * BW + (e & 63)] = 0.0;
-        } else if (rb >= jb) {
+        if (rb >= jb) {
             // stored directly: M(r, j0 + c), r fastest (the diagonal block is stored symmetric)
             for (int e = tid; e < BW * BW; e += BLK_THREADS) {
                 const int r = e & 63, c = e >> 6;
-                gsm[c * GPITCH + h * BW + r] = (j0 + c < p) ? M[(long)(rbase + r) + (long)(j0 + c) * ld] : 0.0;
+                Pk[(long)(rbase + r) + (long)c * ld] = (j0 + c < p) ? M[(long)(rbase + r) + (long)(j0 + c) * ld] : 0.0;
             }
         } else {
-            // rows above the block: M(r, j0 + c) = M(j0 + c, r), c fastest
+            // rows above the block: M(r, j0 + c) = M(j0 + c, r): read c fastest, transpose through shared memory
+            __syncthreads();
             for (int e = tid; e < BW * BW; e += BLK_THREADS) {
                 const int c = e & 63, r = e >> 6;
-                gsm[c * GPITCH + h * BW + r] = (j0 + c < p) ? M[(long)(j0 + c) + (long)(rbase + r) * ld] : 0.0;
+                tile[r][c] = (j0 + c < p) ? M[(long)(j0 + c) + (long)(rbase + r) * ld] : 0.0;
+            }
+            __syncthreads();
+            for (int e = tid; e < BW * BW; e += BLK_THREADS) {
+                const int r = e & 63, c = e >> 6;
+                Pk[(long)(rbase + r) + (long)c * ld] = tile[r][c];
             }
         }
     }
-    __syncthreads();
+}
+
+// partial Gram of one 128-row slab of the current panel Pk (ld x 64)
+__global__ void __launch_bounds__(BLK_THREADS) ccd_block_gram_kernel(const double* __restrict__ Pk, long ld,
+                                                                    double* __restrict__ Gpart) {
+    extern __shared__ double gsm[];          // [64][GPITCH]: column c of the slab at gsm + c * GPITCH
+    const int tid = threadIdx.x;
+    const int r0 = (int)blockIdx.x * SLAB;
     for (int e = tid; e < SLAB * BW; e += BLK_THREADS) {
         const int r = e & (SLAB - 1), c = e >> 7;
-        if (r0 + r < ld) Pbuf[(long)(r0 + r) + (long)c * ld] = gsm[c * GPITCH + r];
+        gsm[c * GPITCH + r] = (r0 + r < ld) ? Pk[(long)(r0 + r) + (long)c * ld] : 0.0;
     }
-    if (WITH_GRAM) {
-        const int tr = tid & 15, tc = tid >> 4;
-        double acc[4][4];
+    __syncthreads();
+    const int tr = tid & 15, tc = tid >> 4;
+    double acc[4][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-        const double* pa = gsm + tr * GPITCH;
-        const double* pb = gsm + tc * GPITCH;
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    const double* pa = gsm + tr * GPITCH;
+    const double* pb = gsm + tc * GPITCH;
 #pragma unroll 4
-        for (int r = 0; r < SLAB; ++r) {
-            double av[4], bv[4];
+    for (int r = 0; r < SLAB; ++r) {
+        double av[4], bv[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                av[a] = pa[a * 16 * GPITCH + r];
-                bv[a] = pb[a * 16 * GPITCH + r];
-            }
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+        for (int a = 0; a < 4; ++a) {
+            av[a] = pa[a * 16 * GPITCH + r];
+            bv[a] = pb[a * 16 * GPITCH + r];
         }
-        double* out = Gpart + (size_t)blockIdx.x * (BW * BW);
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) out[(a * 4 + b) * BLK_THREADS + tid] = acc[a][b];
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
     }
+    double* out = Gpart + (size_t)blockIdx.x * (BW * BW);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) out[(a * 4 + b) * BLK_THREADS + tid] = acc[a][b];
 }
 
 // One CTA walks the block's coordinates in order.  TT (64 x 128, ld 64) receives [t_0 … t_63 | c_0 t_0 … c_63 t_63].
 // sweep bookkeeping (counters[3] running max|δ| of the sweep, counters[1] accepted updates, *status) lives in
 // device memory across the sweep's blocks; `first` resets it, `last` closes the sweep (trace, λ decay, sweeps_out).
-template <bool MVR>
+// After step j only D / G entries with both indices > j and T entries (row <= j, column > j) are read again, so the
+// register tiles are updated from the current 16-column phase bq onwards only (compile-time bounds).
+template <int METHOD>
 __global__ void __launch_bounds__(BLK_THREADS, 1)
-ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict__ Pbuf, const double* __restrict__ Gpart,
+ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict__ Pk, const double* __restrict__ Gpart,
                      int nslab, double* __restrict__ TT, int first, int last) {
+    constexpr bool MVR = (METHOD == KB_METHOD_MVR);
     __shared__ double wbuf[2][BW], gbuf[2][BW], tbuf[2][BW];
     __shared__ double s_s[BW], s_a[BW], s_k[BW];
     const int tid = threadIdx.x;
@@ -118,7 +135,7 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int r = tr + 16 * a, c = tc + 16 * b;
-            D[a][b] = (r < bw && c < bw) ? Pbuf[(long)(j0 + r) + (long)c * ld] : 0.0;
+            D[a][b] = (r < bw && c < bw) ? Pk[(long)(j0 + r) + (long)c * ld] : 0.0;
             T[a][b] = (r == c) ? 1.0 : 0.0;
             G[a][b] = 0.0;
         }
@@ -141,7 +158,6 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
     double max_delta = first ? 0.0 : P.counters[3];
     double nupd = 0.0;
     const double m = P.m, lam = P.sdp_lambda, lambda_min = P.lambda_min;
-    const int method = P.method;
     __syncthreads();
 
 #pragma unroll
@@ -164,7 +180,7 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
             const double sj = s_s[j], ajj = s_a[j];
             double delta, s_new, cfac;
             bool skip;
-            ccd_line_search(method, m, lam, lambda_min, sj, ajj, s_k[j], ss, Mjj, delta, s_new, skip, cfac, status);
+            ccd_line_search(METHOD, m, lam, lambda_min, sj, ajj, s_k[j], ss, Mjj, delta, s_new, skip, cfac, status);
             const bool upd = !skip && status == 0;
             if (upd) {
                 if (fabs(delta) > max_delta) max_delta = fabs(delta);
@@ -186,23 +202,28 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
                 double wr[4], wc[4], al[4], tv[4], gc[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    wr[a] = wbuf[pb][tr + 16 * a];
-                    wc[a] = wbuf[pb][tc + 16 * a];
-                    tv[a] = cfac * tbuf[pb][tr + 16 * a];
-                    if (MVR) {
-                        // G += α wᵀ + β gᵀ,  α = c g + c² ss w,  β = c w
-                        al[a] = cfac * gbuf[pb][tr + 16 * a] + cfac * cfac * ss * wr[a];
-                        gc[a] = gbuf[pb][tc + 16 * a];
+                    if (a >= bq) {
+                        wc[a] = wbuf[pb][tc + 16 * a];
+                        const double w = wbuf[pb][tr + 16 * a];
+                        if (MVR) {
+                            // G += α wᵀ + β gᵀ,  α = c g + c² ss w,  β = c w
+                            al[a] = cfac * gbuf[pb][tr + 16 * a] + cfac * cfac * ss * w;
+                            gc[a] = gbuf[pb][tc + 16 * a];
+                        }
+                        wr[a] = cfac * w;
                     }
-                    wr[a] *= cfac;
+                    if (a <= bq) tv[a] = cfac * tbuf[pb][tr + 16 * a];
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        D[a][b] = fma(wr[a], wc[b], D[a][b]);
-                        T[a][b] = fma(tv[a], wc[b], T[a][b]);
-                        if (MVR) G[a][b] = fma(al[a], wc[b], fma(wr[a], gc[b], G[a][b]));
+                        if (b < bq) continue;
+                        if (a >= bq) {
+                            D[a][b] = fma(wr[a], wc[b], D[a][b]);
+                            if (MVR) G[a][b] = fma(al[a], wc[b], fma(wr[a], gc[b], G[a][b]));
+                        }
+                        if (a <= bq) T[a][b] = fma(tv[a], wc[b], T[a][b]);
                     }
             }
         }
@@ -222,20 +243,29 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
         if (last) {
             if (status == 0) {
                 if (P.sweep0 < KB_MAX_TRACE) P.trace[P.sweep0] = max_delta;
-                P.counters[2] = (method == KB_METHOD_SDP_CCD) ? lam * P.sdp_mu : lam;   // utilities.jl:339
+                P.counters[2] = (METHOD == KB_METHOD_SDP_CCD) ? lam * P.sdp_mu : lam;   // utilities.jl:339
             }
             *P.sweeps_out = 1;
         }
     }
 }
 
+static int outer_blocks() {
+    static const int v = [] {
+        const char* e = getenv("KB_CCD_OUTER");      // inner blocks per outer block (tuning), default 4
+        int x = e ? atoi(e) : 4;
+        return x < 1 ? 1 : (x > MAX_NIN ? MAX_NIN : x);
+    }();
+    return v;
+}
+
 size_t ccd_block_work_doubles(int p) {
     const long ld = ccd_stream_ld(p);
     const long nslab = (ld + SLAB - 1) / SLAB;
-    return (size_t)ld * BW            // Pbuf
-           + (size_t)ld * 2 * BW      // [U | U diag(c)]
-           + (size_t)nslab * BW * BW  // partial Grams
-           + 2 * BW * BW + 64;        // TT
+    const long wo = (long)BW * outer_blocks();
+    return (size_t)ld * wo * 3              // PO, U_all, Uc_all
+           + (size_t)nslab * BW * BW        // partial Grams
+           + 2 * BW * BW + 64;              // TT
 }
 
 // ONE sweep over all coordinates (P.nsweeps is ignored; P.sweep0 / P.sdp_lambda describe this sweep).
@@ -244,57 +274,96 @@ int ccd_block_run(kb_ctx* ctx, const CcdParams& P, double* work) {
     const long ld = P.ld;
     if (ld != ccd_stream_ld(p)) return set_error(ctx, KB_ERR_INVALID, "ccd_block_run: bad leading dimension");
     const int nslab = (int)((ld + SLAB - 1) / SLAB);
-    double* Pbuf = work;
-    double* UU = Pbuf + (size_t)ld * BW;
-    double* Gpart = UU + (size_t)ld * 2 * BW;
+    const int NIN = outer_blocks();
+    const long wo = (long)BW * NIN;
+    double* PO = work;
+    double* Uall = PO + (size_t)ld * wo;
+    double* Ucall = Uall + (size_t)ld * wo;
+    double* Gpart = Ucall + (size_t)ld * wo;
     double* TT = Gpart + (size_t)nslab * BW * BW;
     const bool mvr = (P.method == KB_METHOD_MVR);
     const size_t gsmem = (size_t)BW * GPITCH * sizeof(double);
-    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)ccd_block_gather_kernel<true>, gsmem));
-    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)ccd_block_gather_kernel<false>, gsmem));
+    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)ccd_block_gram_kernel, gsmem));
     const int nblk = (p + BW - 1) / BW;
-    // KB_BLOCK_PHASES=1: CUDA events around every launch of the sweep, per-phase totals on stderr (diagnostics)
+    // KB_BLOCK_PHASES=1: CUDA events around every phase of the sweep, per-phase totals on stderr (diagnostics)
     static const bool phases = getenv("KB_BLOCK_PHASES") != nullptr;
+    enum { PH_GATHER, PH_GRAM, PH_SEQ, PH_PT, PH_INNER, PH_BIG, PH_N };
     std::vector<cudaEvent_t> ev;
-    if (phases) {
-        ev.resize((size_t)nblk * 5);
-        for (auto& e : ev) cudaEventCreate(&e);
+    std::vector<int> ev_phase;
+    auto mark = [&](int phase) {
+        if (!phases) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        ev.push_back(e);
+        ev_phase.push_back(phase);
+    };
+    // rows p..ld-1 of U_all / Uc_all are never written by the GEMMs (M = p) but are read as operand rows of the panel
+    // update: keep them zero
+    KB_CUDA(ctx, cudaMemsetAsync(Uall, 0, sizeof(double) * 2 * (size_t)ld * wo, ctx->stream));
+    mark(-1);
+    for (int ob = 0; ob * NIN < nblk; ++ob) {
+        const int o0 = ob * NIN * BW;
+        const int nin = (nblk - ob * NIN < NIN) ? nblk - ob * NIN : NIN;
+        ccd_block_gather_kernel<<<dim3(nslab, nin), BLK_THREADS, 0, ctx->stream>>>(P.M, ld, p, o0, PO);
+        ctx->launches++;
+        mark(PH_GATHER);
+        for (int k = 0; k < nin; ++k) {
+            const int blk = ob * NIN + k;
+            const int j0 = blk * BW;
+            const int bw = (p - j0 < BW) ? p - j0 : BW;
+            const int first = (blk == 0), last = (blk == nblk - 1);
+            double* Pk = PO + (size_t)k * BW * ld;
+            if (mvr) {
+                ccd_block_gram_kernel<<<nslab, BLK_THREADS, gsmem, ctx->stream>>>(Pk, ld, Gpart);
+                ctx->launches++;
+                mark(PH_GRAM);
+            }
+            if (P.method == KB_METHOD_MVR)
+                ccd_block_seq_kernel<KB_METHOD_MVR><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
+            else if (P.method == KB_METHOD_MAXENT)
+                ccd_block_seq_kernel<KB_METHOD_MAXENT><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
+            else
+                ccd_block_seq_kernel<KB_METHOD_SDP_CCD><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
+            ctx->launches++;
+            KB_CUDA(ctx, cudaGetLastError());
+            mark(PH_SEQ);
+            // [U_k | U_k diag(c)] = P₀ · TT   ->  columns 64k.. of U_all and Uc_all
+            {
+                GemmParams G{};
+                G.M = p; G.N = 2 * BW; G.nseg = 1;
+                G.seg[0] = GemmSeg{Pk, ld, TT, BW, BW, 0};
+                G.C = Uall + (size_t)k * BW * ld; G.ldc = ld; G.Cin = G.C; G.ldcin = ld;
+                G.C2 = Ucall + (size_t)k * BW * ld; G.nsplit = BW;
+                G.alpha = 1.0; G.beta = 0.0;
+                KB_TRY(gemm(ctx, A_MCONTIG, B_KCONTIG, G));
+            }
+            mark(PH_PT);
+            // PO's later columns += (U_k diag(c)) · U_k[rows of those columns, :]ᵀ
+            if (k + 1 < nin) {
+                const int nlater = (nin - 1 - k) * BW;
+                KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, nlater, BW, 1.0, Ucall + (size_t)k * BW * ld, ld,
+                             Uall + (size_t)k * BW * ld + (size_t)(j0 + BW), ld, 1.0, PO + (size_t)(k + 1) * BW * ld, ld));
+                mark(PH_INNER);
+            }
+        }
+        // M (lower tiles) += Uc_all · U_allᵀ   (K = 64 nin)
+        KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, nin * BW, 1.0, Ucall, ld, Uall, ld, 1.0, P.M, ld, 0, 1, 0));
+        mark(PH_BIG);
     }
-#define KB_EV(i) do { if (phases) cudaEventRecord(ev[(size_t)blk * 5 + (i)], ctx->stream); } while (0)
-    for (int blk = 0; blk < nblk; ++blk) {
-        const int j0 = blk * BW;
-        const int bw = (p - j0 < BW) ? p - j0 : BW;
-        const int first = (blk == 0), last = (blk == nblk - 1);
-        KB_EV(0);
-        if (mvr) ccd_block_gather_kernel<true><<<nslab, BLK_THREADS, gsmem, ctx->stream>>>(P.M, ld, p, j0, Pbuf, Gpart);
-        else ccd_block_gather_kernel<false><<<nslab, BLK_THREADS, gsmem, ctx->stream>>>(P.M, ld, p, j0, Pbuf, Gpart);
-        KB_EV(1);
-        if (mvr) ccd_block_seq_kernel<true><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pbuf, Gpart, nslab, TT, first, last);
-        else ccd_block_seq_kernel<false><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pbuf, Gpart, nslab, TT, first, last);
-        KB_EV(2);
-        ctx->launches += 2;
-        KB_CUDA(ctx, cudaGetLastError());
-        // [U | U diag(c)] = P₀ · TT
-        KB_TRY(gemm1(ctx, A_MCONTIG, B_KCONTIG, p, 2 * BW, BW, 1.0, Pbuf, ld, TT, BW, 0.0, UU, ld));
-        KB_EV(3);
-        // M (lower tiles) += (U diag(c)) · Uᵀ
-        KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, BW, 1.0, UU + (size_t)ld * BW, ld, UU, ld, 1.0, P.M, ld, 0, 1, 0));
-        KB_EV(4);
-    }
-#undef KB_EV
     if (phases) {
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        double t[4] = {0, 0, 0, 0};
-        for (int blk = 0; blk < nblk; ++blk)
-            for (int i = 0; i < 4; ++i) {
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, ev[(size_t)blk * 5 + i], ev[(size_t)blk * 5 + i + 1]);
-                t[i] += ms;
-            }
+        double t[PH_N] = {0, 0, 0, 0, 0, 0};
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            t[ev_phase[i]] += ms;
+        }
         float tot = 0.f;
-        cudaEventElapsedTime(&tot, ev[0], ev[(size_t)nblk * 5 - 1]);
-        fprintf(stderr, "[ccd_block sweep: %d blocks, %.2f ms] gather=%.2f seq=%.2f U=P*T=%.2f update=%.2f ms\n", nblk, tot, t[0], t[1],
-                t[2], t[3]);
+        cudaEventElapsedTime(&tot, ev.front(), ev.back());
+        fprintf(stderr, "[ccd_block sweep: %d blocks of 64 in groups of %d, %.2f ms] gather=%.2f gram=%.2f seq=%.2f U=P*T=%.2f "
+                        "panel=%.2f rank-%d update=%.2f ms\n", nblk, NIN, tot, t[PH_GATHER], t[PH_GRAM], t[PH_SEQ], t[PH_PT],
+                t[PH_INNER], NIN * BW, t[PH_BIG]);
         for (auto& e : ev) cudaEventDestroy(e);
     }
     return KB_OK;

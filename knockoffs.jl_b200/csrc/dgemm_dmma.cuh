@@ -20,16 +20,33 @@
 
 namespace kb {
 
-constexpr int GEMM_BM = 128;
+// CTA tile configurations (BN = 128, BK = 16, 3-stage cp.async pipeline in all of them):
+//   GemmCfg<128, 2, 4>  128 x 128, 8 warps of 64 x 32, 1 CTA / SM      (first kernel of round 1)
+//   GemmCfg< 64, 2, 2>   64 x 128, 4 warps of 32 x 64, 2 CTAs / SM: the two resident CTAs run out of phase, so one
+//                        feeds the DMMA pipe while the other sits at its k-tile barrier / waits for cp.async
+#ifndef KB_GEMM_BK
+#define KB_GEMM_BK 16
+#endif
+#ifndef KB_GEMM_STAGES
+#define KB_GEMM_STAGES 3
+#endif
 constexpr int GEMM_BN = 128;
-constexpr int GEMM_BK = 16;
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_STAGES = 3;
-constexpr int GEMM_PADM = GEMM_BM + 4;   // [k][m] rows: stride mod 16 == 4 -> conflict-free fragments
-constexpr int GEMM_PADK = GEMM_BK + 4;   // [m][k] rows: stride mod 16 == 4
-constexpr int GEMM_TILE_DOUBLES = (GEMM_BK * GEMM_PADM > GEMM_BM * GEMM_PADK) ? GEMM_BK * GEMM_PADM
-                                                                              : GEMM_BM * GEMM_PADK;
-constexpr size_t GEMM_SMEM_BYTES = (size_t)GEMM_STAGES * 2 * GEMM_TILE_DOUBLES * sizeof(double);
+constexpr int GEMM_BK = KB_GEMM_BK;
+constexpr int GEMM_STAGES = KB_GEMM_STAGES;
+constexpr int GEMM_PADK = GEMM_BK + 4;   // [m][k] rows: stride mod 16 == 4 -> conflict-free fragments
+
+template <int BM_, int WM_, int WN_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = GEMM_BN, WM = WM_, WN = WN_;
+    static constexpr int WARPS = WM * WN, THREADS = 32 * WARPS;
+    static constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;          // 8 x 8 DMMA tiles per warp
+    static constexpr int PADM = BM + 4, PADN = BN + 4;                // [k][m] / [k][n] rows: stride mod 16 == 4
+    static constexpr int A_TILE = (GEMM_BK * PADM > BM * GEMM_PADK) ? GEMM_BK * PADM : BM * GEMM_PADK;
+    static constexpr int B_TILE = (GEMM_BK * PADN > BN * GEMM_PADK) ? GEMM_BK * PADN : BN * GEMM_PADK;
+    static constexpr int STAGE = A_TILE + B_TILE;
+    static constexpr size_t SMEM_BYTES = (size_t)GEMM_STAGES * STAGE * sizeof(double);
+    static constexpr int MIN_CTAS = (BM <= 64) ? 2 : 1;
+};
 
 enum : int { A_MCONTIG = 0, A_KCONTIG = 1 };   // A(m,k) at m + k*lda   |   k + m*lda
 enum : int { B_KCONTIG = 0, B_NCONTIG = 1 };   // B(k,n) at k + n*ldb   |   n + k*ldb
@@ -63,6 +80,8 @@ struct GemmParams {
     const double* bias_n;   // optional, added per column n
     int tile_mode;          // 0 all tiles, 1 lower tiles only (skip tiles with m0 + BM <= n0)
     int store_mode;         // 0 all, 1 only elements with m >= n (lower incl. diagonal)
+    double* C2;             // optional second destination: columns n >= nsplit are stored to C2 + (n - nsplit) * ldc
+    int nsplit;             //   (C2 == nullptr: off).  Requires beta == 0 or Cin laid out like the logical C.
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -86,37 +105,37 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // Stage one BM x BK tile of A and one BK x BN tile of B into shared memory.
-template <int AL, int BL, bool VEC>
+template <class Cfg, int AL, int BL, bool VEC>
 __device__ __forceinline__ void gemm_load_stage(const GemmSeg& sg, int M, int N, int m0, int n0, int k0,
                                                 int kend, double* As, double* Bs, int tid) {
     // ---- A tile ----
     if (AL == A_MCONTIG) {
         if (VEC) {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BM * GEMM_BK / 2) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
-                int k = c / (GEMM_BM / 2), m = (c % (GEMM_BM / 2)) * 2;
+            for (int it = 0; it < (Cfg::BM * GEMM_BK / 2) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
+                int k = c / (Cfg::BM / 2), m = (c % (Cfg::BM / 2)) * 2;
                 int gm = m0 + m, gk = k0 + k;
                 int valid = (gk < kend) ? max(0, min(2, M - gm)) : 0;
                 const double* src = valid ? sg.A + (long)gm + (long)gk * sg.lda : sg.A;
-                cp_async16(As + k * GEMM_PADM + m, src, valid * 8);
+                cp_async16(As + k * Cfg::PADM + m, src, valid * 8);
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BM * GEMM_BK) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
-                int k = c / GEMM_BM, m = c % GEMM_BM;
+            for (int it = 0; it < (Cfg::BM * GEMM_BK) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
+                int k = c / Cfg::BM, m = c % Cfg::BM;
                 int gm = m0 + m, gk = k0 + k;
                 int valid = (gk < kend && gm < M);
                 const double* src = valid ? sg.A + (long)gm + (long)gk * sg.lda : sg.A;
-                cp_async8(As + k * GEMM_PADM + m, src, valid * 8);
+                cp_async8(As + k * Cfg::PADM + m, src, valid * 8);
             }
         }
     } else {
         if (VEC) {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BM * GEMM_BK / 2) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
+            for (int it = 0; it < (Cfg::BM * GEMM_BK / 2) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
                 int m = c / (GEMM_BK / 2), k = (c % (GEMM_BK / 2)) * 2;
                 int gm = m0 + m, gk = k0 + k;
                 int valid = (gm < M) ? max(0, min(2, kend - gk)) : 0;
@@ -125,8 +144,8 @@ __device__ __forceinline__ void gemm_load_stage(const GemmSeg& sg, int M, int N,
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BM * GEMM_BK) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
+            for (int it = 0; it < (Cfg::BM * GEMM_BK) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
                 int m = c / GEMM_BK, k = c % GEMM_BK;
                 int gm = m0 + m, gk = k0 + k;
                 int valid = (gk < kend && gm < M);
@@ -139,8 +158,8 @@ __device__ __forceinline__ void gemm_load_stage(const GemmSeg& sg, int M, int N,
     if (BL == B_KCONTIG) {
         if (VEC) {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BN * GEMM_BK / 2) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
+            for (int it = 0; it < (Cfg::BN * GEMM_BK / 2) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
                 int n = c / (GEMM_BK / 2), k = (c % (GEMM_BK / 2)) * 2;
                 int gn = n0 + n, gk = k0 + k;
                 int valid = (gn < N) ? max(0, min(2, kend - gk)) : 0;
@@ -149,8 +168,8 @@ __device__ __forceinline__ void gemm_load_stage(const GemmSeg& sg, int M, int N,
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BN * GEMM_BK) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
+            for (int it = 0; it < (Cfg::BN * GEMM_BK) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
                 int n = c / GEMM_BK, k = c % GEMM_BK;
                 int gn = n0 + n, gk = k0 + k;
                 int valid = (gk < kend && gn < N);
@@ -161,42 +180,44 @@ __device__ __forceinline__ void gemm_load_stage(const GemmSeg& sg, int M, int N,
     } else {
         if (VEC) {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BN * GEMM_BK / 2) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
-                int k = c / (GEMM_BN / 2), n = (c % (GEMM_BN / 2)) * 2;
+            for (int it = 0; it < (Cfg::BN * GEMM_BK / 2) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
+                int k = c / (Cfg::BN / 2), n = (c % (Cfg::BN / 2)) * 2;
                 int gn = n0 + n, gk = k0 + k;
                 int valid = (gk < kend) ? max(0, min(2, N - gn)) : 0;
                 const double* src = valid ? sg.B + (long)gn + (long)gk * sg.ldb : sg.B;
-                cp_async16(Bs + k * GEMM_PADM + n, src, valid * 8);
+                cp_async16(Bs + k * Cfg::PADN + n, src, valid * 8);
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < (GEMM_BN * GEMM_BK) / GEMM_THREADS; ++it) {
-                int c = tid + it * GEMM_THREADS;
-                int k = c / GEMM_BN, n = c % GEMM_BN;
+            for (int it = 0; it < (Cfg::BN * GEMM_BK) / Cfg::THREADS; ++it) {
+                int c = tid + it * Cfg::THREADS;
+                int k = c / Cfg::BN, n = c % Cfg::BN;
                 int gn = n0 + n, gk = k0 + k;
                 int valid = (gk < kend && gn < N);
                 const double* src = valid ? sg.B + (long)gn + (long)gk * sg.ldb : sg.B;
-                cp_async8(Bs + k * GEMM_PADM + n, src, valid * 8);
+                cp_async8(Bs + k * Cfg::PADN + n, src, valid * 8);
             }
         }
     }
 }
 
-template <int AL, int BL, bool VEC>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmParams P) {
+template <class Cfg, int AL, int BL, bool VEC>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel(const GemmParams P) {
     extern __shared__ __align__(16) double gemm_smem[];
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, MI = Cfg::MI, NJ = Cfg::NJ;
+    constexpr int WTM = MI * 8, WTN = NJ * 8;          // warp tile
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;   // 2 x 4 warps
-    const int m0 = blockIdx.x * GEMM_BM, n0 = blockIdx.y * GEMM_BN;
-    if (P.tile_mode == 1 && m0 + GEMM_BM <= n0) return;
+    const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    if (P.tile_mode == 1 && m0 + BM <= n0) return;
 
-    double acc[8][4][2];
+    double acc[MI][NJ][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int lr = lane >> 2, lc = lane & 3;
 
@@ -208,13 +229,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmP
     if (preload) {
         const double r = P.beta / P.alpha;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = m0 + wm * 64 + i * 8 + lr;
+        for (int i = 0; i < MI; ++i) {
+            const int m = m0 + wm * WTM + i * 8 + lr;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
+                    const int n = n0 + wn * WTN + j * 8 + 2 * lc + e;
                     if (m < P.M && n < P.N && !(P.store_mode == 1 && m < n))
                         acc[i][j][e] = r * P.Cin[(long)m + (long)n * P.ldcin];
                 }
@@ -227,8 +248,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmP
         int kbeg = 0, kend = sg.K;
         if (sg.flags & SEG_KLO_N) kbeg = max(kbeg, n0);
         if (sg.flags & SEG_KLO_M) kbeg = max(kbeg, m0);
-        if (sg.flags & SEG_KHI_N) kend = min(kend, n0 + GEMM_BN);
-        if (sg.flags & SEG_KHI_M) kend = min(kend, m0 + GEMM_BM);
+        if (sg.flags & SEG_KHI_N) kend = min(kend, n0 + BN);
+        if (sg.flags & SEG_KHI_M) kend = min(kend, m0 + BM);
         kbeg = (kbeg / GEMM_BK) * GEMM_BK;
         if (kend <= kbeg) continue;
         const int nkt = (kend - kbeg + GEMM_BK - 1) / GEMM_BK;
@@ -238,9 +259,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmP
 #pragma unroll
         for (int st = 0; st < GEMM_STAGES - 1; ++st) {
             if (st < nkt)
-                gemm_load_stage<AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + st * GEMM_BK, kend,
-                                             gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES,
-                                             gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES + GEMM_TILE_DOUBLES, tid);
+                gemm_load_stage<Cfg, AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + st * GEMM_BK, kend,
+                                                  gemm_smem + (size_t)st * Cfg::STAGE,
+                                                  gemm_smem + (size_t)st * Cfg::STAGE + Cfg::A_TILE, tid);
             cp_async_commit();
         }
         for (int kt = 0; kt < nkt; ++kt) {
@@ -251,33 +272,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmP
                 int nk = kt + GEMM_STAGES - 1;
                 if (nk < nkt) {
                     int st = nk % GEMM_STAGES;
-                    gemm_load_stage<AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + nk * GEMM_BK, kend,
-                                                 gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES,
-                                                 gemm_smem + (size_t)st * 2 * GEMM_TILE_DOUBLES + GEMM_TILE_DOUBLES,
-                                                 tid);
+                    gemm_load_stage<Cfg, AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + nk * GEMM_BK, kend,
+                                                      gemm_smem + (size_t)st * Cfg::STAGE,
+                                                      gemm_smem + (size_t)st * Cfg::STAGE + Cfg::A_TILE, tid);
                 }
                 cp_async_commit();
             }
-            const double* As = gemm_smem + (size_t)(kt % GEMM_STAGES) * 2 * GEMM_TILE_DOUBLES;
-            const double* Bs = As + GEMM_TILE_DOUBLES;
+            const double* As = gemm_smem + (size_t)(kt % GEMM_STAGES) * Cfg::STAGE;
+            const double* Bs = As + Cfg::A_TILE;
 #pragma unroll
             for (int kk = 0; kk < GEMM_BK / 4; ++kk) {
-                double af[8], bf[4];
+                double af[MI], bf[NJ];
                 const int k = kk * 4 + lc;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int m = wm * 64 + i * 8 + lr;
-                    af[i] = (AL == A_MCONTIG) ? As[k * GEMM_PADM + m] : As[m * GEMM_PADK + k];
+                for (int i = 0; i < MI; ++i) {
+                    const int m = wm * WTM + i * 8 + lr;
+                    af[i] = (AL == A_MCONTIG) ? As[k * Cfg::PADM + m] : As[m * GEMM_PADK + k];
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = wn * 32 + j * 8 + lr;
-                    bf[j] = (BL == B_KCONTIG) ? Bs[n * GEMM_PADK + k] : Bs[k * GEMM_PADM + n];
+                for (int j = 0; j < NJ; ++j) {
+                    const int n = wn * WTN + j * 8 + lr;
+                    bf[j] = (BL == B_KCONTIG) ? Bs[n * GEMM_PADK + k] : Bs[k * Cfg::PADN + n];
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < MI; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
         }
         cp_async_wait<0>();
@@ -285,20 +305,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) dgemm_dmma_kernel(const GemmP
 
     // epilogue: thread holds (row = lr, cols = 2*lc + {0,1}) of every 8x8 tile
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + wm * 64 + i * 8 + lr;
+    for (int i = 0; i < MI; ++i) {
+        const int m = m0 + wm * WTM + i * 8 + lr;
         if (m >= P.M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int n = n0 + wn * 32 + j * 8 + 2 * lc + e;
+                const int n = n0 + wn * WTN + j * 8 + 2 * lc + e;
                 if (n >= P.N) continue;
                 if (P.store_mode == 1 && m < n) continue;
                 double v = P.alpha * acc[i][j][e];
                 if (!preload && P.beta != 0.0) v += P.beta * P.Cin[(long)m + (long)n * P.ldcin];
                 if (P.bias_n) v += P.bias_n[n];
-                P.C[(long)m + (long)n * P.ldc] = v;
+                if (P.C2 && n >= P.nsplit) P.C2[(long)m + (long)(n - P.nsplit) * P.ldc] = v;
+                else P.C[(long)m + (long)n * P.ldc] = v;
             }
         }
     }

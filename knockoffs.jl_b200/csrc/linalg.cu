@@ -31,12 +31,20 @@ cudaError_t raise_max_dynamic_smem(const void* func, size_t bytes) {
 // ------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------
+// CTA configuration: 64 x 128 / 4 warps / 2 CTAs per SM unless KB_GEMM_CFG=128 is defined at build time
+#if defined(KB_GEMM_CFG) && KB_GEMM_CFG == 128
+using GemmDefaultCfg = GemmCfg<128, 2, 4>;
+#else
+using GemmDefaultCfg = GemmCfg<64, 2, 2>;
+#endif
+
 template <int AL, int BL, bool VEC>
 static int launch_gemm_t(kb_ctx* ctx, const GemmParams& P) {
-    auto kern = dgemm_dmma_kernel<AL, BL, VEC>;
-    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)kern, GEMM_SMEM_BYTES));
-    dim3 grid(ceil_div(P.M, GEMM_BM), ceil_div(P.N, GEMM_BN));
-    kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>(P);
+    using Cfg = GemmDefaultCfg;
+    auto kern = dgemm_dmma_kernel<Cfg, AL, BL, VEC>;
+    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)kern, Cfg::SMEM_BYTES));
+    dim3 grid(ceil_div(P.M, Cfg::BM), ceil_div(P.N, Cfg::BN));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(P);
     ctx->launches++;
     KB_CUDA(ctx, cudaGetLastError());
     return KB_OK;
@@ -144,7 +152,7 @@ int fill_zero(kb_ctx* ctx, double* A, size_t count) {
 // Cholesky: diagonal block kernel (one CTA): factor nb x nb block in shared memory, write L back,
 // then invert it in place and write inv(L_bb) to `inv` (ld = POTRF_NB).
 // ------------------------------------------------------------------------------------------
-constexpr int DIAG_PITCH = POTRF_NB + 1;
+constexpr int DIAG_PITCH = POTRF_NB + 4;   // pitch mod 16 == 4: DMMA fragment loads are bank-conflict free
 constexpr int DIAG_THREADS = 512;
 constexpr int DIAG_PANEL = 16;     // columns factored per panel step
 constexpr int DIAG_NPANEL = POTRF_NB / DIAG_PANEL;
@@ -395,33 +403,40 @@ __device__ __forceinline__ double rsqrt_pivot(double d) {
 }
 
 // v2 of the diagonal-block kernel.  Same contract as v1 (factor nb x nb <= 128 in shared memory, write L back, write
-// inv(L) to `inv`), restructured so the serial chain is ~250 cycles per column instead of ~2500:
+// inv(L) to `inv`), restructured so that the serial chain is a few hundred cycles per column and every O(n³)
+// piece runs on the FP64 tensor pipe (DMMA m8n8k4 from shared-memory fragments, pitch 132 = conflict-free):
 //  * 16-column panels; inside a panel thread i (< 128) owns ROW i of the panel in registers and ALL rows below the
 //    pivot take part in the column-by-column elimination (the panel's TRSM is folded into its factorisation -- no
 //    per-panel 16 x 16 inverse on the chain).  Per column the 16 diagonal-block rows publish their unscaled entries
 //    u_k = T(j0+k, j0+c) (one 128-thread named barrier), every row derives 1/sqrt(u_c) itself and applies
 //    row[k] -= (row[c] r)(u_k r).
-//  * rank-16 trailing update with 4 x 4 register tiles on all 16 warps (as v1).
-//  * inverse afterwards: the eight 16 x 16 diagonal inverses in parallel (one warp each), then the recursive doubling of v1.
+//  * rank-16 trailing update: 16 x 16 output tiles dealt to the 16 warps, 2 x 2 DMMA tiles each.
+//  * inverse afterwards: the eight 16 x 16 diagonal inverses in parallel (one warp each), then recursive doubling
+//    16 -> 32 -> 64 -> 128 with X = L21 W11 and W21 = -W22 X as warp-level DMMA products.  W = inv(L) is kept
+//    TRANSPOSED in T's strict upper triangle (W(i,k), i > k, at T(k,i)), its diagonal in dinv[].
+constexpr int XS_PITCH = 68;   // X scratch: column c of pair q at Xs[(q*b + c) * XS_PITCH + r]
 __global__ void __launch_bounds__(DIAG_THREADS, 1)
-potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) {
+potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base, long long* dbg) {
     extern __shared__ double dsm[];
     double* T = dsm;                                   // T(i,k) at k*DIAG_PITCH + i
-    double* W = dsm + POTRF_NB * DIAG_PITCH;           // inverse being assembled (lower, folded)
-    double* ubuf = W + DIAG_PITCH * (POTRF_NB / 2);    // 2 x 16 published column entries
-    double* dinv = ubuf + 2 * DIAG_PANEL;              // 128 reciprocal diagonal entries of L
+    double* Xs = dsm + POTRF_NB * DIAG_PITCH;          // 64 x XS_PITCH
+    double* ubuf = Xs + 64 * XS_PITCH;                 // 2 x 16 published column entries
+    double* dinv = ubuf + 2 * DIAG_PANEL;              // 128 reciprocal diagonal entries of L = diagonal of inv(L)
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tmark = clock64();
+#define DIAG_PHASE(i) do { if (dbg) { const long long t_ = clock64(); tk[i] += t_ - tmark; tmark = t_; } } while (0)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;           // DMMA fragment coordinates
 #define T_(i, k) T[(k) * DIAG_PITCH + (i)]
-#define W_(i, k) W[wfold((i), (k))]
-#define WG_(i, k) (((i) >= (k)) ? W[wfold((i), (k))] : 0.0)
+// W(i,k) = inv(L)(i,k) for i >= k
+#define WL_(i, k) (((i) > (k)) ? T_((k), (i)) : (((i) == (k)) ? dinv[(i)] : 0.0))
     {
         const int i = tid & (POTRF_NB - 1);
-        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB) {
+        for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB)
             T_(i, k) = (i < nb && k < nb) ? ((i >= k) ? A[i + (long)k * ld] : 0.0) : (i == k ? 1.0 : 0.0);
-            if (i >= k) W_(i, k) = 0.0;
-        }
     }
     __syncthreads();
+    DIAG_PHASE(0);
     for (int jb = 0; jb < DIAG_NPANEL; ++jb) {
         const int j0 = jb * DIAG_PANEL;
         if (tid < POTRF_NB) {
@@ -444,30 +459,69 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
                 }
                 const double r = rsqrt_pivot(d);
                 if (i == j0 + c) dinv[j0 + c] = r;
-                const double lc = (rl == c) ? d * r : row[c] * r;         // L(i, j0+c)
-                row[c] = lc;
+                const double lcv = (rl == c) ? d * r : row[c] * r;        // L(i, j0+c)
+                row[c] = lcv;
 #pragma unroll
-                for (int k = c + 1; k < DIAG_PANEL; ++k) row[k] = fma(-lc, ub[k] * r, row[k]);
+                for (int k = c + 1; k < DIAG_PANEL; ++k) row[k] = fma(-lcv, ub[k] * r, row[k]);
             }
             if (active) {
 #pragma unroll
-                for (int c = 0; c < DIAG_PANEL; ++c) T_(i, j0 + c) = (rl >= DIAG_PANEL || c <= rl) ? row[c] : 0.0;
+                for (int c = 0; c < DIAG_PANEL; ++c)
+                    if (rl >= DIAG_PANEL || c <= rl) T_(i, j0 + c) = row[c];
             }
         }
         __syncthreads();
+        DIAG_PHASE(1);
         const int t0 = j0 + DIAG_PANEL;
         if (t0 < POTRF_NB) {
-            // ---- trailing update T(t0.., t0..) -= P P' (lower tiles) ----
-            smem_tile_gemm_nt<true, true>(T, t0, t0, POTRF_NB - t0, POTRF_NB - t0, T, t0, j0, T, t0, j0, DIAG_PANEL, -1.0, tid);
+            // ---- trailing update T(t0.., t0..) -= P P' on the lower 16 x 16 tiles (DMMA, K = 16) ----
+            const int nb16 = (POTRF_NB - t0) / 16;
+            const int ntile = nb16 * (nb16 + 1) / 2;
+            for (int t = warp; t < ntile; t += DIAG_THREADS / 32) {
+                int bi = 0, rem = t;
+                while (rem > bi) { rem -= bi + 1; ++bi; }
+                const int m0 = t0 + 16 * bi, n0 = t0 + 16 * rem;
+                double acc[2][2][2];
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) acc[mi][nj][e] = T_(m0 + mi * 8 + lr, n0 + nj * 8 + 2 * lc + e);
+#pragma unroll
+                for (int k4 = 0; k4 < DIAG_PANEL; k4 += 4) {
+                    double af[2], bf[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        af[q] = -T_(m0 + q * 8 + lr, j0 + k4 + lc);
+                        bf[q] = T_(n0 + q * 8 + lr, j0 + k4 + lc);
+                    }
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                        for (int nj = 0; nj < 2; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                    for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int m = m0 + mi * 8 + lr, n = n0 + nj * 8 + 2 * lc + e;
+                            if (m >= n) T_(m, n) = acc[mi][nj][e];
+                        }
+            }
             __syncthreads();
+            DIAG_PHASE(2);
         }
     }
     {
         const int i = tid & (POTRF_NB - 1);
         if (i < nb)
             for (int k = tid >> 7; k < nb; k += DIAG_THREADS / POTRF_NB)
-                A[i + (long)k * ld] = T_(i, k);        // strict upper of the block becomes 0
+                A[i + (long)k * ld] = (i >= k) ? T_(i, k) : 0.0;
     }
+    DIAG_PHASE(3);
     // ---- 16 x 16 diagonal inverses: warp w < 8 takes block w, lane c < 16 computes column c by forward substitution ----
     if (warp < DIAG_NPANEL && lane < DIAG_PANEL) {
         const int j0 = warp * DIAG_PANEL, c = lane;
@@ -480,85 +534,119 @@ potrf_diag_kernel(double* A, long ld, int nb, double* inv, int* fail, int base) 
                 if (k < i) acc = fma(-T_(j0 + i, j0 + k), (k >= c) ? x[k] : 0.0, acc);
             x[i] = (i >= c) ? acc * dinv[j0 + i] : 0.0;
         }
+        __syncwarp(0x0000ffffu);     // every lane has finished reading L before the block's upper triangle is overwritten
 #pragma unroll
         for (int i = 0; i < DIAG_PANEL; ++i)
-            if (i >= c) W_(j0 + i, j0 + c) = x[i];
+            if (i > c) T_(j0 + c, j0 + i) = x[i];          // W(j0+i, j0+c), transposed; the diagonal x[c] equals dinv
     }
     __syncthreads();
-    // ---- blocked triangular inverse: merge pairs 16 -> 32 -> 64 -> 128 (X = L21 W11 parked in T's free upper part) ----
+    DIAG_PHASE(4);
+    // ---- blocked triangular inverse: merge pairs 16 -> 32 -> 64 -> 128 ----
     for (int b = DIAG_PANEL; b < POTRF_NB; b *= 2) {
-        for (int o = 0; o + b < POTRF_NB; o += 2 * b) {
-            const int tr = b >> 2, tc = b >> 2;
-            for (int tile = tid; tile < tr * tc; tile += DIAG_THREADS) {
-                const int r0 = (tile % tr) * 4, c0 = (tile / tr) * 4;
-                double acc[4][4];
+        const int nt = b / 16;                       // 16 x 16 tiles per side of a b x b block
+        const int njobs = (POTRF_NB / (2 * b)) * nt * nt;   // 4, 8, 16
+        // X = L21 W11  (W11 lower: k >= c)
+        if (warp < njobs) {
+            const int pair = warp / (nt * nt), ri = (warp / nt) % nt, ci = warp % nt;
+            const int o = pair * 2 * b;
+            double acc[2][2][2];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.0;
-                for (int k = c0; k < b; ++k) {                       // W11(k, c) = 0 for k < c
-                    double lv[4], wv[4];
+                for (int nj = 0; nj < 2; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+            for (int k4 = 16 * ci; k4 < b; k4 += 4) {
+                double af[2], bf[2];
+                const int k = k4 + lc;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) { lv[a] = T_(o + b + r0 + a, o + k); wv[a] = WG_(o + k, o + c0 + a); }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(lv[a], wv[bb], acc[a][bb]);
+                for (int q = 0; q < 2; ++q) {
+                    af[q] = T_(o + b + 16 * ri + q * 8 + lr, o + k);
+                    const int c = 16 * ci + q * 8 + lr;
+                    bf[q] = WL_(o + k, o + c);
                 }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) T_(o + c0 + bb, o + b + r0 + a) = acc[a][bb];   // X(r, c) kept at T(c, b + r)
+                    for (int nj = 0; nj < 2; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
             }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 16 * ri + mi * 8 + lr, c = 16 * ci + nj * 8 + 2 * lc + e;
+                        Xs[(pair * b + c) * XS_PITCH + r] = acc[mi][nj][e];
+                    }
         }
         __syncthreads();
-        for (int o = 0; o + b < POTRF_NB; o += 2 * b) {
-            const int tr = b >> 2, tc = b >> 2;
-            for (int tile = tid; tile < tr * tc; tile += DIAG_THREADS) {
-                const int r0 = (tile % tr) * 4, c0 = (tile / tr) * 4;
-                double acc[4][4];
+        // W21 = -W22 X  (W22 lower: k <= r), stored transposed into T's upper triangle
+        if (warp < njobs) {
+            const int pair = warp / (nt * nt), ri = (warp / nt) % nt, ci = warp % nt;
+            const int o = pair * 2 * b;
+            double acc[2][2][2];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) acc[a][bb] = 0.0;
-                for (int k = 0; k < r0 + 4; ++k) {
-                    double wv[4], xv[4];
+                for (int nj = 0; nj < 2; ++nj) acc[mi][nj][0] = acc[mi][nj][1] = 0.0;
+            for (int k4 = 0; k4 < 16 * ri + 16; k4 += 4) {
+                double af[2], bf[2];
+                const int k = k4 + lc;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) { wv[a] = WG_(o + b + r0 + a, o + b + k); xv[a] = T_(o + c0 + a, o + b + k); }
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-#pragma unroll
-                        for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fma(wv[a], xv[bb], acc[a][bb]);
+                for (int q = 0; q < 2; ++q) {
+                    const int r = 16 * ri + q * 8 + lr;
+                    af[q] = WL_(o + b + r, o + b + k);
+                    bf[q] = Xs[(pair * b + 16 * ci + q * 8 + lr) * XS_PITCH + k];
                 }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+                for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-                    for (int bb = 0; bb < 4; ++bb) W_(o + b + r0 + a, o + c0 + bb) = -acc[a][bb];
+                    for (int nj = 0; nj < 2; ++nj) dmma884(acc[mi][nj][0], acc[mi][nj][1], af[mi], bf[nj]);
             }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+                for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int r = 16 * ri + mi * 8 + lr, c = 16 * ci + nj * 8 + 2 * lc + e;
+                        T_(o + c, o + b + r) = -acc[mi][nj][e];        // W(o+b+r, o+c)
+                    }
         }
         __syncthreads();
     }
+    DIAG_PHASE(5);
     {
+        // inv(i,k) = W(i,k): coalesced global stores (i fastest); the transposed shared-memory reads are 4-way conflicted, once
         const int i = tid & (POTRF_NB - 1);
         for (int k = tid >> 7; k < POTRF_NB; k += DIAG_THREADS / POTRF_NB)
-            inv[i + (long)k * POTRF_NB] = (i < nb && k < nb && i >= k) ? W_(i, k) : 0.0;
+            inv[i + (long)k * POTRF_NB] = (i < nb && k < nb && i >= k) ? WL_(i, k) : 0.0;
     }
-#undef WG_
+    DIAG_PHASE(6);
+    if (dbg && tid == 0)
+        for (int i = 0; i < 7; ++i) atomicAdd((unsigned long long*)dbg + i, (unsigned long long)tk[i]);
+#undef DIAG_PHASE
+#undef WL_
 #undef T_
-#undef W_
 }
 
 int potrf_lower(kb_ctx* ctx, double* A, long ld, int p, double* invdiag, int* d_fail) {
     static const bool use_v1 = [] { const char* e = getenv("KB_POTRF_DIAG"); return e && e[0] == '1'; }();
     KB_CUDA(ctx, raise_max_dynamic_smem((const void*)potrf_diag_kernel, DIAG_SMEM));
     KB_CUDA(ctx, raise_max_dynamic_smem((const void*)potrf_diag_kernel_v1, DIAG_SMEM));
+    // KB_POTRF_PHASES=1: per-phase cycle counts of the diagonal kernel (thread 0's clock64), printed per factorisation
+    static const bool dbg_on = getenv("KB_POTRF_PHASES") != nullptr;
+    long long* dbg = nullptr;
+    if (dbg_on) {
+        cudaMalloc(&dbg, 8 * sizeof(long long));
+        cudaMemsetAsync(dbg, 0, 8 * sizeof(long long), ctx->stream);
+    }
     int blk = 0;
     for (int r0 = 0; r0 < p; r0 += POTRF_NB, ++blk) {
         const int nb = (p - r0 < POTRF_NB) ? p - r0 : POTRF_NB;
         double* Abb = A + r0 + (long)r0 * ld;
         double* inv = invdiag + (size_t)blk * POTRF_NB * POTRF_NB;
         if (use_v1) potrf_diag_kernel_v1<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0);
-        else potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0);
+        else potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0, dbg);
         ctx->launches++;
         KB_CUDA(ctx, cudaGetLastError());
         const int rem = p - r0 - nb;
@@ -569,6 +657,14 @@ int potrf_lower(kb_ctx* ctx, double* A, long ld, int p, double* invdiag, int* d_
         // A22 -= L21 L21'  (lower tiles)
         double* A22 = A + (r0 + nb) + (long)(r0 + nb) * ld;
         KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, rem, rem, nb, -1.0, A21, ld, A21, ld, 1.0, A22, ld, 0, 1, 0));
+    }
+    if (dbg) {
+        long long h[8];
+        cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(dbg);
+        fprintf(stderr, "[potrf_diag x%d, kcycles] load=%lld panel=%lld trailing=%lld storeL=%lld inv16=%lld doubling=%lld storeInv=%lld\n",
+                blk + 1, h[0] / 1000, h[1] / 1000, h[2] / 1000, h[3] / 1000, h[4] / 1000, h[5] / 1000, h[6] / 1000);
     }
     return zero_strict_upper(ctx, A, ld, p);
 }

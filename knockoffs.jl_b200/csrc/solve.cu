@@ -202,10 +202,15 @@ int eigmin_lower_dev(kb_ctx* ctx, const double* B, long ld, int p, double* work_
         const double mid = 0.5 * (lo + hi);
         if (!(mid > lo && mid < hi)) break;
         double est = NAN;
-        if (npts == 3) est = powerlaw_root(px, py);
-        if (!(est == est) && npts >= 2) {
+        if (npts >= 2) {
             const double a = px[npts - 2], ha = py[npts - 2], b = px[npts - 1], hb = py[npts - 1];
             if (ha > hb && hb > 0.0) est = b + hb * (b - a) / (ha - hb);       // secant root (>= λmin for concave h)
+        }
+        if (npts == 3 && est == est) {
+            // the curvature-corrected root must lie between the last success and the secant root; anything else is
+            // an ill-conditioned fit (three nearly collinear points) and is discarded
+            const double pl = powerlaw_root(px, py);
+            if (pl == pl && pl > px[2] && pl <= est) est = pl;
         }
         double sigma = mid;
         bool guided = false;
