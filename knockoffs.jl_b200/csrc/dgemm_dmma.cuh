@@ -21,23 +21,23 @@
 namespace kb {
 
 // CTA tile configurations (BN = 128, BK = 16, 3-stage cp.async pipeline in all of them):
-//   GemmCfg<128, 2, 4>  128 x 128, 8 warps of 64 x 32, 1 CTA / SM      (first kernel of round 1)
-//   GemmCfg< 64, 2, 2>   64 x 128, 4 warps of 32 x 64, 2 CTAs / SM: the two resident CTAs run out of phase, so one
-//                        feeds the DMMA pipe while the other sits at its k-tile barrier / waits for cp.async
+//   GemmCfg<128, 128, 2, 4, 1>  128 x 128, 8 warps of 64 x 32, 1 CTA / SM      (first kernel of round 1)
+//   GemmCfg< 64, 128, 2, 2, 2>   64 x 128, 4 warps of 32 x 64, 2 CTAs / SM: the two resident CTAs run out of phase, so
+//                                one feeds the DMMA pipe while the other sits at its k-tile barrier / waits for cp.async
+//   GemmCfg< 64,  64, 2, 2, 3>   64 x  64, 4 warps of 32 x 32, 3 CTAs / SM
 #ifndef KB_GEMM_BK
 #define KB_GEMM_BK 16
 #endif
 #ifndef KB_GEMM_STAGES
 #define KB_GEMM_STAGES 3
 #endif
-constexpr int GEMM_BN = 128;
 constexpr int GEMM_BK = KB_GEMM_BK;
 constexpr int GEMM_STAGES = KB_GEMM_STAGES;
 constexpr int GEMM_PADK = GEMM_BK + 4;   // [m][k] rows: stride mod 16 == 4 -> conflict-free fragments
 
-template <int BM_, int WM_, int WN_>
+template <int BM_, int BN_, int WM_, int WN_, int MIN_CTAS_>
 struct GemmCfg {
-    static constexpr int BM = BM_, BN = GEMM_BN, WM = WM_, WN = WN_;
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_;
     static constexpr int WARPS = WM * WN, THREADS = 32 * WARPS;
     static constexpr int MI = BM / WM / 8, NJ = BN / WN / 8;          // 8 x 8 DMMA tiles per warp
     static constexpr int PADM = BM + 4, PADN = BN + 4;                // [k][m] / [k][n] rows: stride mod 16 == 4
@@ -45,7 +45,7 @@ struct GemmCfg {
     static constexpr int B_TILE = (GEMM_BK * PADN > BN * GEMM_PADK) ? GEMM_BK * PADN : BN * GEMM_PADK;
     static constexpr int STAGE = A_TILE + B_TILE;
     static constexpr size_t SMEM_BYTES = (size_t)GEMM_STAGES * STAGE * sizeof(double);
-    static constexpr int MIN_CTAS = (BM <= 64) ? 2 : 1;
+    static constexpr int MIN_CTAS = MIN_CTAS_;
 };
 
 enum : int { A_MCONTIG = 0, A_KCONTIG = 1 };   // A(m,k) at m + k*lda   |   k + m*lda

@@ -2,6 +2,7 @@
 #include "linalg.cuh"
 #include <cstdarg>
 #include <cstdlib>
+#include <vector>
 #include <map>
 #include <mutex>
 
@@ -31,11 +32,14 @@ cudaError_t raise_max_dynamic_smem(const void* func, size_t bytes) {
 // ------------------------------------------------------------------------------------------
 // GEMM launcher
 // ------------------------------------------------------------------------------------------
-// CTA configuration: 64 x 128 / 4 warps / 2 CTAs per SM unless KB_GEMM_CFG=128 is defined at build time
+// CTA configuration (build-time; measured on B200 at p = 5000, profiles/r01_gemm_variants.md):
+//   default 64 x 64 / 4 warps / 3 CTAs per SM;  KB_GEMM_CFG=128: 128 x 128 / 8 warps / 1 CTA;  =6412: 64 x 128 / 4 warps / 2 CTAs
 #if defined(KB_GEMM_CFG) && KB_GEMM_CFG == 128
-using GemmDefaultCfg = GemmCfg<128, 2, 4>;
+using GemmDefaultCfg = GemmCfg<128, 128, 2, 4, 1>;
+#elif defined(KB_GEMM_CFG) && KB_GEMM_CFG == 6412
+using GemmDefaultCfg = GemmCfg<64, 128, 2, 2, 2>;
 #else
-using GemmDefaultCfg = GemmCfg<64, 2, 2>;
+using GemmDefaultCfg = GemmCfg<64, 64, 2, 2, 3>;
 #endif
 
 template <int AL, int BL, bool VEC>
@@ -640,20 +644,31 @@ int potrf_lower(kb_ctx* ctx, double* A, long ld, int p, double* invdiag, int* d_
         cudaMalloc(&dbg, 8 * sizeof(long long));
         cudaMemsetAsync(dbg, 0, 8 * sizeof(long long), ctx->stream);
     }
+    std::vector<cudaEvent_t> ev;
+    auto mark = [&]() {
+        if (!dbg_on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        ev.push_back(e);
+    };
     int blk = 0;
     for (int r0 = 0; r0 < p; r0 += POTRF_NB, ++blk) {
         const int nb = (p - r0 < POTRF_NB) ? p - r0 : POTRF_NB;
         double* Abb = A + r0 + (long)r0 * ld;
         double* inv = invdiag + (size_t)blk * POTRF_NB * POTRF_NB;
+        mark();
         if (use_v1) potrf_diag_kernel_v1<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0);
         else potrf_diag_kernel<<<1, DIAG_THREADS, DIAG_SMEM, ctx->stream>>>(Abb, ld, nb, inv, d_fail, r0, dbg);
         ctx->launches++;
         KB_CUDA(ctx, cudaGetLastError());
+        mark();
         const int rem = p - r0 - nb;
         if (rem <= 0) break;
         double* A21 = A + (r0 + nb) + (long)r0 * ld;
         // L21 = A21 * inv(L11)'   (in place: one N tile, each CTA reads only the rows it writes)
         KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, rem, nb, nb, 1.0, A21, ld, inv, POTRF_NB, 0.0, A21, ld));
+        mark();
         // A22 -= L21 L21'  (lower tiles)
         double* A22 = A + (r0 + nb) + (long)(r0 + nb) * ld;
         KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, rem, rem, nb, -1.0, A21, ld, A21, ld, 1.0, A22, ld, 0, 1, 0));
@@ -663,6 +678,14 @@ int potrf_lower(kb_ctx* ctx, double* A, long ld, int p, double* invdiag, int* d_
         cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
         cudaFree(dbg);
+        double t[3] = {0, 0, 0};
+        for (size_t i = 0; i + 1 < ev.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            t[i % 3] += ms;
+        }
+        fprintf(stderr, "[potrf p=%d, ms] diag=%.3f trsm=%.3f syrk=%.3f\n", p, t[0], t[1], t[2]);
+        for (auto& e : ev) cudaEventDestroy(e);
         fprintf(stderr, "[potrf_diag x%d, kcycles] load=%lld panel=%lld trailing=%lld storeL=%lld inv16=%lld doubling=%lld storeInv=%lld\n",
                 blk + 1, h[0] / 1000, h[1] / 1000, h[2] / 1000, h[3] / 1000, h[4] / 1000, h[5] / 1000, h[6] / 1000);
     }
