@@ -34,8 +34,9 @@ UNIT = "rows/s"
 NCU_TRAFFIC_BYTES = {
     # profiles/r01_ccd_stream_kernel_ncu_raw.csv: 375.47 GB read + 494.29 GB written per sweep launch (p = 5000)
     "ccd_stream_kernel": 869.76e9,
-    # profiles/r01_dgemm_dmma_kernel_sampling_ncu_raw.csv: one 4096-row chunk GEMM (2 segments): 1.015 GB + 0.138 GB
-    "dgemm_dmma_kernel": 1.153e9,
+    # profiles/r01b_dgemm_dmma_kernel_sampling_ncu_raw.csv: one 4096-row chunk GEMM of the sampling stage (two K = 5000
+    # segments, 64 x 64 tiles): 5.666 GB read + 0.165 GB written (algorithmic: 0.73 GB of operands + 0.33 GB of C)
+    "dgemm_dmma_kernel": 5.831e9,
 }
 
 

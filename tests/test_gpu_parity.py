@@ -481,7 +481,10 @@ def test_sharded_group_solve_equals_full_solve(kb, method):
     V1, V2 = go.get_PCA_vectors(S1, list(g1)), go.get_PCA_vectors(S2, list(g2))
     Vfull = _blockdiag_rect(V1, V2)
     m = 3
-    want_S, _, want_obj = kb.solve_s_group(full, groups_full, method, m=m, V=Vfull, tol=1e-3, ctx=kb.Context(0))
+    # :sdp stops on |Δobj/obj| < tol of a piecewise-linear objective: run it to a tight tolerance so both runs reach the
+    # optimum's plateau instead of stopping tol apart
+    tol = 1e-6 if method == "sdp" else 1e-3
+    want_S, _, want_obj = kb.solve_s_group(full, groups_full, method, m=m, V=Vfull, tol=tol, ctx=kb.Context(0))
     slots = [None, None]
     bar = threading.Barrier(2)
     out = [None, None]
@@ -496,7 +499,7 @@ def test_sharded_group_solve_equals_full_solve(kb, method):
             bar.wait(timeout=60)
             vals[:] = res
         try:
-            out[rank] = kb.solve_s_group_sharded(Sig, grp, method, reduce, m=m, V=V, tol=1e-3, ctx=kb.Context(0))
+            out[rank] = kb.solve_s_group_sharded(Sig, grp, method, reduce, m=m, V=V, tol=tol, ctx=kb.Context(0))
         except Exception as e:                       # noqa: BLE001
             out[rank] = e
             bar.abort()
@@ -524,7 +527,8 @@ def test_sharded_group_solve_equals_full_solve(kb, method):
         S_sh = _blockdiag([out[0][0], out[1][0]])
         kap = (m + 1) / m
         for S_ in (S_sh, want_S):
-            assert np.linalg.eigvalsh(S_).min() > -1e-7 and np.linalg.eigvalsh(kap * full - S_).min() > -1e-7
+            # feasible up to the solver's own 1-D step margin eps = 1e-6 (group.jl:1176-1177)
+            assert np.linalg.eigvalsh(S_).min() > -1e-6 and np.linalg.eigvalsh(kap * full - S_).min() > -1e-6
     assert abs(out[0][1] + out[1][1] - want_obj) < tol_obj
     assert out[0][2]["inner_sweeps"] == out[1][2]["inner_sweeps"]
 
