@@ -39,7 +39,10 @@ using GemmDefaultCfg = GemmCfg<128, 128, 2, 4, 1>;
 #elif defined(KB_GEMM_CFG) && KB_GEMM_CFG == 6412
 using GemmDefaultCfg = GemmCfg<64, 128, 2, 2, 2>;
 #else
-using GemmDefaultCfg = GemmCfg<64, 64, 2, 2, 3>;
+#ifndef KB_GEMM_MINCTAS
+#define KB_GEMM_MINCTAS 3
+#endif
+using GemmDefaultCfg = GemmCfg<64, 64, 2, 2, KB_GEMM_MINCTAS>;
 #endif
 
 template <int AL, int BL, bool VEC>
