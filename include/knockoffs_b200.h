@@ -228,6 +228,45 @@ int kb_sample_dev(kb_ctx* ctx, const double* dX, int64_t n, int64_t ldx, int64_t
                   const double* dSigmaInvS, const double* dLblocks, int32_t m, const double* dZ, int64_t ldz,
                   uint64_t seed, int64_t row_offset, double* dXko, int64_t ldxko);
 
+/* ---- (5) feature statistics and the knockoff filter (the step right after sampling) ----
+ * Importance scores of `fit_marginal` (fit_lasso.jl:214-222): with y_std = zscore(y), X_std / X̃_std the
+ * column-wise z-scores (corrected std), T0 = abs2.(X_std' y_std) ./ n and Tk likewise for copy k.
+ * T_out = [T0 | T1 | ... | Tm], (m+1)·p doubles.  One HBM-bound pass over X and X̃ (8·n·(m+1)·p bytes). */
+int kb_marginal_stats(kb_ctx* ctx, const double* y, const double* X, const double* Xko, int64_t n, int64_t p,
+                      int32_t m, double* T_out);
+int kb_marginal_stats_dev(kb_ctx* ctx, const double* dy, const double* dX, int64_t ldx, const double* dXko,
+                          int64_t ldxko, int64_t n, int64_t p, int32_t m, double* dT_out);
+/* `MK_statistics(T0, Tk)` (threshold.jl:96-120 for m > 1: κ, τ, W; :134-142 for m == 1: W only, kappa_out /
+ * tau_out untouched and may be NULL).  Tk = [T1 | ... | Tm] (m·p).  κ is the LAST k with |Tk| > |T0| and the
+ * filter is the median, exactly as the reference computes them. */
+int kb_mk_statistics(kb_ctx* ctx, const double* T0, const double* Tk, int64_t p, int32_t m, int64_t* kappa_out,
+                     double* tau_out, double* W_out);
+/* `threshold(w, q, method, rej_bounds)` (threshold.jl:19-31); knockoff_plus: 1 = :knockoff_plus, 0 = :knockoff;
+ * reference default rej_bounds = 10000.  tau_out = +Inf when no threshold qualifies. */
+int kb_threshold(kb_ctx* ctx, const double* w, int64_t p, double q, int32_t knockoff_plus, int64_t rej_bounds,
+                 double* tau_out);
+/* `mk_threshold(τ, κ, m, q, :knockoff_plus, rej_bounds)` (threshold.jl:55-75). */
+int kb_mk_threshold(kb_ctx* ctx, const double* tau, const int64_t* kappa, int64_t p, int32_t m, double q,
+                    int64_t rej_bounds, double* tau_hat_out);
+/* `fit_marginal(y, ko; fdrs, filter_method)` (fit_lasso.jl:201-257) on an existing knockoff (X, Xko host
+ * matrices): scores, optional group sums (groups != NULL: W has one entry per unique group, in order of first
+ * appearance, fit_lasso.jl:224-238), MK_statistics, one threshold per target FDR and the selections.
+ * Outputs (host; T_out, kappa_out, tau_out, selected_out, n_w_out may be NULL): T_out (m+1)·p, W_out n_w,
+ * kappa_out / tau_out n_w (m > 1 only), taus_out nfdr, selected_out n_w x nfdr 0/1 mask (column f =
+ * `findall(x -> x >= τ̂_f, W)`), n_w_out = length of W (p, or the number of groups). */
+int kb_marginal_filter(kb_ctx* ctx, const double* y, const double* X, const double* Xko, int64_t n, int64_t p,
+                       int32_t m, const int64_t* groups, const double* fdrs, int32_t nfdr, int32_t knockoff_plus,
+                       double* T_out, double* W_out, int64_t* kappa_out, double* tau_out, double* taus_out,
+                       int32_t* selected_out, int64_t* n_w_out);
+/* `fit_marginal(y, X, μ, Σ; method, m, fdrs, filter_method)` (fit_lasso.jl:188-200 + 201-257), fused: the
+ * knockoffs are generated chunk by chunk and their scores accumulated while each chunk is still on the
+ * device, so X̃ is never stored nor copied back unless Xko_out != NULL (removes the n·m·p·8-byte D2H). */
+int kb_fit_marginal(kb_ctx* ctx, const double* y, const double* X, int64_t n, int64_t p, const double* mu,
+                    const double* Sigma, int32_t method, int32_t m, const kb_solve_opts* opts, const double* fdrs,
+                    int32_t nfdr, int32_t knockoff_plus, const double* Z, uint64_t seed, double* Xko_out,
+                    double* s_out, double* T_out, double* W_out, int64_t* kappa_out, double* tau_out,
+                    double* taus_out, int32_t* selected_out, kb_solve_info* info);
+
 /* ---- test hooks (exercised by tests/, not part of the reference interface) -------------------- */
 /* C (M x N, col-major) = alpha * op(A) * op(B) + beta * C on the hand-written DMMA kernel.
  * transa / transb: 0 = 'N', 1 = 'T' (BLAS dgemm semantics, host pointers). */

@@ -78,6 +78,15 @@ SIGNATURES = {
     "kb_sample_dev": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _u64, _i64, _vp, _i64]),
     "kb_modelx_gaussian_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, C.POINTER(SolveOpts), _vp,
                                                _vp, _u64, _i64, _vp, _vp, C.POINTER(SolveInfo)]),
+    "kb_marginal_stats": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]),
+    "kb_marginal_stats_dev": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
+    "kb_mk_statistics": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "kb_threshold": (C.c_int, [_vp, _vp, _i64, _d, _i32, _i64, c_double_p]),
+    "kb_mk_threshold": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _d, _i64, c_double_p]),
+    "kb_marginal_filter": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
+                                     _vp, _vp, C.POINTER(_i64)]),
+    "kb_fit_marginal": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, C.POINTER(SolveOpts), _vp, _i32,
+                                  _i32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SolveInfo)]),
     "kb_test_dgemm": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_potrf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_spd_inverse": (C.c_int, [_vp, _vp, _i64, _vp]),

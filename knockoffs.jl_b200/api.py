@@ -441,6 +441,168 @@ def modelX_gaussian_group_knockoffs(X, method, groups, mu, Sigma, m=1, V=None, Z
     return GaussianGroupKnockoff(X, Xko, groups, S, np.zeros(0), m, Ssym, str(method).lstrip(":"), obj.value, d)
 
 
+
+# ---- feature statistics and the knockoff filter ----------------------------------------
+DEFAULT_FDRS = (0.01, 0.05, 0.1, 0.25, 0.5)                        # fit_lasso.jl:196
+
+
+def _filter_flag(method) -> int:
+    name = str(method).lstrip(":")
+    if name == "knockoff":
+        return 0
+    if name == "knockoff_plus":
+        return 1
+    raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"method should be :knockoff or :knockoff_plus but was {name}.")
+
+
+def threshold(w, q, method="knockoff_plus", rej_bounds=10000, ctx: Optional[Context] = None) -> float:
+    """``threshold(w, q, method, rej_bounds)`` -- src/threshold.jl:19-31."""
+    ctx = ctx or default_context()
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    out = C.c_double()
+    check(ctx.h, ctx._lib.kb_threshold(ctx.h, _ptr(w), w.size, float(q), _filter_flag(method), int(rej_bounds),
+                                       C.byref(out)))
+    return out.value
+
+
+def mk_threshold(tau, kappa, m, q, method="knockoff_plus", rej_bounds=10000, ctx: Optional[Context] = None) -> float:
+    """``mk_threshold(τ, κ, m, q, method, rej_bounds)`` -- src/threshold.jl:55-75."""
+    ctx = ctx or default_context()
+    if str(method).lstrip(":") != "knockoff_plus":                 # threshold.jl:59
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Multiple knockoffs needs to use :knockoff_plus filtering method")
+    tau = np.ascontiguousarray(tau, dtype=np.float64)
+    kappa = np.ascontiguousarray(kappa, dtype=np.int64)
+    if tau.size != kappa.size:                                     # threshold.jl:60
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Length of τ and κ should be the same")
+    out = C.c_double()
+    check(ctx.h, ctx._lib.kb_mk_threshold(ctx.h, _ptr(tau), _ptr(kappa), tau.size, int(m), float(q), int(rej_bounds),
+                                          C.byref(out)))
+    return out.value
+
+
+def MK_statistics(T0, Tk, ctx: Optional[Context] = None):
+    """``MK_statistics(T0, Tk)`` -- src/threshold.jl:96-120 (``Tk`` a list of m > 1 vectors: returns (κ, τ, W))
+    and :134-142 (``Tk`` one vector: returns W)."""
+    ctx = ctx or default_context()
+    T0 = np.ascontiguousarray(T0, dtype=np.float64)
+    p = T0.size
+    single = np.ndim(Tk[0]) == 0 if len(Tk) else True
+    Tm = np.ascontiguousarray(Tk, dtype=np.float64).reshape(1 if single else len(Tk), -1)
+    m = Tm.shape[0]
+    if Tm.shape[1] != p:                                           # threshold.jl:102, :136
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Length of T0 should equal all vectors in Tk")
+    W = np.empty(p)
+    kappa = np.zeros(p, dtype=np.int64)
+    tau = np.zeros(p)
+    check(ctx.h, ctx._lib.kb_mk_statistics(ctx.h, _ptr(T0), _ptr(Tm), p, m, _ptr(kappa), _ptr(tau), _ptr(W)))
+    return W if single else (kappa, tau, W)
+
+
+def marginal_stats(y, X, Xko, m=1, ctx: Optional[Context] = None):
+    """Importance scores of ``fit_marginal`` (src/fit_lasso.jl:214-222): (T0, [T1, ..., Tm])."""
+    ctx = ctx or default_context()
+    X, Xko = _f(X), _f(Xko)
+    n, p = X.shape
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    if y.size != n or Xko.shape != (n, m * p):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "dimension mismatch between y, X and Xko")
+    T = np.empty((m + 1) * p)
+    check(ctx.h, ctx._lib.kb_marginal_stats(ctx.h, _ptr(y), _ptr(X), _ptr(Xko), n, p, int(m), _ptr(T)))
+    return T[:p], [T[(k + 1) * p:(k + 2) * p] for k in range(m)]
+
+
+@dataclass
+class MarginalKnockoffFilter:
+    """src/struct.jl:134-146 (``d`` is always Normal here; ``kappa``/``tau``/``T0``/``Tk`` are extras)."""
+    y: np.ndarray
+    X: np.ndarray
+    ko: object
+    W: np.ndarray
+    taus: np.ndarray
+    m: int
+    selected: list
+    fdr_target: np.ndarray
+    kappa: Optional[np.ndarray] = None
+    tau: Optional[np.ndarray] = None
+    T0: Optional[np.ndarray] = None
+    Tk: Optional[list] = None
+
+
+def _unpack_filter(p, m, nw, T, W, kappa, tau, taus, sel):
+    W = W[:nw]
+    selected = [np.flatnonzero(sel[f * nw:(f + 1) * nw]) + 1 for f in range(len(taus))]   # 1-based like findall
+    return dict(W=W, taus=taus, selected=selected, kappa=kappa[:nw] if m > 1 else None, tau=tau[:nw] if m > 1 else None,
+                T0=T[:p], Tk=[T[(k + 1) * p:(k + 2) * p] for k in range(m)])
+
+
+def fit_marginal(y, X_or_ko, mu=None, Sigma=None, method="maxent", m=1, fdrs=DEFAULT_FDRS, groups=None,
+                 filter_method="knockoff_plus", Z=None, seed=0, keep_knockoffs=True, ctx: Optional[Context] = None,
+                 **kwargs) -> MarginalKnockoffFilter:
+    """``fit_marginal`` -- src/fit_lasso.jl:188-257.
+
+    ``fit_marginal(y, ko)`` (``ko`` a GaussianKnockoff / GaussianGroupKnockoff) scores an existing knockoff;
+    ``fit_marginal(y, X, mu, Sigma, method=..., m=...)`` generates the knockoffs first.  Without ``groups`` that is
+    ONE fused library call in which X̃ is scored chunk by chunk on the device (``keep_knockoffs=False``: X̃ is never
+    copied back, ``ko.Xko`` is None); with ``groups`` the group knockoffs are generated, then scored.  Selected
+    indices are 1-based like the reference's ``findall``."""
+    ctx = ctx or default_context()
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    fd = np.ascontiguousarray(fdrs, dtype=np.float64)
+    plus = _filter_flag(filter_method)
+    if isinstance(X_or_ko, (GaussianKnockoff, GaussianGroupKnockoff)):
+        ko = X_or_ko
+    elif groups is not None:
+        if mu is None:
+            Sigma, mu, _ = cov_shrink_lw(X_or_ko, ctx=ctx)
+        ko = modelX_gaussian_group_knockoffs(X_or_ko, method, groups, mu, Sigma, m=m, Z=Z, seed=seed, ctx=ctx, **kwargs)
+    else:
+        X = _f(X_or_ko)
+        n, p = X.shape
+        m = int(m)
+        if m < 1:
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
+        if y.size != n:
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "dimension mismatch between y and X")
+        if Sigma is None:
+            Sigma, mu, _ = cov_shrink_lw(X, ctx=ctx)               # fit_lasso.jl:199 -> modelX.jl:47-49
+        Sigma = _f(Sigma)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        opts = make_opts(**kwargs)
+        info = SolveInfo()
+        Zf = None if Z is None else _f(Z)
+        if Zf is not None and Zf.shape != (n, m * p):
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
+        Xko = np.empty((n, m * p), order="F") if keep_knockoffs else None
+        s = np.empty(p)
+        T, W = np.empty((m + 1) * p), np.empty(p)
+        kappa, tau = np.zeros(p, dtype=np.int64), np.zeros(p)
+        taus, sel = np.empty(fd.size), np.zeros(p * max(1, fd.size), dtype=np.int32)
+        rc = ctx._lib.kb_fit_marginal(ctx.h, _ptr(y), _ptr(X), n, p, _ptr(mu), _ptr(Sigma), _method_id(method), m,
+                                      C.byref(opts), _ptr(fd), fd.size, plus, _ptr(Zf), int(seed), _ptr(Xko), _ptr(s),
+                                      _ptr(T), _ptr(W), _ptr(kappa), _ptr(tau), _ptr(taus), _ptr(sel), C.byref(info))
+        check(ctx.h, rc)
+        Ssym = np.triu(Sigma) + np.triu(Sigma, 1).T
+        ko = GaussianKnockoff(X, Xko, s, Ssym, str(method).lstrip(":"), m, _info_dict(info, str(method).lstrip(":")))
+        r = _unpack_filter(p, m, p, T, W, kappa, tau, taus, sel)
+        return MarginalKnockoffFilter(y, X, ko, r["W"], r["taus"], m, r["selected"], fd, r["kappa"], r["tau"], r["T0"], r["Tk"])
+    # score an existing knockoff (fit_lasso.jl:201-257)
+    X, Xko, m = _f(ko.X), _f(ko.Xko), int(ko.m)
+    n, p = X.shape
+    if y.size != n:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "dimension mismatch between y and X")
+    g = getattr(ko, "groups", None)
+    gi = None if g is None else np.ascontiguousarray(g, dtype=np.int64)
+    T, W = np.empty((m + 1) * p), np.empty(p)
+    kappa, tau = np.zeros(p, dtype=np.int64), np.zeros(p)
+    taus, sel = np.empty(fd.size), np.zeros(p * max(1, fd.size), dtype=np.int32)
+    nw = C.c_int64()
+    rc = ctx._lib.kb_marginal_filter(ctx.h, _ptr(y), _ptr(X), _ptr(Xko), n, p, m, _ptr(gi), _ptr(fd), fd.size, plus,
+                                     _ptr(T), _ptr(W), _ptr(kappa), _ptr(tau), _ptr(taus), _ptr(sel), C.byref(nw))
+    check(ctx.h, rc)
+    r = _unpack_filter(p, m, nw.value, T, W, kappa, tau, taus, sel)
+    return MarginalKnockoffFilter(y, X, ko, r["W"], r["taus"], m, r["selected"], fd, r["kappa"], r["tau"], r["T0"], r["Tk"])
+
+
 # ---- hooks used by tests ---------------------------------------------------------------------------
 def hook_dgemm(A, B, C_in=None, transa=False, transb=False, alpha=1.0, beta=0.0, ctx: Optional[Context] = None):
     ctx = ctx or default_context()

@@ -4,7 +4,9 @@
 #include "linalg.cuh"
 #include "pipeline.cuh"
 #include "group.cuh"
+#include "stats.cuh"
 #include <algorithm>
+#include <unordered_map>
 #include <cstring>
 #include <cstdlib>
 #include <new>
@@ -39,11 +41,19 @@ int d2h_matrix(kb_ctx* ctx, const double* d, long dld, double* h, long hld, long
     return KB_OK;
 }
 
+// Marginal-statistic accumulators fed by the sampling pipeline chunk by chunk (fit_marginal: X̃ is consumed
+// while it is still on the device).
+struct StatsHook {
+    const double* dys;   // y_std, n doubles on the device
+    double* dacc_x;      // STATS_ACC * p
+    double* dacc_ko;     // STATS_ACC * m p
+};
+
 // Row-chunk pipeline for host-resident X / Z / X̃: H2D of chunk i+1 and D2H of chunk i-1 overlap the
-// GEMMs of chunk i (three streams, double-buffered device slabs).
+// GEMMs of chunk i (three streams, double-buffered device slabs).  Xko == NULL: X̃ is not copied back.
 int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const double* dmu, const double* dSiS,
                          const double* dLb, long ldo, int m, const double* Z, uint64_t seed, int64_t row_offset,
-                         double* Xko) {
+                         double* Xko, const StatsHook* hook = nullptr) {
     if (n <= 0) return KB_OK;
     long chunk = ctx->sample_chunk_rows > 0 ? ctx->sample_chunk_rows : 4096;
     if (chunk > n) chunk = n;
@@ -73,14 +83,101 @@ int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const doub
         if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[b], 0));
         KB_TRY(sample_chunk(ctx, plan, dXc[b], rows, chunk, Z ? dZc[b] : nullptr, chunk, seed, row_offset + r0, dOut[b],
                             chunk));
+        if (hook) {
+            KB_TRY(marginal_accumulate_dev(ctx, dXc[b], rows, chunk, p, hook->dys + r0, hook->dacc_x, r0 == 0));
+            KB_TRY(marginal_accumulate_dev(ctx, dOut[b], rows, chunk, (long)p * m, hook->dys + r0, hook->dacc_ko, r0 == 0));
+        }
         KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
         KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ev_comp[b], 0));
-        KB_TRY(d2h_matrix(ctx, dOut[b], chunk, Xko + r0, n, rows, (long)p * m, ctx->stream_d2h));
+        if (Xko) KB_TRY(d2h_matrix(ctx, dOut[b], chunk, Xko + r0, n, rows, (long)p * m, ctx->stream_d2h));
         KB_CUDA(ctx, cudaEventRecord(ev_d2h[b], ctx->stream_d2h));
     }
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_d2h));
+    return KB_OK;
+}
+
+// Accumulate the marginal-statistic sums of a HOST matrix A (n x ncols, ld n) against dys: row chunks, H2D of
+// chunk i+1 overlapping the reduction of chunk i.
+int host_marginal_accumulate(kb_ctx* ctx, const double* A, long n, long ncols, const double* dys, double* dacc) {
+    Scope sc(ctx);
+    long chunk = (long)(((size_t)256 << 20) / (sizeof(double) * (size_t)std::max(1L, ncols)));   // ~256 MB slabs
+    chunk = std::max(1024L, std::min(chunk, n));
+    if (chunk > n) chunk = n;
+    double* dA[2];
+    for (int b = 0; b < 2; ++b) KB_TRY(sc.alloc(&dA[b], (size_t)chunk * ncols));
+    cudaEvent_t* ev_h2d = ctx->pipe_ev;
+    cudaEvent_t* ev_comp = ctx->pipe_ev + 2;
+    long i = 0;
+    for (long r0 = 0; r0 < n; r0 += chunk, ++i) {
+        const int b = (int)(i & 1);
+        const long rows = std::min(chunk, n - r0);
+        if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
+        KB_TRY(h2d_matrix(ctx, A + r0, n, dA[b], chunk, rows, ncols, ctx->stream_h2d));
+        KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
+        KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
+        KB_TRY(marginal_accumulate_dev(ctx, dA[b], rows, chunk, ncols, dys + r0, dacc, r0 == 0));
+        KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+// fit_marginal's tail (fit_lasso.jl:223-256) from the importance scores dT = [T0 | T1 | ... | Tm] ((m+1) p, device):
+// optional group sums, MK_statistics, one threshold per target FDR, the selected sets.  Host outputs; optional ones
+// may be NULL.  selected_out: n_w x nfdr 0/1 mask (column f = findall(W .>= τ̂_f)).
+int knockoff_filter_from_T(kb_ctx* ctx, const double* dT, long p, int m, const int64_t* groups, const double* fdrs, int nfdr,
+                           int knockoff_plus, long rej_bounds, double* W_out, int64_t* kappa_out, double* tau_out,
+                           double* taus_out, int32_t* selected_out, int64_t* n_w_out) {
+    if (nfdr < 0 || (nfdr > 0 && (!fdrs || !taus_out))) return set_error(ctx, KB_ERR_INVALID, "knockoff filter: bad fdr arguments");
+    if (m > 1 && !knockoff_plus)                                   // threshold.jl:59
+        return set_error(ctx, KB_ERR_INVALID, "Multiple knockoffs needs to use :knockoff_plus filtering method");
+    Scope sc(ctx);
+    long nw = p;
+    const double* dTs = dT;
+    if (groups) {
+        // unique(groups) in order of first appearance (fit_lasso.jl:225)
+        std::unordered_map<int64_t, int> ids;
+        std::vector<int> gidx((size_t)p);
+        for (long j = 0; j < p; ++j) {
+            auto it = ids.find(groups[j]);
+            if (it == ids.end()) it = ids.emplace(groups[j], (int)ids.size()).first;
+            gidx[(size_t)j] = it->second;
+        }
+        nw = (long)ids.size();
+        int* dgidx;
+        double* dTg;
+        KB_TRY(sc.alloc(&dgidx, (size_t)p));
+        KB_TRY(sc.alloc(&dTg, (size_t)(m + 1) * nw));
+        KB_CUDA(ctx, cudaMemcpyAsync(dgidx, gidx.data(), sizeof(int) * p, cudaMemcpyHostToDevice, ctx->stream));
+        KB_TRY(group_abs_sum_dev(ctx, dT, p, m + 1, dgidx, (int)nw, dTg));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // gidx goes out of scope
+        dTs = dTg;
+    }
+    double *dW, *dtau, *dth;
+    long long* dkap;
+    int* dsel;
+    KB_TRY(sc.alloc(&dW, (size_t)nw));
+    KB_TRY(sc.alloc(&dtau, (size_t)nw));
+    KB_TRY(sc.alloc(&dkap, (size_t)nw));
+    KB_TRY(sc.alloc(&dth, (size_t)std::max(1, nfdr)));
+    KB_TRY(sc.alloc(&dsel, (size_t)nw * std::max(1, nfdr)));
+    KB_TRY(mk_statistics_dev(ctx, dTs, dTs + nw, nw, m, dkap, dtau, dW));
+    for (int f = 0; f < nfdr; ++f) {
+        if (m > 1) KB_TRY(mk_threshold_dev(ctx, dtau, dkap, nw, m, fdrs[f], rej_bounds, dth + f));   // fit_lasso.jl:249
+        else KB_TRY(threshold_dev(ctx, dW, nw, fdrs[f], knockoff_plus ? 1 : 0, rej_bounds, dth + f));
+        KB_TRY(select_dev(ctx, dW, nw, dth + f, dsel + (size_t)f * nw));
+    }
+    if (W_out) KB_CUDA(ctx, cudaMemcpyAsync(W_out, dW, sizeof(double) * nw, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m > 1 && kappa_out) KB_CUDA(ctx, cudaMemcpyAsync(kappa_out, dkap, sizeof(int64_t) * nw, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m > 1 && tau_out) KB_CUDA(ctx, cudaMemcpyAsync(tau_out, dtau, sizeof(double) * nw, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nfdr > 0) KB_CUDA(ctx, cudaMemcpyAsync(taus_out, dth, sizeof(double) * nfdr, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nfdr > 0 && selected_out)
+        KB_CUDA(ctx, cudaMemcpyAsync(selected_out, dsel, sizeof(int32_t) * nw * nfdr, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_w_out) *n_w_out = nw;
     return KB_OK;
 }
 
@@ -470,6 +567,178 @@ int kb_modelx_gaussian_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_
     KB_TRY(sc.alloc(&dLb, pp * nblk));
     KB_TRY(cond_factor_dev(ctx, dSig, (long)p, (int)p, ds, (long)p, 1, m, dSiS, dLb, (long)p));
     return sample_host_pipeline(ctx, X, (long)n, (int)p, dmu, dSiS, dLb, (long)p, m, Z, seed, row_offset, Xko_out);
+}
+
+
+// ---- (5) feature statistics and the knockoff filter ----------------------------------
+int kb_marginal_stats_dev(kb_ctx* ctx, const double* dy, const double* dX, int64_t ldx, const double* dXko, int64_t ldxko,
+                          int64_t n, int64_t p, int32_t m, double* dT_out) {
+    if (!ctx) return bad_ctx();
+    if (!dy || !dX || !dXko || !dT_out || p < 1 || n < 2 || m < 1 || ldx < n || ldxko < n)
+        return set_error(ctx, KB_ERR_INVALID, "marginal_stats: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double *dys, *dsum, *dacc;
+    KB_TRY(sc.alloc(&dys, (size_t)n));
+    KB_TRY(sc.alloc(&dsum, 4));
+    KB_TRY(sc.alloc(&dacc, (size_t)STATS_ACC * (m + 1) * p));
+    KB_TRY(zscore_vec_dev(ctx, dy, (long)n, dys, dsum));
+    KB_TRY(marginal_accumulate_dev(ctx, dX, (long)n, (long)ldx, (long)p, dys, dacc, 1));
+    KB_TRY(marginal_accumulate_dev(ctx, dXko, (long)n, (long)ldxko, (long)p * m, dys, dacc + (size_t)STATS_ACC * p, 1));
+    KB_TRY(marginal_finish_dev(ctx, dacc, (long)(m + 1) * p, (long)n, dsum, dT_out));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_marginal_stats(kb_ctx* ctx, const double* y, const double* X, const double* Xko, int64_t n, int64_t p, int32_t m,
+                      double* T_out) {
+    if (!ctx) return bad_ctx();
+    if (!y || !X || !Xko || !T_out || p < 1 || n < 2 || m < 1) return set_error(ctx, KB_ERR_INVALID, "marginal_stats: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const long nc = (long)(m + 1) * p;
+    double *dy, *dys, *dsum, *dacc, *dT;
+    KB_TRY(sc.alloc(&dy, (size_t)n));
+    KB_TRY(sc.alloc(&dys, (size_t)n));
+    KB_TRY(sc.alloc(&dsum, 4));
+    KB_TRY(sc.alloc(&dacc, (size_t)STATS_ACC * nc));
+    KB_TRY(sc.alloc(&dT, (size_t)nc));
+    KB_CUDA(ctx, cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(zscore_vec_dev(ctx, dy, (long)n, dys, dsum));
+    KB_TRY(host_marginal_accumulate(ctx, X, (long)n, (long)p, dys, dacc));
+    KB_TRY(host_marginal_accumulate(ctx, Xko, (long)n, (long)p * m, dys, dacc + (size_t)STATS_ACC * p));
+    KB_TRY(marginal_finish_dev(ctx, dacc, nc, (long)n, dsum, dT));
+    KB_CUDA(ctx, cudaMemcpyAsync(T_out, dT, sizeof(double) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_mk_statistics(kb_ctx* ctx, const double* T0, const double* Tk, int64_t p, int32_t m, int64_t* kappa_out,
+                     double* tau_out, double* W_out) {
+    if (!ctx) return bad_ctx();
+    if (!T0 || !Tk || !W_out || p < 0 || m < 1 || (m > 1 && (!kappa_out || !tau_out)))
+        return set_error(ctx, KB_ERR_INVALID, "MK_statistics: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const size_t pp = (size_t)std::max<int64_t>(1, p);
+    double *dT0, *dTk, *dtau, *dW;
+    long long* dkap;
+    KB_TRY(sc.alloc(&dT0, pp));
+    KB_TRY(sc.alloc(&dTk, pp * m));
+    KB_TRY(sc.alloc(&dtau, pp));
+    KB_TRY(sc.alloc(&dW, pp));
+    KB_TRY(sc.alloc(&dkap, pp));
+    KB_CUDA(ctx, cudaMemcpyAsync(dT0, T0, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dTk, Tk, sizeof(double) * p * m, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(mk_statistics_dev(ctx, dT0, dTk, (long)p, m, dkap, dtau, dW));
+    KB_CUDA(ctx, cudaMemcpyAsync(W_out, dW, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    if (m > 1) {
+        KB_CUDA(ctx, cudaMemcpyAsync(kappa_out, dkap, sizeof(int64_t) * p, cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaMemcpyAsync(tau_out, dtau, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_threshold(kb_ctx* ctx, const double* w, int64_t p, double q, int32_t knockoff_plus, int64_t rej_bounds,
+                 double* tau_out) {
+    if (!ctx) return bad_ctx();
+    if (!w || !tau_out || p < 0) return set_error(ctx, KB_ERR_INVALID, "threshold: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double *dw, *dout;
+    KB_TRY(sc.alloc(&dw, (size_t)std::max<int64_t>(1, p)));
+    KB_TRY(sc.alloc(&dout, 4));
+    KB_CUDA(ctx, cudaMemcpyAsync(dw, w, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(threshold_dev(ctx, dw, (long)p, q, knockoff_plus ? 1 : 0, (long)rej_bounds, dout));
+    KB_CUDA(ctx, cudaMemcpyAsync(tau_out, dout, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_mk_threshold(kb_ctx* ctx, const double* tau, const int64_t* kappa, int64_t p, int32_t m, double q,
+                    int64_t rej_bounds, double* tau_hat_out) {
+    if (!ctx) return bad_ctx();
+    if (!tau || !kappa || !tau_hat_out || p < 0) return set_error(ctx, KB_ERR_INVALID, "mk_threshold: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double *dtau, *dout;
+    long long* dkap;
+    KB_TRY(sc.alloc(&dtau, (size_t)std::max<int64_t>(1, p)));
+    KB_TRY(sc.alloc(&dkap, (size_t)std::max<int64_t>(1, p)));
+    KB_TRY(sc.alloc(&dout, 4));
+    KB_CUDA(ctx, cudaMemcpyAsync(dtau, tau, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dkap, kappa, sizeof(int64_t) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(mk_threshold_dev(ctx, dtau, dkap, (long)p, m, q, (long)rej_bounds, dout));
+    KB_CUDA(ctx, cudaMemcpyAsync(tau_hat_out, dout, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_marginal_filter(kb_ctx* ctx, const double* y, const double* X, const double* Xko, int64_t n, int64_t p, int32_t m,
+                       const int64_t* groups, const double* fdrs, int32_t nfdr, int32_t knockoff_plus, double* T_out,
+                       double* W_out, int64_t* kappa_out, double* tau_out, double* taus_out, int32_t* selected_out,
+                       int64_t* n_w_out) {
+    if (!ctx) return bad_ctx();
+    if (!y || !X || !Xko || p < 1 || n < 2 || m < 1) return set_error(ctx, KB_ERR_INVALID, "marginal_filter: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const long nc = (long)(m + 1) * p;
+    double *dy, *dys, *dsum, *dacc, *dT;
+    KB_TRY(sc.alloc(&dy, (size_t)n));
+    KB_TRY(sc.alloc(&dys, (size_t)n));
+    KB_TRY(sc.alloc(&dsum, 4));
+    KB_TRY(sc.alloc(&dacc, (size_t)STATS_ACC * nc));
+    KB_TRY(sc.alloc(&dT, (size_t)nc));
+    KB_CUDA(ctx, cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(zscore_vec_dev(ctx, dy, (long)n, dys, dsum));
+    KB_TRY(host_marginal_accumulate(ctx, X, (long)n, (long)p, dys, dacc));
+    KB_TRY(host_marginal_accumulate(ctx, Xko, (long)n, (long)p * m, dys, dacc + (size_t)STATS_ACC * p));
+    KB_TRY(marginal_finish_dev(ctx, dacc, nc, (long)n, dsum, dT));
+    if (T_out) KB_CUDA(ctx, cudaMemcpyAsync(T_out, dT, sizeof(double) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+    return knockoff_filter_from_T(ctx, dT, (long)p, m, groups, fdrs, nfdr, knockoff_plus, 10000, W_out, kappa_out, tau_out,
+                                  taus_out, selected_out, n_w_out);
+}
+
+int kb_fit_marginal(kb_ctx* ctx, const double* y, const double* X, int64_t n, int64_t p, const double* mu,
+                    const double* Sigma, int32_t method, int32_t m, const kb_solve_opts* opts, const double* fdrs,
+                    int32_t nfdr, int32_t knockoff_plus, const double* Z, uint64_t seed, double* Xko_out, double* s_out,
+                    double* T_out, double* W_out, int64_t* kappa_out, double* tau_out, double* taus_out,
+                    int32_t* selected_out, kb_solve_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!y || !X || !mu || !Sigma || p < 1 || n < 2) return set_error(ctx, KB_ERR_INVALID, "fit_marginal: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const size_t pp = (size_t)p * p;
+    const size_t nblk = (size_t)(2 * m - 1);
+    const long nc = (long)(m + 1) * p;
+    double *dSig, *ds, *dmu, *dSiS, *dLb, *dy, *dys, *dsum, *dacc, *dT;
+    KB_TRY(sc.alloc(&dSig, pp));
+    KB_TRY(sc.alloc(&ds, p));
+    KB_TRY(sc.alloc(&dmu, p));
+    KB_TRY(sc.alloc(&dy, (size_t)n));
+    KB_TRY(sc.alloc(&dys, (size_t)n));
+    KB_TRY(sc.alloc(&dsum, 4));
+    KB_TRY(sc.alloc(&dacc, (size_t)STATS_ACC * nc));
+    KB_TRY(sc.alloc(&dT, (size_t)nc));
+    KB_CUDA(ctx, cudaMemcpyAsync(dSig, Sigma, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dmu, mu, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dy, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    // ko = modelX_gaussian_knockoffs(X, method, μ, Σ; m)                  (fit_lasso.jl:199)
+    KB_TRY(solve_s_dev(ctx, dSig, (long)p, (int)p, method, (double)m, opts, nullptr, ds, info));
+    if (s_out) KB_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_TRY(sc.alloc(&dSiS, pp));
+    KB_TRY(sc.alloc(&dLb, pp * nblk));
+    KB_TRY(cond_factor_dev(ctx, dSig, (long)p, (int)p, ds, (long)p, 1, m, dSiS, dLb, (long)p));
+    // feature importance while the chunks of X and X̃ are on the device   (fit_lasso.jl:214-222)
+    KB_TRY(zscore_vec_dev(ctx, dy, (long)n, dys, dsum));
+    StatsHook hook{dys, dacc, dacc + (size_t)STATS_ACC * p};
+    KB_TRY(sample_host_pipeline(ctx, X, (long)n, (int)p, dmu, dSiS, dLb, (long)p, m, Z, seed, 0, Xko_out, &hook));
+    KB_TRY(marginal_finish_dev(ctx, dacc, nc, (long)n, dsum, dT));
+    if (T_out) KB_CUDA(ctx, cudaMemcpyAsync(T_out, dT, sizeof(double) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+    return knockoff_filter_from_T(ctx, dT, (long)p, m, nullptr, fdrs, nfdr, knockoff_plus, 10000, W_out, kappa_out, tau_out,
+                                  taus_out, selected_out, nullptr);
 }
 
 // ---- test hooks -------------------------------------------------------------------------------------
