@@ -267,6 +267,36 @@ int kb_fit_marginal(kb_ctx* ctx, const double* y, const double* X, int64_t n, in
                     double* s_out, double* T_out, double* W_out, int64_t* kappa_out, double* tau_out,
                     double* taus_out, int32_t* selected_out, kb_solve_info* info);
 
+/* ---- (6) approximate (block-diagonal covariance) knockoffs ---------------------------
+ * `approx_modelX_gaussian_knockoffs(X, method, window_ranges; m, kwargs...)` (src/approx.jl:62-102).
+ * window_offsets: nwin + 1 ascending 0-based column offsets, window w = columns [off[w], off[w+1]) (the
+ * reference's `window_ranges`, which must tile 1:p in order for its BlockDiagonal / vcat assembly to make sense;
+ * off[0] = 0 and off[nwin] = p are checked like approx.jl:73-75).  Per window: Σ̂_w = Ledoit-Wolf shrinkage
+ * covariance of X[:, w] (approx.jl:84), s_w = solve_s(Σ̂_w, method; m) (:86); then γ = the `fzero` bisection of
+ * :97 / :105-109 (the positive-definiteness probe is a Cholesky factorisation; γ = min over windows because Σ is
+ * block diagonal), s .*= γ, and X̃ = condition(X, μ̂, BlockDiagonal(Σ̂_w), Diagonal(s); m) window by window.
+ * Outputs: Xko_out n x m·p; s_out p; mu_out p (may be NULL); Sigma_blocks_out = the Σ̂_w packed one after the
+ * other, window w column-major pw x pw (may be NULL); gamma_out (may be NULL). */
+int kb_approx_modelx_gaussian_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p,
+                                        const int64_t* window_offsets, int32_t nwin, int32_t method, int32_t m,
+                                        const kb_solve_opts* opts, const double* Z, uint64_t seed, double* Xko_out,
+                                        double* s_out, double* mu_out, double* Sigma_blocks_out, double* gamma_out,
+                                        kb_solve_info* info);
+/* The two phases of the call above for windows [w0, w1) only -- windows are independent, so ranks of a multi-GPU
+ * job take disjoint window ranges, all-reduce(min) the γ they return and scale s before phase 2 (no other
+ * exchange; X̃ columns of different windows are disjoint).  Arrays are full length (p, Σ pw²); only the entries
+ * of the handled windows are read / written. */
+int kb_approx_solve_windows(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* window_offsets,
+                            int32_t nwin, int32_t w0, int32_t w1, int32_t method, int32_t m,
+                            const kb_solve_opts* opts, double* Sigma_blocks_out, double* s_out, double* mu_out,
+                            double* gamma_min_out, kb_solve_info* info);
+int kb_approx_condition_windows(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* window_offsets,
+                                int32_t nwin, int32_t w0, int32_t w1, int32_t m, const double* Sigma_blocks,
+                                const double* s, const double* mu, const double* Z, uint64_t seed,
+                                int64_t row_offset, double* Xko_out);
+/* sup{γ in [0, 1] : (m+1)/m·Symmetric(Sigma) − γ·Diagonal(s) ≻ 0} -- approx.jl:97, 105-109 on one dense matrix. */
+int kb_feasible_gamma(kb_ctx* ctx, const double* Sigma, int64_t p, const double* s, double m, double* gamma_out);
+
 /* ---- test hooks (exercised by tests/, not part of the reference interface) -------------------- */
 /* C (M x N, col-major) = alpha * op(A) * op(B) + beta * C on the hand-written DMMA kernel.
  * transa / transb: 0 = 'N', 1 = 'T' (BLAS dgemm semantics, host pointers). */

@@ -8,7 +8,8 @@ from .api import (Context, GaussianGroupKnockoff, GaussianKnockoff, make_group_o
                   solve_s_group, solve_s_group_sharded, cond_factor, condition, cov_shrink_lw, default_context, dense_factor_from_blocks,  # noqa: F401
                   eigmin, gram, hook_dgemm, hook_potrf, hook_randn, hook_spd_inverse, make_opts,
                   modelX_gaussian_knockoffs, sample, solve_equi, solve_s, threshold, mk_threshold, MK_statistics,
-                  marginal_stats, fit_marginal, MarginalKnockoffFilter)
+                  marginal_stats, fit_marginal, MarginalKnockoffFilter, approx_modelX_gaussian_knockoffs,
+                  ApproxGaussianKnockoff, feasible_gamma)
 from . import harness, dev, dist  # noqa: F401
 
 __all__ = ["Context", "GaussianKnockoff", "KnockoffsError", "PosDefException", "cond_factor", "condition", "eigmin",

@@ -87,6 +87,13 @@ SIGNATURES = {
                                      _vp, _vp, C.POINTER(_i64)]),
     "kb_fit_marginal": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, C.POINTER(SolveOpts), _vp, _i32,
                                   _i32, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(SolveInfo)]),
+    "kb_approx_modelx_gaussian_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, C.POINTER(SolveOpts),
+                                                      _vp, _u64, _vp, _vp, _vp, _vp, c_double_p, C.POINTER(SolveInfo)]),
+    "kb_approx_solve_windows": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(SolveOpts),
+                                          _vp, _vp, _vp, c_double_p, C.POINTER(SolveInfo)]),
+    "kb_approx_condition_windows": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _u64,
+                                              _i64, _vp]),
+    "kb_feasible_gamma": (C.c_int, [_vp, _vp, _i64, _vp, _d, c_double_p]),
     "kb_test_dgemm": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_potrf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_spd_inverse": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -603,6 +603,103 @@ def fit_marginal(y, X_or_ko, mu=None, Sigma=None, method="maxent", m=1, fdrs=DEF
     return MarginalKnockoffFilter(y, X, ko, r["W"], r["taus"], m, r["selected"], fd, r["kappa"], r["tau"], r["T0"], r["Tk"])
 
 
+
+# ---- approximate (block-diagonal covariance) knockoffs --------------------------------
+@dataclass
+class ApproxGaussianKnockoff:
+    """src/struct.jl:15-22.  ``Sigma`` is the dense block-diagonal matrix like the reference's (None with
+    ``dense_sigma=False``); ``blocks`` holds the windows' Σ̂_w."""
+    X: np.ndarray
+    Xko: np.ndarray
+    s: np.ndarray
+    Sigma: Optional[np.ndarray]
+    method: str
+    m: int
+    mu: Optional[np.ndarray] = None
+    gamma: float = 1.0
+    blocks: list = field(default_factory=list)
+    window_ranges: list = field(default_factory=list)
+    info: dict = field(default_factory=dict)
+
+
+def _window_offsets(p, window_ranges=None, windowsize=500):
+    """approx.jl:46-58 (``windowsize``) or explicit ranges: Julia ``a:b`` ranges / python (a, b) pairs, 1-based
+    inclusive like the reference.  Returns the 0-based offsets array and the (a, b) list."""
+    if window_ranges is None:
+        if not windowsize > 1:                                     # approx.jl:45
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"windowsize should be > 1 but was {windowsize}")
+        windows = -(-p // int(windowsize))
+        window_ranges = [(w * windowsize + 1, p if w == windows - 1 else (w + 1) * windowsize) for w in range(windows)]
+    rng = []
+    for r in window_ranges:
+        a, b = (r.start, r.stop - 1) if isinstance(r, range) else (int(r[0]), int(r[1]))
+        rng.append((a, b))
+    total = sum(b - a + 1 for a, b in rng)
+    if total != p:                                                 # approx.jl:73-75
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"window_ranges have {total} dimensions but X has {p}")
+    off = [0]
+    for a, b in rng:
+        if a != off[-1] + 1 or b < a:
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "window_ranges must tile 1:p in order (the reference "
+                                                           "assembles BlockDiagonal(blocks) / vcat(s) in the given order)")
+        off.append(b)
+    return np.ascontiguousarray(off, dtype=np.int64), rng
+
+
+def _blocks_from_packed(packed, off):
+    out, o = [], 0
+    for w in range(len(off) - 1):
+        pw = int(off[w + 1] - off[w])
+        out.append(packed[o:o + pw * pw].reshape((pw, pw), order="F"))
+        o += pw * pw
+    return out
+
+
+def approx_modelX_gaussian_knockoffs(X, method, window_ranges=None, m=1, windowsize=500, Z=None, seed=0,
+                                     dense_sigma=True, ctx: Optional[Context] = None, **kwargs) -> ApproxGaussianKnockoff:
+    """``approx_modelX_gaussian_knockoffs(X, method[, window_ranges]; m, windowsize, kwargs...)`` -- src/approx.jl:37-102
+    with the default covariance_approximator (Ledoit-Wolf linear shrinkage)."""
+    ctx = ctx or default_context()
+    X = _f(X)
+    n, p = X.shape
+    m = int(m)
+    if m < 1:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
+    off, rng = _window_offsets(p, window_ranges, windowsize)
+    mid = _method_id(method)
+    opts = make_opts(**kwargs)
+    info = SolveInfo()
+    Zf = None if Z is None else _f(Z)
+    if Zf is not None and Zf.shape != (n, m * p):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
+    Xko = np.empty((n, m * p), order="F")
+    s, mu = np.empty(p), np.empty(p)
+    packed = np.empty(int(np.sum(np.diff(off) ** 2)))
+    gamma = C.c_double()
+    rc = ctx._lib.kb_approx_modelx_gaussian_knockoffs(ctx.h, _ptr(X), n, p, _ptr(off), len(off) - 1, mid, m, C.byref(opts),
+                                                      _ptr(Zf), int(seed), _ptr(Xko), _ptr(s), _ptr(mu), _ptr(packed),
+                                                      C.byref(gamma), C.byref(info))
+    check(ctx.h, rc)
+    blocks = _blocks_from_packed(packed, off)
+    Sigma = None
+    if dense_sigma:
+        Sigma = np.zeros((p, p), order="F")
+        for w, B in enumerate(blocks):
+            Sigma[off[w]:off[w + 1], off[w]:off[w + 1]] = B
+    return ApproxGaussianKnockoff(X, Xko, s, Sigma, str(method).lstrip(":"), m, mu, gamma.value, blocks, rng,
+                                  _info_dict(info, str(method).lstrip(":")))
+
+
+def feasible_gamma(Sigma, s, m=1, ctx: Optional[Context] = None) -> float:
+    """``fzero(γ -> f(γ, s, Σ, m), 0, 1)`` of src/approx.jl:97, 105-109 on one dense matrix."""
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    out = C.c_double()
+    check(ctx.h, ctx._lib.kb_feasible_gamma(ctx.h, _ptr(Sigma), Sigma.shape[0], _ptr(s), float(m), C.byref(out)))
+    return out.value
+
+
 # ---- hooks used by tests ---------------------------------------------------------------------------
 def hook_dgemm(A, B, C_in=None, transa=False, transb=False, alpha=1.0, beta=0.0, ctx: Optional[Context] = None):
     ctx = ctx or default_context()

@@ -5,6 +5,7 @@
 #include "pipeline.cuh"
 #include "group.cuh"
 #include "stats.cuh"
+#include "approx.cuh"
 #include <algorithm>
 #include <unordered_map>
 #include <cstring>
@@ -179,6 +180,28 @@ int knockoff_filter_from_T(kb_ctx* ctx, const double* dT, long p, int m, const i
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_w_out) *n_w_out = nw;
     return KB_OK;
+}
+
+int check_windows(kb_ctx* ctx, const int64_t* off, int nwin, int64_t p) {
+    if (!off || nwin < 1 || off[0] != 0 || off[nwin] != p)           // approx.jl:73-75
+        return set_error(ctx, KB_ERR_INVALID, "window_ranges have %lld dimensions but X has %lld",
+                         (long long)(off && nwin >= 1 ? off[nwin] - off[0] : 0), (long long)p);
+    for (int w = 0; w < nwin; ++w)
+        if (off[w + 1] <= off[w]) return set_error(ctx, KB_ERR_INVALID, "window %d is empty or out of order", w + 1);
+    return KB_OK;
+}
+size_t window_block_doubles(const int64_t* off, int nwin) {
+    size_t t = 0;
+    for (int w = 0; w < nwin; ++w) t += (size_t)(off[w + 1] - off[w]) * (size_t)(off[w + 1] - off[w]);
+    return t;
+}
+size_t window_block_offset(const int64_t* off, int w) { return window_block_doubles(off, w); }
+
+// columns [c0, c1) of the host matrix X (n x p, ld n) -> device slab with an even leading dimension
+int h2d_columns(kb_ctx* ctx, Scope& sc, const double* X, long n, long c0, long c1, double** dX, long* ldx) {
+    *ldx = (n + 1) & ~1L;
+    KB_TRY(sc.alloc(dX, (size_t)(*ldx) * (size_t)(c1 - c0)));
+    return h2d_matrix(ctx, X + (size_t)c0 * n, n, *dX, *ldx, n, c1 - c0, ctx->stream);
 }
 
 }  // namespace
@@ -739,6 +762,110 @@ int kb_fit_marginal(kb_ctx* ctx, const double* y, const double* X, int64_t n, in
     if (T_out) KB_CUDA(ctx, cudaMemcpyAsync(T_out, dT, sizeof(double) * nc, cudaMemcpyDeviceToHost, ctx->stream));
     return knockoff_filter_from_T(ctx, dT, (long)p, m, nullptr, fdrs, nfdr, knockoff_plus, 10000, W_out, kappa_out, tau_out,
                                   taus_out, selected_out, nullptr);
+}
+
+
+// ---- (6) approx_modelX_gaussian_knockoffs ---------------------------------------------
+int kb_feasible_gamma(kb_ctx* ctx, const double* Sigma, int64_t p, const double* s, double m, double* gamma_out) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !s || !gamma_out || p < 1 || !(m >= 1.0)) return set_error(ctx, KB_ERR_INVALID, "feasible_gamma: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    double *dS, *ds;
+    KB_TRY(sc.alloc(&dS, (size_t)p * p));
+    KB_TRY(sc.alloc(&ds, (size_t)p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dS, Sigma, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ds, s, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    return feasible_gamma_dev(ctx, dS, (long)p, (int)p, ds, m, gamma_out);
+}
+
+int kb_approx_solve_windows(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* window_offsets,
+                            int32_t nwin, int32_t w0, int32_t w1, int32_t method, int32_t m, const kb_solve_opts* opts,
+                            double* Sigma_blocks_out, double* s_out, double* mu_out, double* gamma_min_out,
+                            kb_solve_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!X || !Sigma_blocks_out || !s_out || !mu_out || !gamma_min_out || p < 1 || n < 2)
+        return set_error(ctx, KB_ERR_INVALID, "approx_solve_windows: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    KB_TRY(check_windows(ctx, window_offsets, nwin, p));
+    if (w0 < 0 || w1 > nwin || w0 > w1) return set_error(ctx, KB_ERR_INVALID, "approx_solve_windows: bad window range");
+    *gamma_min_out = 1.0;
+    if (w0 == w1) return KB_OK;
+    Scope sc(ctx);
+    const long c0 = (long)window_offsets[w0], c1 = (long)window_offsets[w1];
+    double *dX, *dblk, *ds, *dmu;
+    long ldx;
+    KB_TRY(h2d_columns(ctx, sc, X, (long)n, c0, c1, &dX, &ldx));
+    KB_TRY(sc.alloc(&dblk, window_block_doubles(window_offsets, nwin)));
+    KB_TRY(sc.alloc(&ds, (size_t)p));
+    KB_TRY(sc.alloc(&dmu, (size_t)p));
+    KB_TRY(approx_solve_windows(ctx, dX, (long)n, ldx, (long)p, window_offsets, nwin, w0, w1, method, (double)m, opts, dblk, ds,
+                                dmu, gamma_min_out, info));
+    const size_t b0 = window_block_offset(window_offsets, w0), b1 = window_block_offset(window_offsets, w1);
+    KB_CUDA(ctx, cudaMemcpyAsync(Sigma_blocks_out + b0, dblk + b0, sizeof(double) * (b1 - b0), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(s_out + c0, ds + c0, sizeof(double) * (c1 - c0), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(mu_out + c0, dmu + c0, sizeof(double) * (c1 - c0), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_approx_condition_windows(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* window_offsets,
+                                int32_t nwin, int32_t w0, int32_t w1, int32_t m, const double* Sigma_blocks,
+                                const double* s, const double* mu, const double* Z, uint64_t seed, int64_t row_offset,
+                                double* Xko_out) {
+    if (!ctx) return bad_ctx();
+    if (!X || !Sigma_blocks || !s || !mu || !Xko_out || p < 1 || n < 1)
+        return set_error(ctx, KB_ERR_INVALID, "approx_condition_windows: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    KB_TRY(check_windows(ctx, window_offsets, nwin, p));
+    if (w0 < 0 || w1 > nwin || w0 > w1) return set_error(ctx, KB_ERR_INVALID, "approx_condition_windows: bad window range");
+    if (w0 == w1) return KB_OK;
+    Scope sc(ctx);
+    const long c0 = (long)window_offsets[w0], c1 = (long)window_offsets[w1];
+    const size_t b0 = window_block_offset(window_offsets, w0), b1 = window_block_offset(window_offsets, w1);
+    double *dX, *dblk, *ds, *dmu;
+    long ldx;
+    KB_TRY(h2d_columns(ctx, sc, X, (long)n, c0, c1, &dX, &ldx));
+    KB_TRY(sc.alloc(&dblk, window_block_doubles(window_offsets, nwin)));
+    KB_TRY(sc.alloc(&ds, (size_t)p));
+    KB_TRY(sc.alloc(&dmu, (size_t)p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dblk + b0, Sigma_blocks + b0, sizeof(double) * (b1 - b0), cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(ds + c0, s + c0, sizeof(double) * (c1 - c0), cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dmu + c0, mu + c0, sizeof(double) * (c1 - c0), cudaMemcpyHostToDevice, ctx->stream));
+    return approx_condition_windows(ctx, dX, (long)n, ldx, (long)p, window_offsets, nwin, w0, w1, m, dblk, ds, dmu, Z, seed,
+                                    row_offset, Xko_out);
+}
+
+int kb_approx_modelx_gaussian_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* window_offsets,
+                                        int32_t nwin, int32_t method, int32_t m, const kb_solve_opts* opts, const double* Z,
+                                        uint64_t seed, double* Xko_out, double* s_out, double* mu_out,
+                                        double* Sigma_blocks_out, double* gamma_out, kb_solve_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!X || !Xko_out || !s_out || p < 1 || n < 2) return set_error(ctx, KB_ERR_INVALID, "approx modelX: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    KB_TRY(check_windows(ctx, window_offsets, nwin, p));
+    Scope sc(ctx);
+    const size_t nblk = window_block_doubles(window_offsets, nwin);
+    double *dX, *dblk, *ds, *dmu;
+    long ldx;
+    KB_TRY(h2d_columns(ctx, sc, X, (long)n, 0, (long)p, &dX, &ldx));
+    KB_TRY(sc.alloc(&dblk, nblk));
+    KB_TRY(sc.alloc(&ds, (size_t)p));
+    KB_TRY(sc.alloc(&dmu, (size_t)p));
+    double gamma = 1.0;
+    KB_TRY(approx_solve_windows(ctx, dX, (long)n, ldx, (long)p, window_offsets, nwin, 0, nwin, method, (double)m, opts, dblk, ds,
+                                dmu, &gamma, info));
+    KB_TRY(scale_vec_dev(ctx, ds, (long)p, gamma));                                          // s .*= γ  (approx.jl:98)
+    KB_CUDA(ctx, cudaMemcpyAsync(s_out, ds, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mu_out) KB_CUDA(ctx, cudaMemcpyAsync(mu_out, dmu, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    if (Sigma_blocks_out)
+        KB_CUDA(ctx, cudaMemcpyAsync(Sigma_blocks_out, dblk, sizeof(double) * nblk, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gamma_out) *gamma_out = gamma;
+    return approx_condition_windows(ctx, dX, (long)n, ldx, (long)p, window_offsets, nwin, 0, nwin, m, dblk, ds, dmu, Z, seed, 0,
+                                    Xko_out);
 }
 
 // ---- test hooks -------------------------------------------------------------------------------------

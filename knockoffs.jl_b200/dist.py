@@ -100,6 +100,78 @@ def solve_s_group_blockdiag(ctx, Sigma_blocks, groups_blocks, method, m=1, group
     return S, float(tot[0]), info
 
 
+def assign_windows(offsets: Sequence[int], world: int) -> List[tuple]:
+    """Contiguous window ranges [w0, w1) per rank for approx.jl's independent windows, balanced on the windows'
+    cubic solve cost (Σ pw³): rank r gets the windows whose cumulative-cost midpoint falls in its 1/world share."""
+    pw = np.diff(np.asarray(offsets, dtype=np.int64)).astype(np.float64)
+    cost = pw ** 3
+    cum = np.cumsum(cost)
+    mid = (cum - 0.5 * cost) / max(cum[-1], 1e-300)
+    owner = np.minimum((mid * world).astype(int), world - 1)
+    out = []
+    for r in range(world):
+        idx = np.flatnonzero(owner == r)
+        out.append((int(idx[0]), int(idx[-1]) + 1) if idx.size else (0, 0))
+    return out
+
+
+def merge_window_results(s, mu, gamma_local, cols, group=None, device=None):
+    """The approx path's only exchange: min of the ranks' γ (approx.jl:97 on a block-diagonal Σ) and the union of
+    their s / μ̂ segments (each rank owns the columns cols = [c0, c1)).  In place on the numpy arrays; returns γ."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return float(gamma_local)
+    c0, c1 = cols
+    buf = np.zeros((2, s.shape[0]))
+    buf[0, c0:c1], buf[1, c0:c1] = s[c0:c1], mu[c0:c1]
+    t = torch.from_numpy(buf)
+    g = torch.tensor([float(gamma_local)], dtype=torch.float64)
+    if device is not None:
+        t, g = t.to(device), g.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)         # disjoint supports: sum = union
+    dist.all_reduce(g, op=dist.ReduceOp.MIN, group=group)
+    t = t.cpu().numpy()
+    s[:], mu[:] = t[0], t[1]
+    return float(g.item())
+
+
+def approx_knockoffs_sharded(ctx, X, method, window_ranges=None, m=1, windowsize=500, Z=None, seed=0, group=None,
+                             device=None, **kwargs):
+    """approx_modelX_gaussian_knockoffs (src/approx.jl:62-102) with the windows dealt across ranks: every rank
+    estimates Σ̂_w and solves s_w for its contiguous window range, ONE exchange (min γ, union of s and μ̂), then
+    every rank samples the X̃ columns of its own windows.  Returns dict(cols=(c0, c1), Xko (n x m p, only this
+    rank's columns of every copy are filled), s, mu, gamma, blocks_packed, offsets)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from . import api
+    from ._lib import SolveInfo, check
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    X = api._f(X)
+    n, p = X.shape
+    off, _ = api._window_offsets(p, window_ranges, windowsize)
+    nwin = len(off) - 1
+    w0, w1 = assign_windows(off, world)[rank]
+    c0, c1 = int(off[w0]), int(off[w1])
+    opts = api.make_opts(**kwargs)
+    info = SolveInfo()
+    packed = np.zeros(int(np.sum(np.diff(off) ** 2)))
+    s, mu = np.zeros(p), np.zeros(p)
+    gam = C.c_double(1.0)
+    check(ctx.h, ctx._lib.kb_approx_solve_windows(ctx.h, api._ptr(X), n, p, api._ptr(off), nwin, w0, w1,
+                                                  api._method_id(method), int(m), C.byref(opts), api._ptr(packed),
+                                                  api._ptr(s), api._ptr(mu), C.byref(gam), C.byref(info)))
+    gamma = merge_window_results(s, mu, gam.value, (c0, c1), group, device)
+    s *= gamma                                                     # approx.jl:98
+    Xko = np.empty((n, int(m) * p), order="F")
+    Zf = None if Z is None else api._f(Z)
+    check(ctx.h, ctx._lib.kb_approx_condition_windows(ctx.h, api._ptr(X), n, p, api._ptr(off), nwin, w0, w1, int(m),
+                                                      api._ptr(packed), api._ptr(s), api._ptr(mu), api._ptr(Zf), int(seed),
+                                                      0, api._ptr(Xko)))
+    return dict(cols=(c0, c1), Xko=Xko, s=s, mu=mu, gamma=gamma, blocks_packed=packed, offsets=off)
+
+
 def gram_reference_numpy(X_shards: Sequence[np.ndarray], center=True):
     """Host restatement of the sharded Gram algebra (used by the gloo tests to check the partition logic)."""
     n = sum(x.shape[0] for x in X_shards)

@@ -48,7 +48,17 @@ def _worker(rank, world, port, out):
         # row shards tile [0, n) exactly and the global-row keying makes shards independent of world size
         shards = [kb.dist.shard_rows(n, world, r) for r in range(world)]
         ok_shard = shards[0][0] == 0 and shards[-1][1] == n and all(shards[i][1] == shards[i + 1][0] for i in range(world - 1))
-        flag = torch.tensor([int(ok_gram and ok_many and ok_shard)])
+        # approx.jl windows dealt across ranks: the only exchange is min(γ) + the union of the s / μ̂ segments
+        off = np.array([0, 40, 90, 100, 170, 200])
+        parts = kb.dist.assign_windows(off, world)
+        w0, w1 = parts[rank]
+        c0, c1 = int(off[w0]), int(off[w1])
+        s_full, mu_full = np.arange(200) + 1.0, -np.arange(200) - 0.5
+        s, mu = np.zeros(200), np.zeros(200)
+        s[c0:c1], mu[c0:c1] = s_full[c0:c1], mu_full[c0:c1]
+        gam = kb.dist.merge_window_results(s, mu, [0.75, 0.5][rank], (c0, c1))
+        ok_win = gam == 0.5 and np.array_equal(s, s_full) and np.array_equal(mu, mu_full) and parts[0][1] == parts[1][0]
+        flag = torch.tensor([int(ok_gram and ok_many and ok_shard and ok_win)])
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             out.put(int(flag.item()))
