@@ -83,4 +83,83 @@ function modelX_gaussian_knockoffs(X::Matrix{Float64}, method::Union{Symbol,Stri
     return GaussianKnockoff(X, Xko, s, Symmetric(Σd), Symbol(method), mi)   # src/struct.jl:6-13, fields unchanged
 end
 
+# ---- group knockoffs (src/group.jl:109-127, 348-422) ---------------------------------------------------
+const GROUP_METHODS = Dict(:mvr => 0, :maxent => 1, :sdp => 2, :equi => 3)
+struct GroupOpts          # kb_group_opts
+    outer_iter::Int32; inner_pca_iter::Int32; inner_ccd_iter::Int32; tol::Float64; eps::Float64
+    robust::Int32; verbose::Int32
+end
+struct GroupInfo          # kb_group_info
+    outer_iters::Int32; inner_sweeps::Int32; n_directions::Int32; status::Int32
+    obj_init::Float64; obj::Float64; gamma_equi::Float64
+    trace_obj::NTuple{KB_MAX_TRACE,Float64}; trace_delta::NTuple{KB_MAX_TRACE,Float64}
+    trace_kind::NTuple{KB_MAX_TRACE,Int32}
+    steps::Float64; accepted::Float64; solve_ms::Float64; touched_bytes::Float64
+end
+gopts(; outer_iter::Int=100, inner_pca_iter::Int=1, inner_ccd_iter::Int=1, tol=1e-4, ϵ=1e-6, robust::Bool=false,
+      verbose::Bool=false) = GroupOpts(outer_iter, inner_pca_iter, inner_ccd_iter, tol, ϵ, robust, verbose)
+
+"Drop-in for `solve_s_group(Σ::Symmetric, groups, method; m, kwargs...)` (src/group.jl:348-422): returns (S, γs, obj)."
+function solve_s_group(Σ::Symmetric{Float64}, groups::Vector{Int}, method::Union{Symbol,String}; m::Number=1, kwargs...)
+    c = ctx(); p = size(Σ, 1)
+    length(groups) == p || error("Length of groups should be equal to dimension of Σ")
+    S = Matrix{Float64}(undef, p, p); obj = Ref{Float64}(0.0)
+    o = Ref(gopts(; kwargs...)); info = Ref{GroupInfo}(); A = Σ.data
+    GC.@preserve A groups S begin
+        rc = ccall((:kb_solve_s_group, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int64}, Int32, Float64, Ptr{GroupOpts}, Ptr{Float64}, Int64,
+                    Ptr{Float64}, Ptr{Float64}, Ptr{GroupInfo}),
+                   c.h, A, p, groups, GROUP_METHODS[Symbol(method)], Float64(m), o, C_NULL, 0, S, obj, info)
+        check(c, rc)
+    end
+    return S, Float64[], obj[]
+end
+
+# ---- approximate knockoffs (src/approx.jl:62-102) ------------------------------------------------------
+"Drop-in for `approx_modelX_gaussian_knockoffs(X, method, window_ranges; m, kwargs...)`; returns (Xko, s, Σ, γ)."
+function approx_modelX_gaussian_knockoffs(X::Matrix{Float64}, method::Union{Symbol,String},
+                                          window_ranges::Vector{UnitRange{Int64}}; m::Int=1,
+                                          seed::Integer=rand(UInt64), kwargs...)
+    c = ctx(); n, p = size(X)
+    sum(length.(window_ranges)) == p || error("window_ranges have $(sum(length.(window_ranges))) dimensions but X has $p")
+    off = Int64[0; cumsum(length.(window_ranges))]
+    Xko = Matrix{Float64}(undef, n, m * p); s = Vector{Float64}(undef, p); μ = Vector{Float64}(undef, p)
+    blocks = Vector{Float64}(undef, sum(abs2, length.(window_ranges))); γ = Ref{Float64}(1.0)
+    o = Ref(opts(; kwargs...)); info = Ref{SolveInfo}()
+    GC.@preserve X off Xko s μ blocks begin
+        rc = ccall((:kb_approx_modelx_gaussian_knockoffs, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Int32, Int32, Int32, Ptr{SolveOpts}, Ptr{Float64},
+                    UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{SolveInfo}),
+                   c.h, X, n, p, off, length(window_ranges), METHODS[Symbol(method)], m, o, C_NULL, seed, Xko, s, μ,
+                   blocks, γ, info)
+        check(c, rc)
+    end
+    Σ = zeros(p, p); b = 0                                   # BlockDiagonal(block_covariances) |> Matrix  (approx.jl:93)
+    for r in window_ranges
+        w = length(r); Σ[r, r] .= reshape(view(blocks, b+1:b+w*w), w, w); b += w * w
+    end
+    return Xko, s, Symmetric(Σ), γ[]                          # wrap in ApproxGaussianKnockoff (src/struct.jl:15-22)
+end
+
+# ---- feature statistics + filter (src/fit_lasso.jl:188-257) ----------------------------------------------
+"Drop-in for `fit_marginal(y, X, μ, Σ; method, m, fdrs)`: returns (W, τs, selected); X̃ stays on the device."
+function fit_marginal(y::Vector{Float64}, X::Matrix{Float64}, μ::Vector{Float64}, Σ::Matrix{Float64};
+                      method::Union{Symbol,String}=:maxent, m::Int=1, fdrs::Vector{Float64}=[0.01, 0.05, 0.1, 0.25, 0.5],
+                      seed::Integer=rand(UInt64), kwargs...)
+    c = ctx(); n, p = size(X); nf = length(fdrs)
+    s = Vector{Float64}(undef, p); T = Vector{Float64}(undef, (m + 1) * p); W = Vector{Float64}(undef, p)
+    κ = zeros(Int64, p); τ = zeros(p); τs = Vector{Float64}(undef, nf); mask = zeros(Int32, p, nf)
+    o = Ref(opts(; kwargs...)); info = Ref{SolveInfo}()
+    GC.@preserve y X μ Σ fdrs s T W κ τ τs mask begin
+        rc = ccall((:kb_fit_marginal, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Int32,
+                    Ptr{SolveOpts}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64},
+                    Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{SolveInfo}),
+                   c.h, y, X, n, p, μ, Σ, METHODS[Symbol(method)], m, o, fdrs, nf, 1, C_NULL, seed, C_NULL, s, T, W, κ, τ,
+                   τs, mask, info)
+        check(c, rc)
+    end
+    return W, τs, [findall(!iszero, view(mask, :, f)) for f in 1:nf]
+end
+
 end # module
