@@ -297,6 +297,38 @@ int kb_approx_condition_windows(kb_ctx* ctx, const double* X, int64_t n, int64_t
 /* sup{γ in [0, 1] : (m+1)/m·Symmetric(Sigma) − γ·Diagonal(s) ≻ 0} -- approx.jl:97, 105-109 on one dense matrix. */
 int kb_feasible_gamma(kb_ctx* ctx, const double* Sigma, int64_t p, const double* s, double m, double* gamma_out);
 
+/* ---- (7) representative group knockoffs ---------------------------------------------
+ * Index arrays at this boundary (group_reps, prioritize_idx) are 1-BASED like the reference's `Vector{Int}`.
+ *
+ * `choose_group_reps(Σ::Symmetric, groups; threshold, prioritize_idx)` (group.jl:1929-2033): Σ must be a correlation
+ * matrix; prioritize_idx == NULL is `nothing`.  group_reps_out: capacity p, sorted; inv(Σ) runs on the device,
+ * the per-group decisions are g x g host work (see rep.cu for the Schur-complement form of the ratio test). */
+int kb_choose_group_reps(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups, double threshold,
+                         const int64_t* prioritize_idx, int64_t n_prioritize, int64_t* group_reps_out,
+                         int64_t* n_reps_out);
+/* `cond_indep_corr(Σ, groups, group_reps)` (group.jl:205-240): the covariance that satisfies the conditional
+ * independence assumption exactly (p x p, symmetric). */
+int kb_cond_indep_corr(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups, const int64_t* group_reps,
+                       int64_t n_reps, double* Sigma_new_out);
+/* `solve_s_graphical_group(Σ::Symmetric, groups, group_reps, method; m, kwargs...)` (group.jl:268-303): the group
+ * problem on the representatives (S_out, r x r), extended to all variables (D_out, p x p, |x| < 1e-10 zeroed,
+ * symmetric).  V (r x nv, in the order of group_reps) as in kb_solve_s_group. */
+int kb_solve_s_graphical_group(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups,
+                               const int64_t* group_reps, int64_t n_reps, int32_t method, double m,
+                               const kb_group_opts* opts, const double* V, int64_t nv, double* S_out, double* D_out,
+                               double* obj_out, kb_group_info* info);
+/* `modelX_gaussian_rep_group_knockoffs(X, method, groups, μ, Σ; m, rep_threshold, enforce_cond_indep, kwargs...)`
+ * (group.jl:170-203).  group_reps_in == NULL: chosen by choose_group_reps(Σ, groups, threshold = rep_threshold).
+ * Outputs: Xko_out n x m·p; group_reps_out (capacity p) / n_reps_out; S11_out r x r (capacity p·p is always enough);
+ * D_out p x p (may be NULL); obj_out. */
+int kb_modelx_gaussian_rep_group_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* groups,
+                                           const double* mu, const double* Sigma, int32_t method, int32_t m,
+                                           double rep_threshold, int32_t enforce_cond_indep, const kb_group_opts* opts,
+                                           const int64_t* group_reps_in, int64_t n_reps_in, const double* V, int64_t nv,
+                                           const double* Z, uint64_t seed, double* Xko_out, int64_t* group_reps_out,
+                                           int64_t* n_reps_out, double* S11_out, double* D_out, double* obj_out,
+                                           kb_group_info* info);
+
 /* ---- test hooks (exercised by tests/, not part of the reference interface) -------------------- */
 /* C (M x N, col-major) = alpha * op(A) * op(B) + beta * C on the hand-written DMMA kernel.
  * transa / transb: 0 = 'N', 1 = 'T' (BLAS dgemm semantics, host pointers). */

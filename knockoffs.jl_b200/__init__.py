@@ -9,7 +9,8 @@ from .api import (Context, GaussianGroupKnockoff, GaussianKnockoff, make_group_o
                   eigmin, gram, hook_dgemm, hook_potrf, hook_randn, hook_spd_inverse, make_opts,
                   modelX_gaussian_knockoffs, sample, solve_equi, solve_s, threshold, mk_threshold, MK_statistics,
                   marginal_stats, fit_marginal, MarginalKnockoffFilter, approx_modelX_gaussian_knockoffs,
-                  ApproxGaussianKnockoff, feasible_gamma)
+                  ApproxGaussianKnockoff, feasible_gamma, choose_group_reps, cond_indep_corr,
+                  solve_s_graphical_group, modelX_gaussian_rep_group_knockoffs, GaussianRepGroupKnockoff)
 from . import harness, dev, dist  # noqa: F401
 
 __all__ = ["Context", "GaussianKnockoff", "KnockoffsError", "PosDefException", "cond_factor", "condition", "eigmin",

@@ -94,6 +94,13 @@ SIGNATURES = {
     "kb_approx_condition_windows": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _u64,
                                               _i64, _vp]),
     "kb_feasible_gamma": (C.c_int, [_vp, _vp, _i64, _vp, _d, c_double_p]),
+    "kb_choose_group_reps": (C.c_int, [_vp, _vp, _i64, _vp, _d, _vp, _i64, _vp, C.POINTER(_i64)]),
+    "kb_cond_indep_corr": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp]),
+    "kb_solve_s_graphical_group": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i32, _d, C.POINTER(GroupOpts), _vp, _i64, _vp,
+                                             _vp, c_double_p, C.POINTER(GroupInfo)]),
+    "kb_modelx_gaussian_rep_group_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _d, _i32,
+                                                         C.POINTER(GroupOpts), _vp, _i64, _vp, _i64, _vp, _u64, _vp, _vp,
+                                                         C.POINTER(_i64), _vp, _vp, c_double_p, C.POINTER(GroupInfo)]),
     "kb_test_dgemm": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_potrf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_spd_inverse": (C.c_int, [_vp, _vp, _i64, _vp]),

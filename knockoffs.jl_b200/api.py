@@ -700,6 +700,122 @@ def feasible_gamma(Sigma, s, m=1, ctx: Optional[Context] = None) -> float:
     return out.value
 
 
+
+# ---- representative group knockoffs ----------------------------------------------------
+def choose_group_reps(Sigma, groups, threshold=0.5, prioritize_idx=None, ctx: Optional[Context] = None) -> np.ndarray:
+    """``choose_group_reps(Σ::Symmetric, groups; threshold, prioritize_idx)`` -- src/group.jl:1929-2033.
+    Indices (result and ``prioritize_idx``) are 1-based like the reference's."""
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    p = Sigma.shape[0]
+    groups = np.ascontiguousarray(groups, dtype=np.int64)
+    pr = None if prioritize_idx is None else np.ascontiguousarray(prioritize_idx, dtype=np.int64)
+    out = np.zeros(p, dtype=np.int64)
+    nr = C.c_int64()
+    check(ctx.h, ctx._lib.kb_choose_group_reps(ctx.h, _ptr(Sigma), p, _ptr(groups), float(threshold), _ptr(pr),
+                                               0 if pr is None else pr.size, _ptr(out), C.byref(nr)))
+    return out[:nr.value].copy()
+
+
+def cond_indep_corr(Sigma, groups, group_reps, ctx: Optional[Context] = None) -> np.ndarray:
+    """``cond_indep_corr(Σ, groups, group_reps)`` -- src/group.jl:205-240 (1-based ``group_reps``)."""
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    p = Sigma.shape[0]
+    groups = np.ascontiguousarray(groups, dtype=np.int64)
+    reps = np.ascontiguousarray(group_reps, dtype=np.int64)
+    out = np.empty((p, p), order="F")
+    check(ctx.h, ctx._lib.kb_cond_indep_corr(ctx.h, _ptr(Sigma), p, _ptr(groups), _ptr(reps), reps.size, _ptr(out)))
+    return out
+
+
+def solve_s_graphical_group(Sigma, groups, group_reps, method, m=1, V=None, ctx: Optional[Context] = None,
+                            return_info=False, **kwargs):
+    """``solve_s_graphical_group(Σ::Symmetric, groups, group_reps, method; m, kwargs...)`` -- src/group.jl:268-303.
+    Returns (S, D, obj)."""
+    ctx = ctx or default_context()
+    Sigma = _f(Sigma)
+    p = Sigma.shape[0]
+    groups = np.ascontiguousarray(groups, dtype=np.int64)
+    reps = np.ascontiguousarray(group_reps, dtype=np.int64)
+    r = reps.size
+    opts = make_group_opts(**kwargs)
+    info = GroupInfo()
+    Vf = None if V is None else _f(V)
+    S = np.empty((r, r), order="F")
+    D = np.empty((p, p), order="F")
+    obj = C.c_double()
+    check(ctx.h, ctx._lib.kb_solve_s_graphical_group(ctx.h, _ptr(Sigma), p, _ptr(groups), _ptr(reps), r,
+                                                     _group_method_id(method), float(m), C.byref(opts), _ptr(Vf),
+                                                     0 if Vf is None else Vf.shape[1], _ptr(S), _ptr(D), C.byref(obj),
+                                                     C.byref(info)))
+    out = (S, D, obj.value)
+    return out + (_group_info_dict(info, str(method).lstrip(":")),) if return_info else out
+
+
+@dataclass
+class GaussianRepGroupKnockoff:
+    """src/struct.jl:36-48."""
+    X: np.ndarray
+    Xko: np.ndarray
+    groups: np.ndarray
+    group_reps: np.ndarray
+    S11: np.ndarray
+    S: np.ndarray
+    m: int
+    Sigma: np.ndarray
+    method: str
+    obj: float
+    enforce_cond_indep: bool
+    info: dict = field(default_factory=dict)
+
+
+def modelX_gaussian_rep_group_knockoffs(X, method, groups, mu=None, Sigma=None, m=1, rep_threshold=0.5,
+                                        enforce_cond_indep=False, group_reps=None, V=None, Z=None, seed=0,
+                                        ctx: Optional[Context] = None, **kwargs) -> GaussianRepGroupKnockoff:
+    """``modelX_gaussian_rep_group_knockoffs(X, method, groups[, μ, Σ]; m, rep_threshold, enforce_cond_indep, kwargs...)``
+    -- src/group.jl:155-203.  ``group_reps`` (1-based) overrides choose_group_reps."""
+    ctx = ctx or default_context()
+    X = _f(X)
+    n, p = X.shape
+    groups = np.ascontiguousarray(groups, dtype=np.int64)
+    if groups.shape != (p,):                                       # group.jl:183
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Dimensions of X and groups doesn't match")
+    if (mu is None) != (Sigma is None):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "give both mu and Sigma, or neither")
+    if Sigma is None:
+        Sigma, mu, _ = cov_shrink_lw(X, ctx=ctx)                   # group.jl:164-165
+    Sigma = _f(Sigma)
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    m = int(m)
+    if m < 1:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
+    opts = make_group_opts(**kwargs)
+    info = GroupInfo()
+    Vf = None if V is None else _f(V)
+    Zf = None if Z is None else _f(Z)
+    if Zf is not None and Zf.shape != (n, m * p):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
+    rin = None if group_reps is None else np.ascontiguousarray(group_reps, dtype=np.int64)
+    Xko = np.empty((n, m * p), order="F")
+    reps = np.zeros(p, dtype=np.int64)
+    nr = C.c_int64()
+    S11 = np.empty(p * p)
+    D = np.empty((p, p), order="F")
+    obj = C.c_double()
+    rc = ctx._lib.kb_modelx_gaussian_rep_group_knockoffs(
+        ctx.h, _ptr(X), n, p, _ptr(groups), _ptr(mu), _ptr(Sigma), _group_method_id(method), m, float(rep_threshold),
+        int(bool(enforce_cond_indep)), C.byref(opts), _ptr(rin), 0 if rin is None else rin.size, _ptr(Vf),
+        0 if Vf is None else Vf.shape[1], _ptr(Zf), int(seed), _ptr(Xko), _ptr(reps), C.byref(nr), _ptr(S11), _ptr(D),
+        C.byref(obj), C.byref(info))
+    check(ctx.h, rc)
+    r = nr.value
+    Ssym = np.triu(Sigma) + np.triu(Sigma, 1).T
+    return GaussianRepGroupKnockoff(X, Xko, groups, reps[:r].copy(), S11[:r * r].reshape((r, r), order="F").copy(), D, m, Ssym,
+                                    str(method).lstrip(":"), obj.value, bool(enforce_cond_indep),
+                                    _group_info_dict(info, str(method).lstrip(":")))
+
+
 # ---- hooks used by tests ---------------------------------------------------------------------------
 def hook_dgemm(A, B, C_in=None, transa=False, transb=False, alpha=1.0, beta=0.0, ctx: Optional[Context] = None):
     ctx = ctx or default_context()

@@ -6,6 +6,7 @@
 #include "group.cuh"
 #include "stats.cuh"
 #include "approx.cuh"
+#include "rep.cuh"
 #include <algorithm>
 #include <unordered_map>
 #include <cstring>
@@ -202,6 +203,27 @@ int h2d_columns(kb_ctx* ctx, Scope& sc, const double* X, long n, long c0, long c
     *ldx = (n + 1) & ~1L;
     KB_TRY(sc.alloc(dX, (size_t)(*ldx) * (size_t)(c1 - c0)));
     return h2d_matrix(ctx, X + (size_t)c0 * n, n, *dX, *ldx, n, c1 - c0, ctx->stream);
+}
+
+// 1-based index array of the ABI -> 0-based vector
+int from_one_based(kb_ctx* ctx, const int64_t* idx, int64_t n, int64_t p, std::vector<int>* out, const char* what) {
+    out->clear();
+    for (int64_t i = 0; i < n; ++i) {
+        if (idx[i] < 1 || idx[i] > p) return set_error(ctx, KB_ERR_INVALID, "%s: index %lld is outside 1..%lld", what, (long long)idx[i], (long long)p);
+        out->push_back((int)(idx[i] - 1));
+    }
+    return KB_OK;
+}
+// Σ[reps, reps] of Symmetric(Σ) (host)
+std::vector<double> gather_sigma11(const double* Sigma, int64_t p, const std::vector<int>& reps) {
+    const size_t r = reps.size();
+    std::vector<double> S11(r * r);
+    for (size_t j = 0; j < r; ++j)
+        for (size_t i = 0; i < r; ++i) {
+            const int a = std::min(reps[i], reps[j]), b = std::max(reps[i], reps[j]);
+            S11[i + j * r] = Sigma[a + (size_t)b * p];
+        }
+    return S11;
 }
 
 }  // namespace
@@ -866,6 +888,113 @@ int kb_approx_modelx_gaussian_knockoffs(kb_ctx* ctx, const double* X, int64_t n,
     if (gamma_out) *gamma_out = gamma;
     return approx_condition_windows(ctx, dX, (long)n, ldx, (long)p, window_offsets, nwin, 0, nwin, m, dblk, ds, dmu, Z, seed, 0,
                                     Xko_out);
+}
+
+
+// ---- (7) representative group knockoffs ------------------------------------------------
+int kb_choose_group_reps(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups, double threshold,
+                         const int64_t* prioritize_idx, int64_t n_prioritize, int64_t* group_reps_out,
+                         int64_t* n_reps_out) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !groups || !group_reps_out || !n_reps_out || p < 1 || p > 46000 || n_prioritize < 0)
+        return set_error(ctx, KB_ERR_INVALID, "choose_group_reps: bad arguments");
+    DeviceGuard g(ctx->device);
+    std::vector<int> prior, reps;
+    if (prioritize_idx) KB_TRY(from_one_based(ctx, prioritize_idx, n_prioritize, p, &prior, "prioritize_idx"));
+    KB_TRY(choose_group_reps_host(ctx, Sigma, (long)p, (int)p, groups, threshold, prioritize_idx != nullptr, prior, &reps));
+    for (size_t i = 0; i < reps.size(); ++i) group_reps_out[i] = reps[i] + 1;
+    *n_reps_out = (int64_t)reps.size();
+    return KB_OK;
+}
+
+int kb_cond_indep_corr(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups, const int64_t* group_reps,
+                       int64_t n_reps, double* Sigma_new_out) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !groups || !group_reps || !Sigma_new_out || p < 1 || n_reps < 1 || n_reps > p)
+        return set_error(ctx, KB_ERR_INVALID, "cond_indep_corr: bad arguments");
+    DeviceGuard g(ctx->device);
+    std::vector<int> reps;
+    KB_TRY(from_one_based(ctx, group_reps, n_reps, p, &reps, "group_reps"));
+    Scope sc(ctx);
+    double* dOut;
+    KB_TRY(sc.alloc(&dOut, (size_t)p * p));
+    KB_TRY(cond_indep_corr_dev(ctx, Sigma, (long)p, (int)p, groups, reps, dOut));
+    KB_CUDA(ctx, cudaMemcpyAsync(Sigma_new_out, dOut, sizeof(double) * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+int kb_solve_s_graphical_group(kb_ctx* ctx, const double* Sigma, int64_t p, const int64_t* groups,
+                               const int64_t* group_reps, int64_t n_reps, int32_t method, double m,
+                               const kb_group_opts* opts, const double* V, int64_t nv, double* S_out, double* D_out,
+                               double* obj_out, kb_group_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!Sigma || !groups || !group_reps || !S_out || !D_out || p < 1 || p > 46000 || n_reps < 1 || n_reps > p || nv < 0)
+        return set_error(ctx, KB_ERR_INVALID, "solve_s_graphical_group: bad arguments");
+    DeviceGuard g(ctx->device);
+    std::vector<int> reps;
+    KB_TRY(from_one_based(ctx, group_reps, n_reps, p, &reps, "group_reps"));
+    Scope sc(ctx);
+    double *dRaw, *dSig, *dD;
+    KB_TRY(sc.alloc(&dRaw, (size_t)p * p));
+    KB_TRY(sc.alloc(&dSig, (size_t)p * p));
+    KB_TRY(sc.alloc(&dD, (size_t)p * p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dRaw, Sigma, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(sym_upper_to_full_dev(ctx, dRaw, (long)p, (int)p, dSig, (long)p));
+    std::vector<double> S11 = gather_sigma11(Sigma, p, reps);
+    double obj = 0.0;
+    KB_TRY(solve_s_graphical_group_dev(ctx, dSig, (int)p, S11.data(), groups, reps, method, m, opts, V, (int)nv, S_out, dD, &obj,
+                                       info));
+    KB_CUDA(ctx, cudaMemcpyAsync(D_out, dD, sizeof(double) * p * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (obj_out) *obj_out = obj;
+    return KB_OK;
+}
+
+int kb_modelx_gaussian_rep_group_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const int64_t* groups,
+                                           const double* mu, const double* Sigma, int32_t method, int32_t m,
+                                           double rep_threshold, int32_t enforce_cond_indep, const kb_group_opts* opts,
+                                           const int64_t* group_reps_in, int64_t n_reps_in, const double* V, int64_t nv,
+                                           const double* Z, uint64_t seed, double* Xko_out, int64_t* group_reps_out,
+                                           int64_t* n_reps_out, double* S11_out, double* D_out, double* obj_out,
+                                           kb_group_info* info) {
+    if (!ctx) return bad_ctx();
+    if (!X || !mu || !Sigma || !groups || !Xko_out || !group_reps_out || !n_reps_out || !S11_out || p < 1 || p > 46000 || n < 0 ||
+        nv < 0)
+        return set_error(ctx, KB_ERR_INVALID, "modelX rep group: bad arguments");
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);
+    DeviceGuard g(ctx->device);
+    // group_reps = choose_group_reps(Symmetric(Σ), groups, threshold=rep_threshold)                (group.jl:186)
+    std::vector<int> reps;
+    if (group_reps_in) KB_TRY(from_one_based(ctx, group_reps_in, n_reps_in, p, &reps, "group_reps"));
+    else KB_TRY(choose_group_reps_host(ctx, Sigma, (long)p, (int)p, groups, rep_threshold, false, {}, &reps));
+    for (size_t i = 0; i < reps.size(); ++i) group_reps_out[i] = reps[i] + 1;
+    *n_reps_out = (int64_t)reps.size();
+    Scope sc(ctx);
+    const size_t pp = (size_t)p * p;
+    const size_t nblk = (size_t)(2 * m - 1);
+    double *dRaw, *dSig, *dD, *dmu, *dSiS, *dLb;
+    KB_TRY(sc.alloc(&dRaw, pp));
+    KB_TRY(sc.alloc(&dSig, pp));
+    KB_TRY(sc.alloc(&dD, pp));
+    KB_TRY(sc.alloc(&dmu, (size_t)p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dRaw, Sigma, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dmu, mu, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    // sigma = enforce_cond_indep ? cond_indep_corr(Σ, groups, group_reps) : Σ                       (group.jl:189)
+    if (enforce_cond_indep) KB_TRY(cond_indep_corr_dev(ctx, Sigma, (long)p, (int)p, groups, reps, dSig));
+    else KB_TRY(sym_upper_to_full_dev(ctx, dRaw, (long)p, (int)p, dSig, (long)p));
+    // S, D, obj = solve_s_graphical_group(Symmetric(sigma), groups, group_reps, method; m, kwargs...) (group.jl:192-193)
+    std::vector<double> S11 = gather_sigma11(Sigma, p, reps);          // cond_indep_corr keeps Σ[reps, reps]
+    double obj = 0.0;
+    KB_TRY(solve_s_graphical_group_dev(ctx, dSig, (int)p, S11.data(), groups, reps, method, (double)m, opts, V, (int)nv, S11_out,
+                                       dD, &obj, info));
+    if (obj_out) *obj_out = obj;
+    if (D_out) KB_CUDA(ctx, cudaMemcpyAsync(D_out, dD, sizeof(double) * pp, cudaMemcpyDeviceToHost, ctx->stream));
+    // X̃ = condition(X, μ, Σ, Symmetric(D); m)                                                      (group.jl:196)
+    KB_TRY(sc.alloc(&dSiS, pp));
+    KB_TRY(sc.alloc(&dLb, pp * nblk));
+    KB_TRY(cond_factor_dev(ctx, dRaw, (long)p, (int)p, dD, (long)p, 0, m, dSiS, dLb, (long)p));
+    return sample_host_pipeline(ctx, X, (long)n, (int)p, dmu, dSiS, dLb, (long)p, m, Z, seed, 0, Xko_out);
 }
 
 // ---- test hooks -------------------------------------------------------------------------------------
