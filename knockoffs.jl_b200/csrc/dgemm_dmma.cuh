@@ -82,6 +82,14 @@ struct GemmParams {
     int store_mode;         // 0 all, 1 only elements with m >= n (lower incl. diagonal)
     double* C2;             // optional second destination: columns n >= nsplit are stored to C2 + (n - nsplit) * ldc
     int nsplit;             //   (C2 == nullptr: off).  Requires beta == 0 or Cin laid out like the logical C.
+    // Batched launch (gridDim.z = batch > 1): problem z uses seg[s].A + z * zA[s], seg[s].B + z * zB[s], C + z * zC
+    // (Cin / bias are shared); the LAST problem uses only its first `last_nseg` segments when last_nseg > 0.
+    // One launch for the m copies of the sampling stage: 5 x 5056 CTAs instead of 5 launches with a partial last
+    // wave each.
+    int batch;
+    int last_nseg;
+    long zA[3], zB[3];
+    long zC;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
@@ -228,6 +236,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel
     }
     const int m0 = bx * BM, n0 = by * BN;
     if (P.tile_mode == 1 && m0 + BM <= n0) return;
+    const long zb = blockIdx.z;
+    const int nseg = (P.batch > 1 && P.last_nseg > 0 && (int)zb == P.batch - 1) ? P.last_nseg : P.nseg;
+    double* const Cz = P.C + zb * P.zC;
 
     double acc[MI][NJ][2];
 #pragma unroll
@@ -259,8 +270,10 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel
         }
     }
 
-    for (int s = 0; s < P.nseg; ++s) {
-        const GemmSeg sg = P.seg[s];
+    for (int s = 0; s < nseg; ++s) {
+        GemmSeg sg = P.seg[s];
+        sg.A += zb * P.zA[s];
+        sg.B += zb * P.zB[s];
         int kbeg = 0, kend = sg.K;
         if (sg.flags & SEG_KLO_N) kbeg = max(kbeg, n0);
         if (sg.flags & SEG_KLO_M) kbeg = max(kbeg, m0);
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel
                 if (!preload && P.beta != 0.0) v += P.beta * P.Cin[(long)m + (long)n * P.ldcin];
                 if (P.bias_n) v += P.bias_n[n];
                 if (P.C2 && n >= P.nsplit) P.C2[(long)m + (long)(n - P.nsplit) * P.ldc] = v;
-                else P.C[(long)m + (long)n * P.ldc] = v;
+                else Cz[(long)m + (long)n * P.ldc] = v;
             }
         }
     }

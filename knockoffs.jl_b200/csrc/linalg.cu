@@ -50,7 +50,7 @@ static int launch_gemm_t(kb_ctx* ctx, const GemmParams& P) {
     using Cfg = GemmDefaultCfg;
     auto kern = dgemm_dmma_kernel<Cfg, AL, BL, VEC>;
     KB_CUDA(ctx, raise_max_dynamic_smem((const void*)kern, Cfg::SMEM_BYTES));
-    dim3 grid(ceil_div(P.M, Cfg::BM), ceil_div(P.N, Cfg::BN));
+    dim3 grid(ceil_div(P.M, Cfg::BM), ceil_div(P.N, Cfg::BN), P.batch > 1 ? P.batch : 1);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(P);
     ctx->launches++;
     KB_CUDA(ctx, cudaGetLastError());
@@ -63,6 +63,7 @@ int gemm(kb_ctx* ctx, int AL, int BL, const GemmParams& P) {
     for (int s = 0; s < P.nseg; ++s) {
         const GemmSeg& g = P.seg[s];
         if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda & 1) || (g.ldb & 1)) vec = false;
+        if (P.batch > 1 && ((P.zA[s] & 1) || (P.zB[s] & 1))) vec = false;
     }
 #define KB_DISPATCH(al, bl)                                         \
     if (AL == al && BL == bl)                                       \

@@ -275,8 +275,9 @@ int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const do
         KB_TRY(trtri_lower(ctx, Lkk, ldo, p, invdiag, W, ld, work));
         // M_k = B_k * W'   :  B(kk, n) = W(n, kk), zero for kk > n
         KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, p, 1.0, B, ld, W, ld, 0.0, Mk, ldo, SEG_KHI_N));
-        // B_{k+1} = B_k − M_k M_k'
-        KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, p, -1.0, Mk, ldo, Mk, ldo, 1.0, B, ld));
+        // B_{k+1} = B_k − M_k M_k'  (symmetric: lower tiles only -- half the flops -- then mirrored)
+        KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, p, -1.0, Mk, ldo, Mk, ldo, 1.0, B, ld, 0, 1, 0));
+        KB_TRY(mirror_lower_to_upper(ctx, B, ld, p));
         // A_{k+1} = B_{k+1} + S
         sub_S_kernel<<<eg, 256, 0, ctx->stream>>>(B, ld, Sptr, Sld, s_is_diag, p, +1.0, C, ld);
         ctx->launches++;
@@ -302,14 +303,19 @@ __global__ void mu_sis_kernel(const double* mu, const double* SiS, long ld, int 
     }
     if (threadIdx.x == 0) bias[n] = red[0];
 }
-// T (+)= Z  (rows x cols)
-__global__ void accumulate_kernel(double* T, long ldt, const double* Z, long ldz, long rows, int cols, int first) {
+// Suffix sums of the noise blocks: T_k = Σ_{i>k} Z_i for k = 0 .. m−2 (T_k at T + k * tstride, Z_i at Z + i * zstride),
+// one pass (reads m−1 blocks, writes m−1 blocks).
+__global__ void suffix_sum_kernel(double* __restrict__ T, long ldt, long tstride, const double* __restrict__ Z, long ldz,
+                                  long zstride, long rows, int cols, int m) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long total = rows * cols;
     for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const long i = idx % rows, k = idx / rows;
-        const double z = Z[i + k * ldz];
-        T[i + k * ldt] = first ? z : T[i + k * ldt] + z;
+        const long i = idx % rows, c = idx / rows;
+        double acc = 0.0;
+        for (int k = m - 2; k >= 0; --k) {
+            acc += Z[i + c * ldz + (long)(k + 1) * zstride];
+            T[i + c * ldt + (long)k * tstride] = acc;
+        }
     }
 }
 
@@ -324,7 +330,7 @@ int sample_plan_create(kb_ctx* ctx, Scope& sc, int p, int m, const double* dmu, 
     KB_TRY(sc.alloc(&plan->bias, p));
     if (m > 1) {
         KB_TRY(sc.alloc(&plan->Mu, (size_t)plan->chunk * p));
-        KB_TRY(sc.alloc(&plan->T, (size_t)plan->chunk * p));
+        KB_TRY(sc.alloc(&plan->T, (size_t)plan->chunk * p * (m - 1)));
     }
     if (need_zbuf) KB_TRY(sc.alloc(&plan->Zbuf, (size_t)plan->chunk * p * m));
     negate_kernel<<<ew_grid2(ctx, (long)p * p), 256, 0, ctx->stream>>>(dSiS, ldo, p, p, plan->nSiS, plan->ld);
@@ -364,25 +370,26 @@ int sample_chunk(kb_ctx* ctx, const SamplePlan& pl, const double* Xc, long rows,
         KB_TRY(gemm(ctx, A_MCONTIG, B_KCONTIG, P));
     }
     // copy k (columns k p .. (k+1) p of X̃): μi + Z_k L_kk + (Σ_{i>k} Z_i) M_k  (block column k of
-    // randn(n, mp) * L, modelX.jl:121), k descending so the suffix sum T = Σ_{i>k} Z_i is a running sum.
-    for (int k = m - 1; k >= 0; --k) {
-        const double* Zk = Zc + (size_t)k * p * ldzc;
+    // randn(n, mp) * L, modelX.jl:121).  The suffix sums T_k = Σ_{i>k} Z_i are formed first, then ALL m copies run as
+    // ONE batched launch (gridDim.z = m: 5 x 5056 CTAs at p = 5000 instead of 5 launches with a partial last wave
+    // each); the last copy has no M block (one segment).
+    const size_t tstride = (size_t)pl.chunk * p;
+    suffix_sum_kernel<<<ew_grid2(ctx, rows * p), 256, 0, ctx->stream>>>(pl.T, pl.chunk, (long)tstride, Zc, ldzc, (long)p * ldzc,
+                                                                        rows, p, m);
+    ctx->launches++;
+    {
         GemmParams P{};
         P.M = (int)rows; P.N = p;
-        P.seg[0] = GemmSeg{Zk, ldzc, pl.dLb + (size_t)(2 * k) * bstride, pl.ldo, p, SEG_KLO_N};
-        P.nseg = 1;
-        if (k < m - 1) {
-            P.seg[1] = GemmSeg{pl.T, pl.chunk, pl.dLb + (size_t)(2 * k + 1) * bstride, pl.ldo, p, 0};
-            P.nseg = 2;
-        }
-        P.C = Xko + (size_t)k * p * ldxko; P.ldc = ldxko; P.Cin = pl.Mu; P.ldcin = pl.chunk;
+        P.seg[0] = GemmSeg{Zc, ldzc, pl.dLb, pl.ldo, p, SEG_KLO_N};            // Z_k L_kk, L lower
+        P.seg[1] = GemmSeg{pl.T, pl.chunk, pl.dLb + bstride, pl.ldo, p, 0};    // T_k M_k
+        P.nseg = 2;
+        P.batch = m; P.last_nseg = 1;
+        P.zA[0] = (long)p * ldzc; P.zB[0] = 2 * (long)bstride;
+        P.zA[1] = (long)tstride;  P.zB[1] = 2 * (long)bstride;
+        P.zC = (long)p * ldxko;
+        P.C = Xko; P.ldc = ldxko; P.Cin = pl.Mu; P.ldcin = pl.chunk;
         P.alpha = 1.0; P.beta = 1.0; P.bias_n = nullptr;
         KB_TRY(gemm(ctx, A_MCONTIG, B_KCONTIG, P));
-        if (k > 0) {
-            accumulate_kernel<<<ew_grid2(ctx, rows * p), 256, 0, ctx->stream>>>(pl.T, pl.chunk, Zk, ldzc, rows, p,
-                                                                                k == m - 1 ? 1 : 0);
-            ctx->launches++;
-        }
     }
     KB_CUDA(ctx, cudaGetLastError());
     return KB_OK;
