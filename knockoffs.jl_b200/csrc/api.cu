@@ -261,6 +261,8 @@ int kb_create(kb_ctx** out, int device) {
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
     for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
@@ -280,6 +282,9 @@ void kb_destroy(kb_ctx* ctx) {
         ctx->pool_free.clear();
         if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
         if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
+        if (ctx->stream_aux) { cudaStreamSynchronize(ctx->stream_aux); cudaStreamDestroy(ctx->stream_aux); }
+        for (int i = 0; i < 2; ++i)
+            if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
         for (int i = 0; i < 6; ++i)

@@ -27,6 +27,8 @@ struct kb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_h2d = nullptr;   // copy streams for the row-chunk pipeline
     cudaStream_t stream_d2h = nullptr;
+    cudaStream_t stream_aux = nullptr;   // look-ahead stream of the blocked Cholesky (trailing update || next panel)
+    cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string last_error;
     std::vector<void*> allocs;           // everything cudaMalloc'ed through ws_alloc (freed per call)

@@ -212,9 +212,12 @@ int choose_group_reps_host(kb_ctx* ctx, const double* Sigma, long lds, int p, co
         std::vector<char> seen(p, 0);
         for (int i = 0; i < p; ++i)
             for (int j = i + 1; j < p; ++j) {
-                bool dep = true;
-                for (int k = 0; k <= i; ++k)
-                    if (!isapprox(S(k, i), S(k, j))) { dep = false; break; }
+                // the predicate is "rows 1..i of columns i and j agree"; row i (Σ_ii = 1 against Σ_ij) is tested first
+                // -- same boolean, but structured matrices whose columns share long equal prefixes (block-equicorrelated
+                // Σ) no longer make this pre-pass O(p³)
+                bool dep = isapprox(S(i, i), S(i, j));
+                for (int k = 0; dep && k < i; ++k)
+                    if (!isapprox(S(k, i), S(k, j))) dep = false;
                 if (!dep) continue;
                 int d = j;
                 if (has_prior && std::find(prioritize.begin(), prioritize.end(), j) != prioritize.end()) d = i;
