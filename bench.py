@@ -398,6 +398,18 @@ def run_ours(a):
                      "traffic": NCU_TRAFFIC_BYTES["dgemm_dmma_kernel"],
                      "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, best of 6",
                      "algorithmic_flops_per_step": sample_flops, "stage_ms": sample_ms}
+        # conditional-covariance factor (modelX.jl:106-120).  SURVEY 8(d) algorithmic flops for diagonal S: p^3/3 + p^3
+        # (inverse) + m p^3/3 + (m-1)(p^3 + p^3) (structured factor).  Executed: p^3 + m p^3/3 + (m-1) 2p^3/3 -- for diagonal S
+        # the off-diagonal blocks are M_k = L_kk - S inv(L_kk)' and A_{k+1} = 2S - S inv(A_k) S (no p^3 GEMMs).
+        factor_ms = stage["factor_ms"] / k
+        fl_alg = float(p) ** 3 * (4.0 / 3.0 + m / 3.0 + 2.0 * (m - 1))
+        fl_exe = float(p) ** 3 * (1.0 + m / 3.0 + (m - 1) * 2.0 / 3.0)
+        roof_factor = {"kernel": "cond_factor (potrf_diag_kernel + dgemm_dmma_kernel trailing updates / trtri / syrk)", "bound": "tensor",
+                       "achieved": fl_alg / (factor_ms * 1e-3) / 1e12 if factor_ms > 0 else 0.0, "peak": fp64_peak, "unit": "TFLOP/s",
+                       "frac": (fl_alg / (factor_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and factor_ms > 0) else None,
+                       "algorithmic_flops_per_step": fl_alg, "executed_flops_per_step": fl_exe,
+                       "executed_tflops": fl_exe / (factor_ms * 1e-3) / 1e12 if factor_ms > 0 else 0.0, "stage_ms": factor_ms,
+                       "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"}
         dominant = roof_ccd if ccd_ms >= sample_ms else roof_gemm
         other = roof_gemm if dominant is roof_ccd else roof_ccd
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -411,6 +423,7 @@ def run_ours(a):
                               "cond_factor": stage["factor_ms"] / k, "sampling": sample_ms},
                 "solve_s_seconds": stage["solve_ms"] / k / 1e3,
                 "roofline": dominant, "roofline_secondary": other}
+        line["roofline_cond_factor"] = roof_factor
         if stream_roof is not None:
             line["roofline_ccd_stream"] = stream_roof
         if e2e is not None:
