@@ -373,6 +373,54 @@ __global__ void suffix_sum_kernel(double* __restrict__ T, long ldt, long tstride
     }
 }
 
+// Inclusive suffix sums S_k = Σ_{i>=k} Z_i for k = 0 .. m−1 (S_k at T + k * tstride).
+__global__ void suffix_sum_incl_kernel(double* __restrict__ T, long ldt, long tstride, const double* __restrict__ Z, long ldz,
+                                       long zstride, long rows, int cols, int m) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = rows * cols;
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long i = idx % rows, c = idx / rows;
+        double acc = 0.0;
+        for (int k = m - 1; k >= 0; --k) {
+            acc += Z[i + c * ldz + (long)k * zstride];
+            T[i + c * ldt + (long)k * tstride] = acc;
+        }
+    }
+}
+// flag |= 1 if some strictly-lower entry of an M_k differs from the same entry of L_kk (blocks [L_11 | M_1 | L_22 | ...])
+__global__ void factor_structure_kernel(const double* __restrict__ Lb, long ldo, long bstride, int p, int m, int* __restrict__ flag) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per = (long)p * p, total = per * (m - 1);
+    int bad = 0;
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx / per);
+        const long e = idx % per;
+        const int i = (int)(e % p), j = (int)(e / p);
+        if (i > j) {
+            const double l = Lb[(size_t)(2 * k) * bstride + i + (long)j * ldo], mk = Lb[(size_t)(2 * k + 1) * bstride + i + (long)j * ldo];
+            if (!(l == mk)) bad = 1;
+        }
+    }
+    if (bad) atomicOr(flag, 1);
+}
+// N_k = triu(M_k) − diag(L_kk)   (upper triangular; strict lower zero)
+__global__ void factor_upper_part_kernel(const double* __restrict__ Lb, long ldo, long bstride, int p, int m, double* __restrict__ N,
+                                         long ldn) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per = (long)p * p, total = per * (m - 1);
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx / per);
+        const long e = idx % per;
+        const int i = (int)(e % p), j = (int)(e / p);
+        double v = 0.0;
+        if (i <= j) {
+            v = Lb[(size_t)(2 * k + 1) * bstride + i + (long)j * ldo];
+            if (i == j) v -= Lb[(size_t)(2 * k) * bstride + i + (long)j * ldo];
+        }
+        N[(size_t)k * ldn * p + i + (long)j * ldn] = v;
+    }
+}
+
 int sample_plan_create(kb_ctx* ctx, Scope& sc, int p, int m, const double* dmu, const double* dSiS, const double* dLb,
                        long ldo, long chunk, bool need_zbuf, SamplePlan* plan) {
     if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);   // modelX.jl:105
@@ -383,8 +431,31 @@ int sample_plan_create(kb_ctx* ctx, Scope& sc, int p, int m, const double* dmu, 
     KB_TRY(sc.alloc(&plan->nSiS, (size_t)plan->ld * p));
     KB_TRY(sc.alloc(&plan->bias, p));
     if (m > 1) {
+        // Structure of the factor blocks: for Diagonal(s) every M_k = L_kk − S inv(L_kk)' has the strict lower triangle of
+        // L_kk (bit for bit), i.e. M_k = L_kk + N_k with N_k upper triangular.  Then, with S_k = Σ_{i>=k} Z_i,
+        //     Z_k L_kk + (Σ_{i>k} Z_i) M_k = S_k L_kk + S_{k+1} N_k
+        // is TWO triangular products (2 n p² flops per copy) instead of a triangular and a dense one (3 n p²).
+        // Detected here, so kb_sample also takes the short form for factor blocks passed in by the caller;
+        // anything else (dense S of the group path) keeps the general form.
+        static const bool allow = [] { const char* e = getenv("KB_SAMPLE_STRUCTURED"); return !(e && e[0] == '0'); }();
+        int* dflag;
+        KB_TRY(sc.alloc(&dflag, 4));
+        KB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
+        const size_t bstride = (size_t)ldo * p;
+        factor_structure_kernel<<<ew_grid2(ctx, (long)p * p * (m - 1)), 256, 0, ctx->stream>>>(dLb, ldo, (long)bstride, p, m, dflag);
+        ctx->launches++;
+        int hflag = 1;
+        KB_CUDA(ctx, cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        plan->structured = allow && (hflag == 0);
         KB_TRY(sc.alloc(&plan->Mu, (size_t)plan->chunk * p));
-        KB_TRY(sc.alloc(&plan->T, (size_t)plan->chunk * p * (m - 1)));
+        KB_TRY(sc.alloc(&plan->T, (size_t)plan->chunk * p * (plan->structured ? m : m - 1)));
+        if (plan->structured) {
+            KB_TRY(sc.alloc(&plan->N, (size_t)plan->ld * p * (m - 1)));
+            factor_upper_part_kernel<<<ew_grid2(ctx, (long)p * p * (m - 1)), 256, 0, ctx->stream>>>(dLb, ldo, (long)bstride, p, m,
+                                                                                                  plan->N, plan->ld);
+            ctx->launches++;
+        }
     }
     if (need_zbuf) KB_TRY(sc.alloc(&plan->Zbuf, (size_t)plan->chunk * p * m));
     negate_kernel<<<ew_grid2(ctx, (long)p * p), 256, 0, ctx->stream>>>(dSiS, ldo, p, p, plan->nSiS, plan->ld);
@@ -428,6 +499,27 @@ int sample_chunk(kb_ctx* ctx, const SamplePlan& pl, const double* Xc, long rows,
     // ONE batched launch (gridDim.z = m: 5 x 5056 CTAs at p = 5000 instead of 5 launches with a partial last wave
     // each); the last copy has no M block (one segment).
     const size_t tstride = (size_t)pl.chunk * p;
+    if (pl.structured) {
+        // X̃_k = μi + S_k L_kk + S_{k+1} N_k  (S_k inclusive suffix sums; L_kk lower, N_k upper: every tile's two clipped
+        // k-ranges add up to p + BN, so the batched launch is perfectly balanced)
+        suffix_sum_incl_kernel<<<ew_grid2(ctx, rows * p), 256, 0, ctx->stream>>>(pl.T, pl.chunk, (long)tstride, Zc, ldzc,
+                                                                                 (long)p * ldzc, rows, p, m);
+        ctx->launches++;
+        GemmParams P{};
+        P.M = (int)rows; P.N = p;
+        P.seg[0] = GemmSeg{pl.T, pl.chunk, pl.dLb, pl.ldo, p, SEG_KLO_N};                       // S_k L_kk
+        P.seg[1] = GemmSeg{pl.T + tstride, pl.chunk, pl.N, pl.ld, p, SEG_KHI_N};                // S_{k+1} N_k
+        P.nseg = 2;
+        P.batch = m; P.last_nseg = 1;
+        P.zA[0] = (long)tstride; P.zB[0] = 2 * (long)bstride;
+        P.zA[1] = (long)tstride; P.zB[1] = (long)pl.ld * p;
+        P.zC = (long)p * ldxko;
+        P.C = Xko; P.ldc = ldxko; P.Cin = pl.Mu; P.ldcin = pl.chunk;
+        P.alpha = 1.0; P.beta = 1.0; P.bias_n = nullptr;
+        KB_TRY(gemm(ctx, A_MCONTIG, B_KCONTIG, P));
+        KB_CUDA(ctx, cudaGetLastError());
+        return KB_OK;
+    }
     suffix_sum_kernel<<<ew_grid2(ctx, rows * p), 256, 0, ctx->stream>>>(pl.T, pl.chunk, (long)tstride, Zc, ldzc, (long)p * ldzc,
                                                                         rows, p, m);
     ctx->launches++;

@@ -27,7 +27,9 @@ struct SamplePlan {
     double* nSiS = nullptr;    // −ΣinvS
     double* bias = nullptr;    // μ'ΣinvS
     double* Mu = nullptr;      // m > 1: X − (X .− μ')ΣinvS of the current chunk
-    double* T = nullptr;       // m > 1: running suffix sum of the Z blocks
+    double* T = nullptr;       // m > 1: suffix sums of the Z blocks (m − 1 exclusive ones, or m inclusive ones if structured)
+    bool structured = false;   // every M_k = L_kk + (upper triangular N_k): copies cost 2 n p² instead of 3 n p²
+    double* N = nullptr;       // structured: N_k = triu(M_k) − diag(L_kk), m − 1 blocks of ld x p
     double* Zbuf = nullptr;    // device-generated Z of the current chunk (chunk x m p)
     const double* dLb = nullptr;
     long ldo = 0;
