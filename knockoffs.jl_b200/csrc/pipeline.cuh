@@ -9,8 +9,10 @@ void default_solve_opts(kb_solve_opts* o);
 int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, double m, const kb_solve_opts* opts,
                 const double* d_s_init, double* d_s_out, kb_solve_info* info);
 
+// inverse_iteration: place the probes with Rayleigh-quotient upper bounds (solve.cu).  Off for the group solver, whose
+// sharded form needs every rank to walk the SAME deterministic probe sequence as the single-GPU solve.
 int eigmin_lower_dev(kb_ctx* ctx, const double* B, long ld, int p, double* work_A, double* invdiag, int* d_fail,
-                     double* lambda_out);
+                     double* lambda_out, bool inverse_iteration = false);
 // λmin(Symmetric(Sigma)) for a matrix given by its upper triangle
 int eigmin_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, double* lambda_out);
 

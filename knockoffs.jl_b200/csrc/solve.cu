@@ -111,6 +111,58 @@ __global__ void shift_copy_lower_kernel(const double* B, long ld, int p, double 
     }
 }
 
+
+// ---- inverse iteration on a successful probe's factor: Rayleigh-quotient UPPER bounds for λmin ----------------------
+// t_part[ks][i] = scale * Σ_{k in chunk ks, k <= i} W[i,k] x[k]      (W lower triangular, column-major)
+__global__ void tri_gemv_lower_kernel(const double* __restrict__ W, long ldw, int p, const double* __restrict__ x, double scale,
+                                      int kchunk, double* __restrict__ part, long ldp) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int k0 = blockIdx.y * kchunk;
+    if (i >= p) return;
+    const int k1 = min(min(p, k0 + kchunk), i + 1);
+    double a0 = 0.0, a1 = 0.0;
+    int k = k0;
+    for (; k + 1 < k1; k += 2) {
+        a0 = fma(W[i + (long)k * ldw], x[k], a0);
+        a1 = fma(W[i + (long)(k + 1) * ldw], x[k + 1], a1);
+    }
+    if (k < k1) a0 = fma(W[i + (long)k * ldw], x[k], a0);
+    part[(long)blockIdx.y * ldp + i] = (a0 + a1) * scale;
+}
+__global__ void reduce_parts_kernel(const double* __restrict__ part, long ldp, int ks, int p, double* __restrict__ t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p) return;
+    double a = 0.0;
+    for (int k = 0; k < ks; ++k) a += part[(long)k * ldp + i];
+    t[i] = a;
+}
+// y_k = Σ_{i >= k} W[i,k] t_i : one warp per column
+__global__ void tri_gemv_lower_T_kernel(const double* __restrict__ W, long ldw, int p, const double* __restrict__ t,
+                                        double* __restrict__ y) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= p) return;
+    const double* w = W + (long)k * ldw;
+    double a = 0.0;
+    for (int i = k + lane; i < p; i += 32) a = fma(w[i], t[i], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) y[k] = a;
+}
+// colq[k] = y_k (B_kk y_k + 2 Σ_{i > k} B_ik y_i)  (B symmetric, lower triangle stored);  Σ_k colq[k] = y'By
+__global__ void quadform_lower_kernel(const double* __restrict__ B, long ld, int p, const double* __restrict__ y,
+                                      double* __restrict__ colq) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= p) return;
+    const double* b = B + (long)k * ld;
+    double a = 0.0;
+    for (int i = k + 1 + lane; i < p; i += 32) a = fma(b[i], y[i], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) colq[k] = y[k] * (b[k] * y[k] + 2.0 * a);
+}
+
 static inline int ewg(kb_ctx* ctx, long total) {
     long g = (total + 255) / 256, cap = (long)ctx->num_sms * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -145,7 +197,7 @@ static double powerlaw_root(const double x[3], const double y[3]) {
 // to halve the bracket is followed by a plain bisection step, so the worst case is ~bisection (≈ 45
 // factorisations) and isolated / multiple smallest eigenvalues take ≈ 13.  No host LAPACK anywhere.
 int eigmin_lower_dev(kb_ctx* ctx, const double* B, long ld, int p, double* work_A, double* invdiag, int* d_fail,
-                     double* lambda_out) {
+                     double* lambda_out, bool inverse_iteration) {
     double* d_g = nullptr;
     Scope sc(ctx);
     KB_TRY(sc.alloc(&d_g, 2 * 64));
@@ -194,6 +246,95 @@ int eigmin_lower_dev(kb_ctx* ctx, const double* B, long ld, int p, double* work_
         else { lo = lb - 1e-12 * fabs(lb) - 1e-300; hi = fmin(hi, 0.0); }
     }
     if (hi <= lo) { *lambda_out = hi; return KB_OK; }
+    // Inverse iteration on the factor of the first successful probe: x <- (B − lo I)⁻¹ x through W = L⁻¹ (two
+    // triangular matrix-vector products per step, HBM-bound); every Rayleigh quotient ρ(x) = x'Bx / x'x is an UPPER
+    // bound of λmin.  With a spectral gap above λmin (any multiplicity: block-equicorrelated Σ) it converges in a
+    // handful of steps and ONE more probe just below it closes the bracket (p = 5000: 11 -> 3 factorisations);
+    // without a gap (AR(1) edge) it still replaces the first bisection steps.  The probes stay the only arbiter.
+    static const bool use_rq = [] { const char* e = getenv("KB_EIGMIN_RQ"); return !(e && e[0] == '0'); }();
+    const bool rq_on = inverse_iteration && use_rq && p >= 2;
+    const int KS = 16;
+    const int kchunk = (p + KS - 1) / KS;
+    double *Wi = nullptr, *wk = nullptr, *part = nullptr, *xv = nullptr, *tv = nullptr, *yv = nullptr, *colq = nullptr;
+    std::vector<double> hy, hq;
+    const double* xin = nullptr;
+    double xscale = 1.0, stage_width = INFINITY;
+    if (rq_on) {
+        KB_TRY(sc.alloc(&Wi, (size_t)ld * p));
+        KB_TRY(sc.alloc(&wk, (size_t)ld * p / 2 + 2 * ld + 64));
+        KB_TRY(sc.alloc(&part, (size_t)KS * ld));
+        KB_TRY(sc.alloc(&xv, (size_t)ld));
+        KB_TRY(sc.alloc(&tv, (size_t)ld));
+        KB_TRY(sc.alloc(&yv, (size_t)ld));
+        KB_TRY(sc.alloc(&colq, (size_t)ld));
+        hy.resize(p); hq.resize(p);
+        std::vector<double> hx(p);
+        for (int i = 0; i < p; ++i) hx[i] = 1.0 + 0.37 * sin(1.0 + 2.39996322972865332 * i);   // fixed, generic start
+        KB_CUDA(ctx, cudaMemcpyAsync(xv, hx.data(), sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        xin = xv;
+    }
+    // One stage: work_A must hold the factor of B − lo I (the last probe was the successful one at lo).
+    auto rq_stage = [&]() -> int {
+        stage_width = hi - lo;
+        KB_TRY(trtri_lower(ctx, work_A, ld, p, invdiag, Wi, ld, wk));
+        double rho_prev = NAN, d_prev = NAN, rho = NAN, est_err = NAN, qr_last = 1.0;
+        int its = 0;
+        for (; its < 40; ++its) {
+            dim3 g1(ceil_div(p, 128), KS);
+            tri_gemv_lower_kernel<<<g1, 128, 0, ctx->stream>>>(Wi, ld, p, xin, xscale, kchunk, part, ld);
+            reduce_parts_kernel<<<ceil_div(p, 256), 256, 0, ctx->stream>>>(part, ld, KS, p, tv);
+            tri_gemv_lower_T_kernel<<<ceil_div(p, 8), 256, 0, ctx->stream>>>(Wi, ld, p, tv, yv);
+            quadform_lower_kernel<<<ceil_div(p, 8), 256, 0, ctx->stream>>>(B, ld, p, yv, colq);
+            ctx->launches += 4;
+            KB_CUDA(ctx, cudaMemcpyAsync(hy.data(), yv, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+            KB_CUDA(ctx, cudaMemcpyAsync(hq.data(), colq, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+            KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            long double yy = 0.0L, q = 0.0L;
+            for (int i = 0; i < p; ++i) { yy += (long double)hy[i] * hy[i]; q += hq[i]; }
+            if (!(yy > 0.0L) || !std::isfinite((double)yy) || !std::isfinite((double)q)) return KB_OK;
+            rho = (double)(q / yy);
+            xscale = 1.0 / sqrt((double)yy);
+            xin = yv;   // next step reads y (scaled inside the kernel); y is rewritten only after t has been formed
+            const double dcur = rho_prev - rho;                      // >= 0 up to rounding
+            if (its >= 1) {
+                double qr = (d_prev == d_prev && d_prev > 0.0) ? dcur / d_prev : NAN;   // ≈ r², r = (λmin − lo)/(λ2 − lo)
+                if (!(qr == qr) || qr < 0.0) qr = 0.0;
+                qr_last = qr;
+                if (qr > 0.95) qr = 0.95;
+                est_err = fabs(dcur) * qr / (1.0 - qr);
+                if (fabs(dcur) <= 4e-16 * fabs(rho)) { est_err = 0.0; ++its; break; }
+                if (its >= 8 && qr > 0.8) { ++its; break; }           // no gap at this shift: leave the rest to the probes
+            }
+            d_prev = dcur; rho_prev = rho;
+        }
+        if (trace_probes) fprintf(stderr, "[eigmin rq] %d steps rho=%.17g est_err=%.3e\n", its, rho, est_err);
+        if (rho == rho && rho > lo && rho * (1.0 + 64.0 * 2.220446049250313e-16) < hi)
+            hi = rho * (1.0 + 64.0 * 2.220446049250313e-16) + 1e-300;   // upper bound, padded for the rounding of x'Bx
+        if (!(rho == rho) || !(rho > lo)) return KB_OK;
+        // two probes below the bound: a safe one (the Rayleigh quotient of an eigenvector of a matrix with condition
+        // number c carries ~c·eps of rounding), then one at a quarter of the final tolerance
+        const double margins[2] = {fmax(4.0 * (est_err == est_err ? est_err : 0.0), 2.5e-12 * fabs(rho)), 0.25 * tol * fabs(rho)};
+        if (margins[0] > 0.5 * (hi - lo) || (est_err != 0.0 && qr_last > 0.5)) return KB_OK;   // slow / unconverged: the error
+                                                                      // estimate is not trustworthy, keep only the bound
+        for (int t = 0; t < 2; ++t) {
+            const double sigma = rho - margins[t];
+            if (!(sigma > lo && sigma < hi)) break;
+            KB_TRY(is_pd(sigma, &pd, &h));
+            if (pd) { lo = sigma; if (t == 0) npts = 0; push(sigma, h); } else hi = sigma;
+            if (trace_probes)
+                fprintf(stderr, "[eigmin rq] probe sigma=%.17g %s width=%.3e\n", sigma, pd ? "PD" : "no", hi - lo);
+            if (!pd || margins[0] > 1e-9 * fabs(rho)) break;          // not converged: hand over to the bracket loop
+        }
+        return KB_OK;
+    };
+    // Inverse iteration on the factor of a successful probe: x <- (B − lo I)⁻¹ x through W = L⁻¹ (two triangular
+    // matrix-vector products per step, HBM-bound); every Rayleigh quotient ρ(x) = x'Bx / x'x is an UPPER bound of λmin.
+    // With a spectral gap above λmin (any multiplicity: block-equicorrelated Σ) the first stage converges in a handful
+    // of steps and two more probes just below ρ close the bracket (p = 5000: 11 -> 3 factorisations).  Without a gap
+    // (AR(1) edge) the stage is repeated whenever the bracket has shrunk 100x -- it converges once lo is within the
+    // gap of λmin (~22 instead of 46 factorisations).  The Cholesky probes stay the only arbiter.
+    if (rq_on && pd) KB_TRY(rq_stage());
     double est_prev = NAN;
     bool force_bisect = false;
     for (int it = 0; it < 200; ++it) {
@@ -226,6 +367,7 @@ int eigmin_lower_dev(kb_ctx* ctx, const double* B, long ld, int p, double* work_
         KB_TRY(is_pd(sigma, &pd, &h));
         if (pd) { lo = sigma; push(sigma, h); } else hi = sigma;
         force_bisect = guided && (hi - lo) > 0.5 * w0;
+        if (rq_on && pd && (hi - lo) <= 0.01 * stage_width && (hi - lo) > tol * fmax(fabs(lo), fabs(hi))) KB_TRY(rq_stage());
         if (trace_probes)
             fprintf(stderr, "[eigmin %2d] %s sigma=%.17g %s h=%.6e est=%.17g width=%.3e\n", it, guided ? "guided" : "bisect", sigma,
                     pd ? "PD" : "no", pd ? h : 0.0, est, hi - lo);
@@ -248,7 +390,7 @@ int eigmin_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, double* lambd
     build_cor_lower_kernel<<<grid, block, 0, ctx->stream>>>(dSigma, lds, p, d_one, 1, B, ld);
     ctx->launches++;
     KB_CUDA(ctx, cudaGetLastError());
-    return eigmin_lower_dev(ctx, B, ld, p, A, invdiag, d_fail, lambda_out);
+    return eigmin_lower_dev(ctx, B, ld, p, A, invdiag, d_fail, lambda_out, true);
 }
 
 void default_solve_opts(kb_solve_opts* o) {
@@ -324,7 +466,7 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
     const bool need_equi = (method == KB_METHOD_EQUI) || (method != KB_METHOD_SDP_CCD && d_s_init == nullptr);
     if (need_equi) {
         double lam = 0.0;
-        KB_TRY(eigmin_lower_dev(ctx, Cor, ld, p, A, invdiag, d_fail, &lam));
+        KB_TRY(eigmin_lower_dev(ctx, Cor, ld, p, A, invdiag, d_fail, &lam, true));
         double sj = kappa * lam;                           // utilities.jl:108-110
         if (sj > 1.0) sj = 1.0;
         fill_kernel<<<ceil_div(p, 256), 256, 0, ctx->stream>>>(s, p, sj);
