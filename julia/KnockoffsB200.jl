@@ -162,4 +162,42 @@ function fit_marginal(y::Vector{Float64}, X::Matrix{Float64}, μ::Vector{Float64
     return W, τs, [findall(!iszero, view(mask, :, f)) for f in 1:nf]
 end
 
+# ---- representative group knockoffs (src/group.jl:155-303, 1929-2033) -----------------------------------------
+"Drop-in for `choose_group_reps(Σ::Symmetric, groups; threshold, prioritize_idx)`; indices are 1-based on both sides."
+function choose_group_reps(Σ::Symmetric{Float64}, groups::Vector{Int}; threshold=0.5,
+                           prioritize_idx::Union{Vector{Int},Nothing}=nothing)
+    c = ctx(); p = size(Σ, 1); reps = Vector{Int64}(undef, p); nr = Ref{Int64}(0); A = Σ.data
+    pr = prioritize_idx === nothing ? C_NULL : pointer(prioritize_idx)
+    GC.@preserve A groups reps prioritize_idx begin
+        rc = ccall((:kb_choose_group_reps, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Ptr{Int64}, Float64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}),
+                   c.h, A, p, groups, Float64(threshold), pr, prioritize_idx === nothing ? 0 : length(prioritize_idx), reps, nr)
+        check(c, rc)
+    end
+    return reps[1:nr[]]
+end
+
+"Drop-in for `modelX_gaussian_rep_group_knockoffs(X, method, groups, μ, Σ; m, rep_threshold, enforce_cond_indep, kwargs...)`."
+function modelX_gaussian_rep_group_knockoffs(X::Matrix{Float64}, method::Union{Symbol,String}, groups::Vector{Int},
+                                             μ::Vector{Float64}, Σ::Matrix{Float64}; m::Int=1, rep_threshold=0.5,
+                                             enforce_cond_indep::Bool=false, seed::Integer=rand(UInt64), kwargs...)
+    c = ctx(); n, p = size(X)
+    p == length(groups) || error("Dimensions of X and groups doesn't match")
+    Xko = Matrix{Float64}(undef, n, m * p); reps = Vector{Int64}(undef, p); nr = Ref{Int64}(0)
+    S11 = Vector{Float64}(undef, p * p); D = Matrix{Float64}(undef, p, p); obj = Ref{Float64}(0.0)
+    o = Ref(gopts(; kwargs...)); info = Ref{GroupInfo}()
+    GC.@preserve X groups μ Σ Xko reps S11 D begin
+        rc = ccall((:kb_modelx_gaussian_rep_group_knockoffs, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64, Int32,
+                    Ptr{GroupOpts}, Ptr{Int64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Int64},
+                    Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{GroupInfo}),
+                   c.h, X, n, p, groups, μ, Σ, GROUP_METHODS[Symbol(method)], m, Float64(rep_threshold), enforce_cond_indep, o,
+                   C_NULL, 0, C_NULL, 0, C_NULL, seed, Xko, reps, nr, S11, D, obj, info)
+        check(c, rc)
+    end
+    r = nr[]
+    # wrap in GaussianRepGroupKnockoff (src/struct.jl:36-48)
+    return Xko, reps[1:r], reshape(S11[1:r*r], r, r), Symmetric(D), obj[]
+end
+
 end # module
