@@ -158,7 +158,8 @@ def test_cond_factor_matches_oracle(kb, ctx, p, m):
     assert np.max(np.abs(L - L_w)) / np.max(np.abs(L_w)) < 1e-8
 
 
-@pytest.mark.parametrize("n,p,m", [(1000, 500, 1), (333, 130, 3), (4097, 200, 2), (1, 64, 1), (9000, 96, 5)])
+@pytest.mark.parametrize("n,p,m", [(1000, 500, 1), (333, 130, 3), (4097, 200, 2), (1, 64, 1), (9000, 96, 5),
+                                   (257, 131, 3), (65, 33, 4), (4099, 67, 2)])   # odd p / n: unvectorised operand paths
 def test_condition_matches_oracle_with_injected_Z(kb, ctx, n, p, m):
     rng = np.random.default_rng(n + p + m)
     Sigma = toeplitz(p, 0.5)
