@@ -335,6 +335,10 @@ int kb_modelx_gaussian_rep_group_knockoffs(kb_ctx* ctx, const double* X, int64_t
 int kb_test_dgemm(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_t N, int64_t K,
                   double alpha, const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
                   double* C, int64_t ldc);
+/* the same on DEVICE pointers, enqueued on ctx's stream without synchronisation (kernel timing against cuBLAS) */
+int kb_test_dgemm_dev(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_t N, int64_t K, double alpha,
+                      const double* dA, int64_t lda, const double* dB, int64_t ldb, double beta, double* dC,
+                      int64_t ldc);
 /* lower Cholesky factor (potrf) and inverse of an SPD matrix on the device kernels. */
 int kb_test_potrf(kb_ctx* ctx, const double* A, int64_t p, double* L_out);
 int kb_test_spd_inverse(kb_ctx* ctx, const double* A, int64_t p, double* Ainv_out);

@@ -1024,6 +1024,15 @@ int kb_test_dgemm(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_
     return KB_OK;
 }
 
+int kb_test_dgemm_dev(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_t N, int64_t K, double alpha,
+                      const double* dA, int64_t lda, const double* dB, int64_t ldb, double beta, double* dC, int64_t ldc) {
+    if (!ctx) return bad_ctx();
+    if (!dA || !dB || !dC || M < 1 || N < 1 || K < 1) return set_error(ctx, KB_ERR_INVALID, "test_dgemm_dev: bad arguments");
+    DeviceGuard g(ctx->device);
+    return gemm1(ctx, transa ? A_KCONTIG : A_MCONTIG, transb ? B_NCONTIG : B_KCONTIG, (int)M, (int)N, (int)K, alpha, dA, (long)lda,
+                 dB, (long)ldb, beta, dC, (long)ldc);
+}
+
 int kb_test_potrf(kb_ctx* ctx, const double* A, int64_t p, double* L_out) {
     if (!ctx) return bad_ctx();
     DeviceGuard g(ctx->device);
