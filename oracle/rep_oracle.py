@@ -7,7 +7,7 @@ Restates, line by line (paths relative to /root/reference):
   src/group.jl:2050-2056  prioritize_variants         src/group.jl:2070-2098  select_one / select_best_rss_subset
   src/group.jl:205-240    cond_indep_corr             src/group.jl:268-303    solve_s_graphical_group
   src/group.jl:170-203    modelX_gaussian_rep_group_knockoffs
-Pinned against the reference's own known answers for this path: test/runtests.jl:735-744 (issue 71: the 6 x 6
+Pinned against the reference's own known answers for this path: test/runtests.jl:733-744 (issue 71: the 6 x 6
 correlation matrix with groups [1,2,3,4,3,3] -> representatives [1,2,3,4] at threshold 0.5 and [1,2,3,4,5] at 0.999)
 = tests/golden/reference_known_answers.json key K9; the nesting property of runtests.jl:712-716 is checked too.
 Indices are 0-based here (the golden file keeps the reference's 1-based values).

@@ -1,6 +1,6 @@
 """Representative group knockoffs (src/group.jl:155-303, 1929-2098).
 
-CPU: the oracle against the reference's known answers (test/runtests.jl:735-744 = golden K9) and its property
+CPU: the oracle against the reference's known answers (test/runtests.jl:733-744 = golden K9) and its property
 tests (:712-716 nesting of representatives, :747-770 dependent columns / prioritize_idx).  GPU: the library against
 the same known answers and against the oracle (identical representative sets; S, D within 1e-8 relative, X̃ within
 1e-10 with injected Z and a shared direction set V)."""
