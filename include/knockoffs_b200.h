@@ -339,6 +339,9 @@ int kb_test_dgemm(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_
 int kb_test_dgemm_dev(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_t N, int64_t K, double alpha,
                       const double* dA, int64_t lda, const double* dB, int64_t ldb, double beta, double* dC,
                       int64_t ldc);
+/* structure of factor blocks as the sampling stage detects it: band_out = 0 (every M_k = L_kk + upper triangular:
+ * Diagonal(s)), a multiple of 16 up to 64 (banded below the diagonal: contiguous group blocks) or -1 (general form). */
+int kb_test_factor_band(kb_ctx* ctx, const double* Lblocks, int64_t p, int32_t m, int32_t* band_out);
 /* lower Cholesky factor (potrf) and inverse of an SPD matrix on the device kernels. */
 int kb_test_potrf(kb_ctx* ctx, const double* A, int64_t p, double* L_out);
 int kb_test_spd_inverse(kb_ctx* ctx, const double* A, int64_t p, double* Ainv_out);

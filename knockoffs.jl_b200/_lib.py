@@ -103,6 +103,7 @@ SIGNATURES = {
                                                          C.POINTER(_i64), _vp, _vp, c_double_p, C.POINTER(GroupInfo)]),
     "kb_test_dgemm": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_dgemm_dev": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
+    "kb_test_factor_band": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_int32)]),
     "kb_test_potrf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_spd_inverse": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_randn": (C.c_int, [_vp, _u64, _i64, _i64, _i64, _vp]),

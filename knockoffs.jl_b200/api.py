@@ -829,6 +829,15 @@ def hook_dgemm(A, B, C_in=None, transa=False, transb=False, alpha=1.0, beta=0.0,
     return Cm
 
 
+def hook_factor_band(Lblocks, ctx: Optional[Context] = None) -> int:
+    """Structure of factor blocks as the sampling stage sees it: 0 / 16..64 (two triangular products per copy) or -1."""
+    ctx = ctx or default_context()
+    Lb = _f(Lblocks)
+    out = C.c_int32()
+    check(ctx.h, ctx._lib.kb_test_factor_band(ctx.h, _ptr(Lb), Lb.shape[0], (Lb.shape[2] + 1) // 2, C.byref(out)))
+    return out.value
+
+
 def hook_potrf(A, ctx: Optional[Context] = None):
     ctx = ctx or default_context()
     A = _f(A)

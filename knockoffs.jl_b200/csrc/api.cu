@@ -1033,6 +1033,21 @@ int kb_test_dgemm_dev(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, in
                  dB, (long)ldb, beta, dC, (long)ldc);
 }
 
+int kb_test_factor_band(kb_ctx* ctx, const double* Lblocks, int64_t p, int32_t m, int32_t* band_out) {
+    if (!ctx) return bad_ctx();
+    if (!Lblocks || !band_out || p < 1 || m < 1) return set_error(ctx, KB_ERR_INVALID, "test_factor_band: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const size_t cnt = (size_t)p * p * (2 * m - 1);
+    double* dLb;
+    KB_TRY(sc.alloc(&dLb, cnt));
+    KB_CUDA(ctx, cudaMemcpyAsync(dLb, Lblocks, sizeof(double) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+    int band = 0;
+    KB_TRY(factor_band_dev(ctx, dLb, (long)p, (int)p, m, &band));
+    *band_out = band;
+    return KB_OK;
+}
+
 int kb_test_potrf(kb_ctx* ctx, const double* A, int64_t p, double* L_out) {
     if (!ctx) return bad_ctx();
     DeviceGuard g(ctx->device);

@@ -88,6 +88,7 @@ struct GemmParams {
     // wave each.
     int batch;
     int last_nseg;
+    int khi_slack;          // SEG_KHI_N segments: B is zero for k >= n + 1 + khi_slack (banded below the diagonal)
     long zA[3], zB[3];
     long zC;
 };
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel
         int kbeg = 0, kend = sg.K;
         if (sg.flags & SEG_KLO_N) kbeg = max(kbeg, n0);
         if (sg.flags & SEG_KLO_M) kbeg = max(kbeg, m0);
-        if (sg.flags & SEG_KHI_N) kend = min(kend, n0 + BN);
+        if (sg.flags & SEG_KHI_N) kend = min(kend, n0 + BN + P.khi_slack);
         if (sg.flags & SEG_KHI_M) kend = min(kend, m0 + BM);
         kbeg = (kbeg / GEMM_BK) * GEMM_BK;
         if (kend <= kbeg) continue;

@@ -327,8 +327,17 @@ int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const do
         if (k == m - 1) break;
         double* Mk = dLb + (size_t)(2 * k + 1) * bstride;
         KB_TRY(trtri_lower(ctx, Lkk, ldo, p, invdiag, W, ld, work));
-        // M_k = B_k * W'   :  B(kk, n) = W(n, kk), zero for kk > n
-        KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, p, 1.0, B, ld, W, ld, 0.0, Mk, ldo, SEG_KHI_N));
+        // M_k = B_k W' = (L_kk L_kk' − S) W' = L_kk − S W'   :  B(kk, n) = W(n, kk), zero for kk > n.  Same p^3 product as
+        // B_k W', but where S W' is structurally zero (S group-block-diagonal, W lower: rows more than g − 1 below the
+        // diagonal) the result is L_kk BIT FOR BIT, which is what lets the sampling stage use two (banded-)triangular
+        // products per copy (sample_plan_create).
+        {
+            GemmParams P{};
+            P.M = p; P.N = p; P.nseg = 1;
+            P.seg[0] = GemmSeg{Sfull, ld, W, ld, p, SEG_KHI_N};
+            P.C = Mk; P.ldc = ldo; P.Cin = Lkk; P.ldcin = ldo; P.alpha = -1.0; P.beta = 1.0;
+            KB_TRY(gemm(ctx, A_MCONTIG, B_NCONTIG, P));
+        }
         // B_{k+1} = B_k − M_k M_k'  (symmetric: lower tiles only -- half the flops -- then mirrored)
         KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, p, -1.0, Mk, ldo, Mk, ldo, 1.0, B, ld, 0, 1, 0));
         KB_TRY(mirror_lower_to_upper(ctx, B, ld, p));
@@ -387,25 +396,26 @@ __global__ void suffix_sum_incl_kernel(double* __restrict__ T, long ldt, long ts
         }
     }
 }
-// flag |= 1 if some strictly-lower entry of an M_k differs from the same entry of L_kk (blocks [L_11 | M_1 | L_22 | ...])
-__global__ void factor_structure_kernel(const double* __restrict__ Lb, long ldo, long bstride, int p, int m, int* __restrict__ flag) {
+// band = max over k and over entries i > j with M_k(i,j) != L_kk(i,j) of (i − j)   (blocks [L_11 | M_1 | L_22 | ...]);
+// 0 if the strict lower triangles agree bit for bit.
+__global__ void factor_structure_kernel(const double* __restrict__ Lb, long ldo, long bstride, int p, int m, int* __restrict__ band) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long per = (long)p * p, total = per * (m - 1);
-    int bad = 0;
+    int bw = 0;
     for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int k = (int)(idx / per);
         const long e = idx % per;
         const int i = (int)(e % p), j = (int)(e / p);
         if (i > j) {
             const double l = Lb[(size_t)(2 * k) * bstride + i + (long)j * ldo], mk = Lb[(size_t)(2 * k + 1) * bstride + i + (long)j * ldo];
-            if (!(l == mk)) bad = 1;
+            if (!(l == mk)) bw = max(bw, i - j);
         }
     }
-    if (bad) atomicOr(flag, 1);
+    if (bw) atomicMax(band, bw);
 }
-// N_k = triu(M_k) − diag(L_kk)   (upper triangular; strict lower zero)
-__global__ void factor_upper_part_kernel(const double* __restrict__ Lb, long ldo, long bstride, int p, int m, double* __restrict__ N,
-                                         long ldn) {
+// N_k = M_k − L_kk on and above the band (i <= j + band), zero below it
+__global__ void factor_upper_part_kernel(const double* __restrict__ Lb, long ldo, long bstride, int p, int m, int band,
+                                         double* __restrict__ N, long ldn) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long per = (long)p * p, total = per * (m - 1);
     for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -413,12 +423,28 @@ __global__ void factor_upper_part_kernel(const double* __restrict__ Lb, long ldo
         const long e = idx % per;
         const int i = (int)(e % p), j = (int)(e / p);
         double v = 0.0;
-        if (i <= j) {
+        if (i <= j + band) {
             v = Lb[(size_t)(2 * k + 1) * bstride + i + (long)j * ldo];
-            if (i == j) v -= Lb[(size_t)(2 * k) * bstride + i + (long)j * ldo];
+            if (i >= j) v -= Lb[(size_t)(2 * k) * bstride + i + (long)j * ldo];
         }
         N[(size_t)k * ldn * p + i + (long)j * ldn] = v;
     }
+}
+
+int factor_band_dev(kb_ctx* ctx, const double* dLb, long ldo, int p, int m, int* band_out) {
+    *band_out = 0;
+    if (m <= 1) return KB_OK;
+    Scope sc(ctx);
+    int* dflag;
+    KB_TRY(sc.alloc(&dflag, 4));
+    KB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
+    factor_structure_kernel<<<ew_grid2(ctx, (long)p * p * (m - 1)), 256, 0, ctx->stream>>>(dLb, ldo, (long)ldo * p, p, m, dflag);
+    ctx->launches++;
+    int hband = 1 << 30;
+    KB_CUDA(ctx, cudaMemcpyAsync(&hband, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *band_out = hband <= 64 ? ((hband + 15) / 16) * 16 : -1;
+    return KB_OK;
 }
 
 int sample_plan_create(kb_ctx* ctx, Scope& sc, int p, int m, const double* dmu, const double* dSiS, const double* dLb,
@@ -438,22 +464,19 @@ int sample_plan_create(kb_ctx* ctx, Scope& sc, int p, int m, const double* dmu, 
         // Detected here, so kb_sample also takes the short form for factor blocks passed in by the caller;
         // anything else (dense S of the group path) keeps the general form.
         static const bool allow = [] { const char* e = getenv("KB_SAMPLE_STRUCTURED"); return !(e && e[0] == '0'); }();
-        int* dflag;
-        KB_TRY(sc.alloc(&dflag, 4));
-        KB_CUDA(ctx, cudaMemsetAsync(dflag, 0, sizeof(int), ctx->stream));
         const size_t bstride = (size_t)ldo * p;
-        factor_structure_kernel<<<ew_grid2(ctx, (long)p * p * (m - 1)), 256, 0, ctx->stream>>>(dLb, ldo, (long)bstride, p, m, dflag);
-        ctx->launches++;
-        int hflag = 1;
-        KB_CUDA(ctx, cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        plan->structured = allow && (hflag == 0);
+        // group blocks (contiguous groups of size g): M_k = L_kk − S inv(L_kk)' differs from L_kk at most g − 1 rows
+        // below the diagonal; a band of up to 64 rows still leaves the second product (almost) triangular
+        int band = -1;
+        KB_TRY(factor_band_dev(ctx, dLb, ldo, p, m, &band));
+        plan->structured = allow && band >= 0;
+        plan->band = plan->structured ? band : 0;
         KB_TRY(sc.alloc(&plan->Mu, (size_t)plan->chunk * p));
         KB_TRY(sc.alloc(&plan->T, (size_t)plan->chunk * p * (plan->structured ? m : m - 1)));
         if (plan->structured) {
             KB_TRY(sc.alloc(&plan->N, (size_t)plan->ld * p * (m - 1)));
             factor_upper_part_kernel<<<ew_grid2(ctx, (long)p * p * (m - 1)), 256, 0, ctx->stream>>>(dLb, ldo, (long)bstride, p, m,
-                                                                                                  plan->N, plan->ld);
+                                                                                                  plan->band, plan->N, plan->ld);
             ctx->launches++;
         }
     }
@@ -510,7 +533,7 @@ int sample_chunk(kb_ctx* ctx, const SamplePlan& pl, const double* Xc, long rows,
         P.seg[0] = GemmSeg{pl.T, pl.chunk, pl.dLb, pl.ldo, p, SEG_KLO_N};                       // S_k L_kk
         P.seg[1] = GemmSeg{pl.T + tstride, pl.chunk, pl.N, pl.ld, p, SEG_KHI_N};                // S_{k+1} N_k
         P.nseg = 2;
-        P.batch = m; P.last_nseg = 1;
+        P.batch = m; P.last_nseg = 1; P.khi_slack = pl.band;
         P.zA[0] = (long)tstride; P.zB[0] = 2 * (long)bstride;
         P.zA[1] = (long)tstride; P.zB[1] = (long)pl.ld * p;
         P.zC = (long)p * ldxko;

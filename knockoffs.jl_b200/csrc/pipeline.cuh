@@ -30,7 +30,9 @@ struct SamplePlan {
     double* bias = nullptr;    // μ'ΣinvS
     double* Mu = nullptr;      // m > 1: X − (X .− μ')ΣinvS of the current chunk
     double* T = nullptr;       // m > 1: suffix sums of the Z blocks (m − 1 exclusive ones, or m inclusive ones if structured)
-    bool structured = false;   // every M_k = L_kk + (upper triangular N_k): copies cost 2 n p² instead of 3 n p²
+    bool structured = false;   // every M_k = L_kk + N_k with N_k upper triangular up to a narrow band below the diagonal:
+                               // copies cost 2 n p² instead of 3 n p²
+    int band = 0;              // rows below the diagonal where N_k may be non-zero (0 for Diagonal(s); g − 1 for group blocks)
     double* N = nullptr;       // structured: N_k = triu(M_k) − diag(L_kk), m − 1 blocks of ld x p
     double* Zbuf = nullptr;    // device-generated Z of the current chunk (chunk x m p)
     const double* dLb = nullptr;
@@ -46,6 +48,9 @@ int sample_chunk(kb_ctx* ctx, const SamplePlan& plan, const double* Xc, long row
 int sample_dev(kb_ctx* ctx, const double* dX, long n, long ldx, int p, const double* dmu, const double* dSiS,
                const double* dLb, long ldo, int m, const double* dZ, long ldz, uint64_t seed, int64_t row_offset,
                double* dXko, long ldxko);
+
+// band of the factor blocks' structure as sample_plan_create detects it (device blocks, ld ldo): -1 = general form
+int factor_band_dev(kb_ctx* ctx, const double* dLb, long ldo, int p, int m, int* band_out);
 
 int randn_dev(kb_ctx* ctx, uint64_t seed, int64_t row_offset, long n, long ncols, long col0, double* dZ, long ldz);
 

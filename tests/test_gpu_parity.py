@@ -187,6 +187,24 @@ def test_condition_dense_S(kb, ctx):
     assert np.max(np.abs(got - want)) < XKO_TOL
 
 
+def test_factor_structure_is_detected(kb, ctx):
+    """The sampling stage's short form (two triangular products per copy) rests on M_k = L_kk + N_k with N_k upper
+    triangular (Diagonal(s)) or banded below the diagonal (contiguous group blocks); anything else takes the general form."""
+    p, m = 120, 3
+    g = np.repeat(np.arange(p // 5), 5)
+    Sigma = np.asfortranarray(ko.simulate_block_covariance(g, 0.6, 0.3))
+    _, Lb = kb.cond_factor(Sigma, np.full(p, 0.3), m=m, ctx=ctx)
+    assert kb.hook_factor_band(Lb, ctx=ctx) == 0
+    S = np.where(g[:, None] == g[None, :], Sigma, 0.0) * 0.4
+    _, Lg = kb.cond_factor(Sigma, S, m=m, ctx=ctx)
+    assert kb.hook_factor_band(Lg, ctx=ctx) == 16                  # g − 1 = 4 rows below the diagonal, rounded up to 16
+    perm = np.random.default_rng(0).permutation(p)                 # scattered groups: no band
+    _, Lp = kb.cond_factor(np.asfortranarray(Sigma[np.ix_(perm, perm)]), np.asfortranarray(S[np.ix_(perm, perm)]), m=m, ctx=ctx)
+    assert kb.hook_factor_band(Lp, ctx=ctx) == -1
+    want = ko.cond_factor(Sigma, S, m)[1]
+    assert np.max(np.abs(kb.dense_factor_from_blocks(Lg) - want)) / np.max(np.abs(want)) < 1e-8
+
+
 def test_modelX_one_shot_config1(kb, ctx):
     """BASELINE config 1 end to end through kb_modelx_gaussian_knockoffs with Z injected."""
     p, n = 500, 1000
