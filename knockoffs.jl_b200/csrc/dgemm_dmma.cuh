@@ -211,6 +211,58 @@ __device__ __forceinline__ void gemm_load_stage(const GemmSeg& sg, int M, int N,
     }
 }
 
+
+// Interior-tile fast path of the stage loader (VEC layouts, tile fully inside M x N, k-tile fully inside the segment's
+// k-range): every 16-byte chunk of a thread sits a fixed stride behind the previous one, so the whole stage is 8
+// unpredicated LDGSTS from two running pointers -- the general loader above spends ~180 integer instructions per
+// k-tile on index / bounds arithmetic (SASS of r01e), which a microbenchmark of the same LDS + DMMA + barrier loop
+// without global loads (tests/ub_dmma_smem.cu: 35.3 TFLOP/s) showed to be where the kernel loses against cuBLAS.
+template <class Cfg, int AL, int BL>
+struct FastLoad {
+    const double* a;      // this thread's first A chunk of the current k-tile
+    const double* b;
+    long a_it, b_it;      // element stride between a thread's consecutive chunks
+    long a_kt, b_kt;      // element stride between consecutive k-tiles
+    int sa, sb;           // shared-memory offsets (doubles) of the first chunks
+    static constexpr int ITA = (Cfg::BM * GEMM_BK / 2) / Cfg::THREADS, ITB = (Cfg::BN * GEMM_BK / 2) / Cfg::THREADS;
+    static constexpr int SA_IT = (AL == A_MCONTIG) ? (Cfg::THREADS / (Cfg::BM / 2)) * Cfg::PADM : (Cfg::THREADS / (GEMM_BK / 2)) * GEMM_PADK;
+    static constexpr int SB_IT = (BL == B_KCONTIG) ? (Cfg::THREADS / (GEMM_BK / 2)) * GEMM_PADK : (Cfg::THREADS / (Cfg::BN / 2)) * Cfg::PADN;
+    static constexpr bool OK = (Cfg::THREADS % (Cfg::BM / 2) == 0) && (Cfg::THREADS % (Cfg::BN / 2) == 0) && (Cfg::THREADS % (GEMM_BK / 2) == 0);
+    __device__ __forceinline__ void init(const GemmSeg& sg, int m0, int n0, int k0, int tid) {
+        if (AL == A_MCONTIG) {
+            const int k = tid / (Cfg::BM / 2), m = (tid % (Cfg::BM / 2)) * 2;
+            a = sg.A + (long)(m0 + m) + (long)(k0 + k) * sg.lda;
+            a_it = (long)(Cfg::THREADS / (Cfg::BM / 2)) * sg.lda; a_kt = (long)GEMM_BK * sg.lda;
+            sa = k * Cfg::PADM + m;
+        } else {
+            const int m = tid / (GEMM_BK / 2), k = (tid % (GEMM_BK / 2)) * 2;
+            a = sg.A + (long)(k0 + k) + (long)(m0 + m) * sg.lda;
+            a_it = (long)(Cfg::THREADS / (GEMM_BK / 2)) * sg.lda; a_kt = GEMM_BK;
+            sa = m * GEMM_PADK + k;
+        }
+        if (BL == B_KCONTIG) {
+            const int n = tid / (GEMM_BK / 2), k = (tid % (GEMM_BK / 2)) * 2;
+            b = sg.B + (long)(k0 + k) + (long)(n0 + n) * sg.ldb;
+            b_it = (long)(Cfg::THREADS / (GEMM_BK / 2)) * sg.ldb; b_kt = GEMM_BK;
+            sb = n * GEMM_PADK + k;
+        } else {
+            const int k = tid / (Cfg::BN / 2), n = (tid % (Cfg::BN / 2)) * 2;
+            b = sg.B + (long)(n0 + n) + (long)(k0 + k) * sg.ldb;
+            b_it = (long)(Cfg::THREADS / (Cfg::BN / 2)) * sg.ldb; b_kt = (long)GEMM_BK * sg.ldb;
+            sb = k * Cfg::PADN + n;
+        }
+    }
+    // loads k-tile number `kt` (relative to the k0 given to init) into the stage buffers
+    __device__ __forceinline__ void load(int kt, double* As, double* Bs) const {
+        const double* pa = a + (long)kt * a_kt;
+        const double* pb = b + (long)kt * b_kt;
+#pragma unroll
+        for (int it = 0; it < ITA; ++it) cp_async16(As + sa + it * SA_IT, pa + it * a_it, 16);
+#pragma unroll
+        for (int it = 0; it < ITB; ++it) cp_async16(Bs + sb + it * SB_IT, pb + it * b_it, 16);
+    }
+};
+
 template <class Cfg, int AL, int BL, bool VEC>
 __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel(const GemmParams P) {
     extern __shared__ __align__(16) double gemm_smem[];
@@ -285,13 +337,20 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel
         const int nkt = (kend - kbeg + GEMM_BK - 1) / GEMM_BK;
 
         __syncthreads();   // previous segment's readers are done with the stage buffers
+        // interior tiles take the unpredicated fast loader for every k-tile that lies fully inside [kbeg, kend)
+        FastLoad<Cfg, AL, BL> fl;
+        const bool fast = VEC && FastLoad<Cfg, AL, BL>::OK && (m0 + BM <= P.M) && (n0 + BN <= P.N);
+        const int nfull = fast ? (kend - kbeg) / GEMM_BK : 0;      // k-tiles [0, nfull) are complete
+        if (fast) fl.init(sg, m0, n0, kbeg, tid);
+        auto load_tile = [&](int t) {
+            double* As_ = gemm_smem + (size_t)(t % GEMM_STAGES) * Cfg::STAGE;
+            if (t < nfull) fl.load(t, As_, As_ + Cfg::A_TILE);
+            else gemm_load_stage<Cfg, AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + t * GEMM_BK, kend, As_, As_ + Cfg::A_TILE, tid);
+        };
         // prologue
 #pragma unroll
         for (int st = 0; st < GEMM_STAGES - 1; ++st) {
-            if (st < nkt)
-                gemm_load_stage<Cfg, AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + st * GEMM_BK, kend,
-                                                  gemm_smem + (size_t)st * Cfg::STAGE,
-                                                  gemm_smem + (size_t)st * Cfg::STAGE + Cfg::A_TILE, tid);
+            if (st < nkt) load_tile(st);
             cp_async_commit();
         }
         for (int kt = 0; kt < nkt; ++kt) {
@@ -300,12 +359,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MIN_CTAS) dgemm_dmma_kernel
             // prefetch tile kt + STAGES - 1 into the buffer consumed at iteration kt - 1
             {
                 int nk = kt + GEMM_STAGES - 1;
-                if (nk < nkt) {
-                    int st = nk % GEMM_STAGES;
-                    gemm_load_stage<Cfg, AL, BL, VEC>(sg, P.M, P.N, m0, n0, kbeg + nk * GEMM_BK, kend,
-                                                      gemm_smem + (size_t)st * Cfg::STAGE,
-                                                      gemm_smem + (size_t)st * Cfg::STAGE + Cfg::A_TILE, tid);
-                }
+                if (nk < nkt) load_tile(nk);
                 cp_async_commit();
             }
             const double* As = gemm_smem + (size_t)(kt % GEMM_STAGES) * Cfg::STAGE;
