@@ -43,7 +43,7 @@ function check(c::Context, rc::Integer)
 end
 
 opts(; niter::Int=100, tol=1e-6, λmin=1e-6, λ=0.5, μ=0.8, robust::Bool=false, verbose::Bool=false) =
-    SolveOpts(niter, tol, λmin, λ, μ, robust, verbose, 0, 1)
+    SolveOpts(niter, tol, λmin, λ, μ, robust, verbose, 0, -1)     # mode = KB_MODE_AUTO, refresh_every = -1 (library default)
 
 "Drop-in for `solve_s(Σ::Symmetric, method; m, kwargs...)` (src/utilities.jl:27-51) for :mvr, :maxent, :sdp_ccd, :equi."
 function solve_s(Σ::Symmetric{Float64}, method::Union{Symbol,String}; m::Number=1, s_init=nothing, kwargs...)

@@ -549,7 +549,7 @@ def fit_marginal(y, X_or_ko, mu=None, Sigma=None, method="maxent", m=1, fdrs=DEF
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     fd = np.ascontiguousarray(fdrs, dtype=np.float64)
     plus = _filter_flag(filter_method)
-    if isinstance(X_or_ko, (GaussianKnockoff, GaussianGroupKnockoff)):
+    if hasattr(X_or_ko, "Xko") and hasattr(X_or_ko, "X"):        # any knockoff struct (src/struct.jl)
         ko = X_or_ko
     elif groups is not None:
         if mu is None:

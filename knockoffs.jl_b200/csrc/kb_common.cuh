@@ -31,10 +31,6 @@ struct kb_ctx {
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string last_error;
-    std::vector<void*> allocs;           // everything cudaMalloc'ed through ws_alloc (freed per call)
-    // pinned staging for host<->device pipelines
-    void* pinned[4] = {nullptr, nullptr, nullptr, nullptr};
-    size_t pinned_cap[4] = {0, 0, 0, 0};
     unsigned long long launches = 0;     // kernels launched by this library since creation
     long sample_chunk_rows = 0;          // 0 = default (4096)
     size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
@@ -94,7 +90,6 @@ struct Scope {
                 cudaGetLastError();
                 for (auto& f : ctx->pool_free) cudaFree(f.ptr);
                 ctx->pool_bytes = 0;
-                for (auto& f : ctx->pool_free) (void)f;
                 ctx->pool_free.clear();
                 e = cudaMalloc(&blk.ptr, want);
             }
