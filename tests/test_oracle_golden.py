@@ -104,3 +104,17 @@ def test_condition_block_structure_equals_dense_factor():
     X = rng.standard_normal((20, p)); Z = rng.standard_normal((20, m * p))
     Xko = ko.condition(X, np.zeros(p), Sigma, s, m=m, Z=Z)
     assert Xko.shape == (20, m * p)
+
+
+def test_golden_fixture_matches_its_sources():
+    """tests/golden/make_golden.py re-reads the cited lines of the reference checkout (build container only; the GPU box has
+    no /root/reference) and checks every number of the fixture against them."""
+    import os
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    r = subprocess.run([sys.executable, script, ref], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
