@@ -61,6 +61,8 @@ typedef struct {
     int32_t mode;        /* KB_MODE_* */
     int32_t refresh_every; /* rebuild the device-resident inverse from the current diagonal every k sweeps
                               (-1 = default: 1 in KB_MODE_STREAM, 4 in KB_MODE_BLOCK; 0 = never) */
+    int32_t objective;   /* 1 (default): evaluate kb_solve_info.objective at exit (one extra factorisation of κΣ − S);
+                            0: skip it */
 } kb_solve_opts;
 
 typedef struct {
@@ -73,9 +75,13 @@ typedef struct {
     double init_ms;               /* device time of the initial factorisation */
     double ref_bytes;             /* algorithmic bytes of the reference's steps actually taken */
     double touched_bytes;         /* bytes this implementation's update passes read + wrote */
-    double flops;                 /* FP64 flops of tensor-core stages */
+    double flops;                 /* FP64 flops the call issued to the tensor-core (DMMA) GEMM kernel: inverse builds,
+                                     eigmin probes, blocked sweeps, objective */
     double updates;               /* coordinates whose |δ| >= 1e-15 (factor updates performed) */
-    double objective;             /* MVR trace / ME logdet / SDP sum(s) of the returned s (on the correlation scale) */
+    double objective;             /* objective at the returned s, on the correlation scale Σcor the solver works in, with the
+                                     definitions of group_block_objective (group.jl:24,27) / utilities.jl:79:
+                                     :mvr m²·Σ1/s_j + tr((κΣcor − S)⁻¹); :maxent logdet(κΣcor − S + 1e-8 I) + m·Σlog(s_j + 1e-8);
+                                     :sdp_ccd Σ s_j.  NaN when κΣcor − S is not positive definite; 0 when opts.objective == 0 */
 } kb_solve_info;
 
 /* Keyword arguments of solve_group_{max_entropy,mvr,sdp}_hybrid (group.jl:870-881, 951-962, 1057-1068). */

@@ -13,7 +13,7 @@ const METHODS = Dict(:mvr => 0, :maxent => 1, :sdp_ccd => 2, :equi => 3)
 
 struct SolveOpts          # kb_solve_opts
     niter::Int32; tol::Float64; lambda_min::Float64; sdp_lambda::Float64; sdp_mu::Float64
-    robust::Int32; verbose::Int32; mode::Int32; refresh_every::Int32
+    robust::Int32; verbose::Int32; mode::Int32; refresh_every::Int32; objective::Int32
 end
 struct SolveInfo          # kb_solve_info
     sweeps::Int32; status::Int32; mode::Int32; launches::Int32
@@ -43,7 +43,7 @@ function check(c::Context, rc::Integer)
 end
 
 opts(; niter::Int=100, tol=1e-6, λmin=1e-6, λ=0.5, μ=0.8, robust::Bool=false, verbose::Bool=false) =
-    SolveOpts(niter, tol, λmin, λ, μ, robust, verbose, 0, -1)     # mode = KB_MODE_AUTO, refresh_every = -1 (library default)
+    SolveOpts(niter, tol, λmin, λ, μ, robust, verbose, 0, -1, 1)  # mode = KB_MODE_AUTO, refresh_every = -1 (library default), objective on
 
 "Drop-in for `solve_s(Σ::Symmetric, method; m, kwargs...)` (src/utilities.jl:27-51) for :mvr, :maxent, :sdp_ccd, :equi."
 function solve_s(Σ::Symmetric{Float64}, method::Union{Symbol,String}; m::Number=1, s_init=nothing, kwargs...)

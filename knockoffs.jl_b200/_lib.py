@@ -21,7 +21,7 @@ c_double_p = C.POINTER(C.c_double)
 class SolveOpts(C.Structure):
     _fields_ = [("niter", C.c_int32), ("tol", C.c_double), ("lambda_min", C.c_double), ("sdp_lambda", C.c_double),
                 ("sdp_mu", C.c_double), ("robust", C.c_int32), ("verbose", C.c_int32), ("mode", C.c_int32),
-                ("refresh_every", C.c_int32)]
+                ("refresh_every", C.c_int32), ("objective", C.c_int32)]
 
 
 class SolveInfo(C.Structure):

@@ -89,7 +89,7 @@ def _method_id(method) -> int:
 
 
 def make_opts(niter=100, tol=1e-6, λmin=None, lambda_min=1e-6, λ=None, sdp_lambda=0.5, μ=None, sdp_mu=0.8,
-              robust=False, verbose=False, refresh_every=-1, mode="auto", **unknown) -> SolveOpts:
+              robust=False, verbose=False, refresh_every=-1, mode="auto", objective=True, **unknown) -> SolveOpts:
     """Keyword arguments of solve_MVR / solve_max_entropy / solve_sdp_ccd (utilities.jl:124-133, 221-230, 291-300)."""
     if unknown:
         raise TypeError(f"unsupported keyword argument(s): {sorted(unknown)}")   # Julia: MethodError
@@ -103,6 +103,7 @@ def make_opts(niter=100, tol=1e-6, λmin=None, lambda_min=1e-6, λ=None, sdp_lam
     o.robust = int(bool(robust))
     o.verbose = int(bool(verbose))
     o.refresh_every = int(refresh_every)
+    o.objective = int(bool(objective))
     o.mode = {"auto": 0, "stream": 1, "block": 2}[mode] if isinstance(mode, str) else int(mode)
     return o
 
@@ -111,7 +112,8 @@ def _info_dict(info: SolveInfo, method: str) -> dict:
     n = max(0, min(info.sweeps, _lib.KB_MAX_TRACE))
     return dict(sweeps=info.sweeps, status=info.status, launches=info.launches, trace=list(info.trace[:n]),
                 solve_ms=info.solve_ms, init_ms=info.init_ms, ref_bytes=info.ref_bytes,
-                touched_bytes=info.touched_bytes, updates=info.updates, method=method,
+                touched_bytes=info.touched_bytes, updates=info.updates, flops=info.flops, objective=info.objective,
+                method=method,
                 mode={1: "stream", 2: "block"}.get(info.mode, "none"))
 
 

@@ -33,6 +33,8 @@ constexpr int MAX_NIN = 8;             // inner blocks per outer block: at most 
 constexpr int SLAB = 128;              // rows per gather / Gram CTA
 constexpr int GPITCH = SLAB + 1;       // shared-memory pitch of one panel column
 constexpr int BLK_THREADS = 256;
+constexpr int GRAM_SLOTS = 5;                    // double2 rows per thread and pass of the direct column-norm recompute
+constexpr double GRAM_RECOMPUTE_RATIO = 2e-6;    // recompute G_jj when it is below this fraction of its error scale
 static_assert(BW == 64 && SLOT_ROWS == 64, "ownership maps below assume 64-wide blocks");
 
 // Thread t of the 256 owns the 4 x 4 entries (tr + 16a, tc + 16b), tr = t & 15, tc = t >> 4, of every 64 x 64
@@ -126,6 +128,8 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
     constexpr bool MVR = (METHOD == KB_METHOD_MVR);
     __shared__ double wbuf[2][BW], gbuf[2][BW], tbuf[2][BW];
     __shared__ double s_s[BW], s_a[BW], s_k[BW];
+    __shared__ double gsc[BW];      // MVR: magnitude of everything summed into G_jj so far (its rounding-error scale)
+    __shared__ double red[BLK_THREADS / 32];
     const int tid = threadIdx.x;
     const int tr = tid & 15, tc = tid >> 4;
     const long ld = P.ld;
@@ -147,6 +151,10 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
 #pragma unroll
                 for (int b = 0; b < 4; ++b) G[a][b] += gp[(a * 4 + b) * BLK_THREADS + tid];
         }
+    }
+    if (MVR && tr == tc) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) gsc[tr + 16 * a] = fabs(G[a][a]);
     }
     if (tid < BW) {
         const bool in = tid < bw;
@@ -176,7 +184,36 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
             }
             __syncthreads();
             const double Mjj = wbuf[pb][j];
-            const double ss = MVR ? gbuf[pb][j] : 0.0;
+            double ss = MVR ? gbuf[pb][j] : 0.0;
+            if (MVR && ss < GRAM_RECOMPUTE_RATIO * gsc[j]) {
+                // The recurrence for G_jj = ‖M[:, j]‖² has cancelled more than ~6 digits (first sweep from the equi start:
+                // A is within λmin of singular, the columns of M shrink from ~1/λmin to O(1) as a near-null group is
+                // eliminated): recompute it directly from the data, ‖P₀ t_j‖², where only ~6 digits cancel.  The branch is
+                // uniform (every thread reads the same shared values); ≈ one pass of this CTA over the p x (j+1) panel.
+                double acc = 0.0;
+                const double* tj = tbuf[pb];
+                for (long base = 2 * tid; base < ld; base += 2L * BLK_THREADS * GRAM_SLOTS) {
+                    double2 u[GRAM_SLOTS];
+#pragma unroll
+                    for (int i = 0; i < GRAM_SLOTS; ++i) u[i] = make_double2(0.0, 0.0);
+                    const double* col = Pk + base;
+#pragma unroll 2
+                    for (int k = 0; k <= j; ++k, col += ld) {
+                        const double t = tj[k];
+#pragma unroll
+                        for (int i = 0; i < GRAM_SLOTS; ++i) {
+                            if (base + 2L * BLK_THREADS * i < ld) {
+                                const double2 v = *reinterpret_cast<const double2*>(col + 2 * BLK_THREADS * i);
+                                u[i].x = fma(v.x, t, u[i].x);
+                                u[i].y = fma(v.y, t, u[i].y);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < GRAM_SLOTS; ++i) acc = fma(u[i].x, u[i].x, fma(u[i].y, u[i].y, acc));
+                }
+                ss = block_sum<BLK_THREADS / 32>(acc, red, tid);
+            }
             const double sj = s_s[j], ajj = s_a[j];
             double delta, s_new, cfac;
             bool skip;
@@ -211,6 +248,8 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
                             gc[a] = gbuf[pb][tc + 16 * a];
                         }
                         wr[a] = cfac * w;
+                        if (MVR && tr == tc && tr + 16 * a > j)        // |terms| added to G_ii below (i > j only: gsc[j] is being read)
+                            gsc[tr + 16 * a] += fabs(cfac) * 2.0 * fabs(gbuf[pb][tr + 16 * a] * w) + cfac * cfac * ss * w * w;
                     }
                     if (a <= bq) tv[a] = cfac * tbuf[pb][tr + 16 * a];
                 }

@@ -32,6 +32,7 @@ struct kb_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string last_error;
     unsigned long long launches = 0;     // kernels launched by this library since creation
+    double flops = 0.0;                  // FP64 flops issued to the DMMA GEMM kernel since creation (clipped k-ranges counted as clipped)
     long sample_chunk_rows = 0;          // 0 = default (4096)
     size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
     size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize

@@ -62,6 +62,12 @@ int gemm(kb_ctx* ctx, int AL, int BL, const GemmParams& P) {
     bool vec = true;
     for (int s = 0; s < P.nseg; ++s) {
         const GemmSeg& g = P.seg[s];
+        // executed flops: a triangular (k-clipped) operand or a lower-tiles-only output halves the work
+        double f = 2.0 * (double)P.M * (double)P.N * (double)g.K;
+        if (g.flags) f *= 0.5;
+        if (P.tile_mode == 1) f *= 0.5;
+        const int nb = P.batch > 1 ? P.batch : 1;
+        ctx->flops += f * ((P.batch > 1 && P.last_nseg > 0 && s >= P.last_nseg) ? nb - 1 : nb);
         if (((uintptr_t)g.A & 15) || ((uintptr_t)g.B & 15) || (g.lda & 1) || (g.ldb & 1)) vec = false;
         if (P.batch > 1 && ((P.zA[s] & 1) || (P.zB[s] & 1))) vec = false;
     }

@@ -163,6 +163,29 @@ __global__ void quadform_lower_kernel(const double* __restrict__ B, long ld, int
     if (lane == 0) colq[k] = y[k] * (b[k] * y[k] + 2.0 * a);
 }
 
+// Reductions behind the objective values (deterministic: fixed per-block partials, summed on the host).
+// mode 0: part[b] = Σ x_i² over `count` contiguous doubles;  mode 1: part[b] = Σ_j log(x[j * stride]) (j < count);
+// mode 2: part[b] = Σ_j log(x_j + shift);  mode 3: part[b] = Σ_j 1 / x_j;  mode 4: part[b] = Σ_j x_j.
+__global__ void objective_reduce_kernel(const double* __restrict__ x, long count, long stride, double shift, int mode,
+                                        double* __restrict__ part) {
+    __shared__ double red[256];
+    double a = 0.0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long)gridDim.x * blockDim.x) {
+        if (mode == 0) { const double v = x[i]; a = fma(v, v, a); }
+        else if (mode == 1) a += log(x[i * stride]);
+        else if (mode == 2) a += log(x[i] + shift);
+        else if (mode == 3) a += 1.0 / x[i];
+        else a += x[i];
+    }
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
 static inline int ewg(kb_ctx* ctx, long total) {
     long g = (total + 255) / 256, cap = (long)ctx->num_sms * 16;
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -395,7 +418,7 @@ int eigmin_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, double* lambd
 
 void default_solve_opts(kb_solve_opts* o) {
     o->niter = 100; o->tol = 1e-6; o->lambda_min = 1e-6; o->sdp_lambda = 0.5; o->sdp_mu = 0.8;
-    o->robust = 0; o->verbose = 0; o->mode = KB_MODE_AUTO; o->refresh_every = -1;
+    o->robust = 0; o->verbose = 0; o->mode = KB_MODE_AUTO; o->refresh_every = -1; o->objective = 1;
 }
 
 // dSigma: p x p, leading dimension lds, upper triangle trusted.  d_s_init may be NULL.  d_s_out: p.
@@ -422,6 +445,7 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
     }
     if (opts.niter < 0) return set_error(ctx, KB_ERR_INVALID, "niter must be >= 0");
     const unsigned long long launches0 = ctx->launches;
+    const double flops0 = ctx->flops;
     const double kappa = (m + 1.0) / m;
     const long ld = ccd_stream_ld(p);
     Scope sc(ctx);
@@ -618,6 +642,53 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
         }
         if (status == KB_ERR_NOT_PD) set_error(ctx, status, "PosDefException: rank-1 downdate left the positive definite cone.");
         else if (status == KB_ERR_NAN) set_error(ctx, status, "delta_j is Inf/NaN, aborting.");
+        // ---- objective of the returned s on the correlation scale (north-star "MVR trace / ME logdet / SDP sum"; the
+        //      single-knockoff solvers of the reference never evaluate one, so the definitions are group_block_objective's,
+        //      group.jl:24 (ME, with its 1e-8 shifts) and :27 (MVR), and sum(s) for sdp_ccd, utilities.jl:79).
+        //      Evaluated from a FRESH factorisation of κΣ − S (not from the Sherman–Morrison-updated inverse, which
+        //      also carries the λmin shift): one Cholesky (ME) plus one triangular inverse (MVR).  NaN if κΣ − S is not PD.
+        if (info && status == KB_OK && opts.objective) {
+            double* part;
+            KB_TRY(sc.alloc(&part, 256));
+            auto reduce = [&](const double* x, long count, long stride, double shift_, int rmode, double* out) -> int {
+                objective_reduce_kernel<<<256, 256, 0, ctx->stream>>>(x, count, stride, shift_, rmode, part);
+                ctx->launches++;
+                double h[256];
+                KB_CUDA(ctx, cudaMemcpyAsync(h, part, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+                KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                long double t = 0.0L;
+                for (int i = 0; i < 256; ++i) t += h[i];
+                *out = (double)t;
+                return KB_OK;
+            };
+            double obj = NAN;
+            if (method == KB_METHOD_SDP_CCD) {
+                KB_TRY(reduce(s, p, 1, 0.0, 4, &obj));
+            } else {
+                const double oshift = (method == KB_METHOD_MAXENT) ? 1e-8 : 0.0;
+                build_A_lower_kernel<<<ewg(ctx, (long)ld * p), 256, 0, ctx->stream>>>(Cor, ld, p, kappa, s, oshift, A, nullptr, adiag, 1);
+                ctx->launches++;
+                KB_CUDA(ctx, cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
+                KB_TRY(potrf_lower(ctx, A, ld, p, invdiag, d_fail));
+                int f = 0;
+                KB_CUDA(ctx, cudaMemcpyAsync(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (f == 0) {
+                    double t1 = 0.0, t2 = 0.0;
+                    if (method == KB_METHOD_MAXENT) {
+                        KB_TRY(reduce(A, p, ld + 1, 0.0, 1, &t1));          // Σ log L_jj
+                        KB_TRY(reduce(s, p, 1, 1e-8, 2, &t2));              // Σ log(s_j + 1e-8)
+                        obj = 2.0 * t1 + m * t2;
+                    } else {
+                        KB_TRY(trtri_lower(ctx, A, ld, p, invdiag, W, ld, work));
+                        KB_TRY(reduce(W, (long)ld * p, 1, 0.0, 0, &t1));    // ‖L⁻¹‖_F² = tr((κΣ − S)⁻¹)
+                        KB_TRY(reduce(s, p, 1, 0.0, 3, &t2));               // Σ 1 / s_j
+                        obj = m * m * t2 + t1;
+                    }
+                }
+            }
+            info->objective = obj;
+        }
     }
     // ---- rescale (utilities.jl:49) ----
     if (!iscor) {
@@ -629,6 +700,7 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
     if (info) {
         info->status = status;
         info->launches = (int)(ctx->launches - launches0);
+        info->flops = ctx->flops - flops0;
     }
     return status;
 }

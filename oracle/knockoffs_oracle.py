@@ -294,7 +294,7 @@ def solve_s(Sigma, method, m=1, **kw):
 # --------------------------------------------------------------------------
 # conditional sampling (src/modelX.jl:96-122), Z injected
 # --------------------------------------------------------------------------
-def cond_factor(Sigma, S, m=1):
+def cond_factor(Sigma, S, m=1, lean=False):
     """Returns (SigmaInvS, L) of src/modelX.jl:106-120.  S: vector (Diagonal) or dense matrix.
     L is the *lower* factor of C (m = 1) or of the pm x pm Sigma-tilde (m > 1)."""
     p = Sigma.shape[0]
@@ -306,6 +306,18 @@ def cond_factor(Sigma, S, m=1):
     if m == 1:
         Csym = np.triu(C) + np.triu(C, 1).T              # Symmetric(C)
         return SiS, np.linalg.cholesky(Csym)
+    if lean:
+        # same matrix as below without the 4 pm x pm temporaries (pm = 25000 at BASELINE configs[2]): Symmetric(St)
+        # reads the upper triangle of St, i.e. whole C - S blocks above the block diagonal, their transposes below it,
+        # and the upper triangle of (C - S) + S on it.  Factored in place.
+        B = C - Smat
+        D = B + Smat
+        D = np.triu(D) + np.triu(D, 1).T
+        St = np.empty((m * p, m * p))
+        for k in range(m):
+            for l in range(m):
+                St[k * p:(k + 1) * p, l * p:(l + 1) * p] = D if k == l else (B if k < l else B.T)
+        return SiS, sla.cholesky(St, lower=True, overwrite_a=True, check_finite=False)
     St = np.tile(C - Smat, (m, m))                       # :116
     for k in range(m):
         St[k * p:(k + 1) * p, k * p:(k + 1) * p] += Smat # :117
@@ -313,7 +325,7 @@ def cond_factor(Sigma, S, m=1):
     return SiS, np.linalg.cholesky(St)
 
 
-def condition(X, mu, Sigma, S, m=1, Z=None, rng=None):
+def condition(X, mu, Sigma, S, m=1, Z=None, rng=None, lean=False):
     """src/modelX.jl:96-122 with Z = randn(n, m*p) injected.  Note quirk Q1:
     the noise is Z @ L with L *lower* (literal reference)."""
     n, p = X.shape
@@ -322,7 +334,7 @@ def condition(X, mu, Sigma, S, m=1, Z=None, rng=None):
         raise ValueError(f"m should be 1 or larger but was {m}.")
     if Z is None:
         Z = (rng or np.random.default_rng()).standard_normal((n, m * p))
-    SiS, L = cond_factor(Sigma, S, m)
+    SiS, L = cond_factor(Sigma, S, m, lean=lean)
     mui = X - (X - mu[None, :]) @ SiS
     if m == 1:
         return mui + Z @ L                               # :112

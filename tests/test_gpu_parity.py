@@ -402,6 +402,45 @@ def test_modelX_group_one_shot(kb, ctx):
         kb.modelX_gaussian_group_knockoffs(X, "maxent", groups[:-1], np.zeros(p), Sigma, ctx=ctx)
 
 
+def _objective(Sigma, s, m, method):
+    # definitions of group_block_objective (group.jl:24, :27) and utilities.jl:79 on the correlation scale
+    kap = (m + 1) / m
+    A = kap * Sigma - np.diag(s)
+    if method == "sdp_ccd":
+        return float(np.sum(s))
+    if method == "maxent":
+        return float(np.linalg.slogdet(A + 1e-8 * np.eye(len(s)))[1] + m * np.sum(np.log(s + 1e-8)))
+    return float(m * m * np.sum(1.0 / s) + np.trace(np.linalg.inv(A)))
+
+
+@pytest.mark.parametrize("kind,p,method,m", [("ar1", 500, "mvr", 1), ("ar1", 500, "maxent", 1), ("ar1", 300, "sdp_ccd", 1),
+                                             ("block", 400, "mvr", 5), ("block", 400, "maxent", 5), ("block", 250, "sdp_ccd", 5)])
+@pytest.mark.parametrize("mode", ["block", "stream"])
+def test_single_knockoff_objective_values(kb, ctx, kind, p, method, m, mode):
+    """north_star: 'Objective values (MVR trace / ME logdet / SDP sum) must agree to 1e-8' -- kb_solve_info.objective
+    against the oracle's s pushed through the reference's own objective definitions."""
+    Sigma = _sigma(kind, p)
+    s0 = ko.solve_equi(Sigma, m)
+    want = c_oracle.solve_ccd(Sigma, method, m=m, s_init=s0)
+    got, info = kb.solve_s(Sigma, method, m=m, s_init=s0, ctx=ctx, return_info=True, mode=mode)
+    obj = _objective(Sigma, want["s"], m, method)
+    assert abs(info["objective"] - obj) <= 1e-8 * abs(obj), (info["objective"], obj)
+    assert info["flops"] > 0
+    _, info0 = kb.solve_s(Sigma, method, m=m, s_init=s0, ctx=ctx, return_info=True, mode=mode, objective=False)
+    assert info0["objective"] == 0.0
+
+
+def test_objective_on_covariance_input_uses_correlation_scale(kb, ctx):
+    rng = np.random.default_rng(5)
+    p, m = 120, 2
+    Sigma = toeplitz(p, 0.4)
+    sd = rng.uniform(0.5, 2.0, p)
+    Cov = np.asfortranarray(Sigma * np.outer(sd, sd))
+    s, info = kb.solve_s(Cov, "maxent", m=m, ctx=ctx, return_info=True)
+    obj = _objective(Sigma, s / sd ** 2, m, "maxent")
+    assert abs(info["objective"] - obj) <= 1e-8 * abs(obj)
+
+
 # ---- BASELINE-size cases ---------------------------------------------------------------------------------
 def test_config2_maxent_p2000_matches_oracle(kb, ctx):
     """BASELINE configs[1]: AR(1) rho = 0.5, p = 2000, :maxent, m = 1 -- full solve against the C oracle."""
@@ -433,13 +472,12 @@ def test_config3_full_size_properties(kb, ctx):
     got1 = kb.solve_s(Sigma, "mvr", m=m, s_init=s0, niter=1, mode="stream", ctx=ctx)
     assert rel(got1[:300], want["s"][:300]) < S_RTOL
     # The blocked kernel carries ‖M[:, j]‖² through a 64 x 64 Gram recurrence.  The equi start makes A nearly singular
-    # (4500 eigenvalues at λmin = 1e-6, entries of M ~ 1e6, squared column norms ~ 1e12), so in sweep 1 -- and only
-    # there -- the LAST variable of every 10-block sees its norm fall by ~12 orders of magnitude and inherits
-    # ~1e-4 absolute / ~4e-8 relative error in s.  It is a transient: the inverse is rebuilt after sweep 1 and the
-    # converged solutions of the two kernels agree to rounding (checked next), as they do with the oracle at the
-    # sizes the oracle can finish (test_solve_s_matches_oracle).
+    # (4500 eigenvalues at λmin = 1e-6, entries of M ~ 1e6, squared column norms ~ 1e12), so in sweep 1 the LAST variable
+    # of every 10-block sees its norm fall by ~12 orders of magnitude; ccd_block_seq_kernel detects that cancellation
+    # (running error scale of G_jj) and recomputes the norm directly from the panel, so sweep 1 holds 1e-8 as well.
     got1b = kb.solve_s(Sigma, "mvr", m=m, s_init=s0, niter=1, mode="block", ctx=ctx)
-    assert rel(got1b[:300], want["s"][:300]) < 1e-6
+    assert rel(got1b[:300], want["s"][:300]) < S_RTOL
+    assert rel(got1b, got1) < S_RTOL                       # the whole first sweep, blocked vs rank-1 streaming
     s_stream = kb.solve_s(Sigma, "mvr", m=m, s_init=s0, mode="stream", ctx=ctx)
     assert info["mode"] == "block" and rel(s, s_stream) < 1e-10
 
