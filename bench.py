@@ -1,13 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- the model-X Gaussian knockoff hot path on B200 (BASELINE.json metric).
+"""bench.py -- the model-X Gaussian knockoff hot path on B200 (BASELINE.json metric, configs[2]).
 
-A "step" is one pass of the hot path over one batch of synthetic input:
-    s = solve_s(Sigma, :mvr; m)  ->  conditional factor  ->  X~ = condition(X, mu, Sigma, diag(s); m)
-on the workload of BASELINE.json configs[2] (block-equicorrelated Sigma, p = 5000, n = 100000 rows per GPU,
-m = 5, :mvr).  `value` = knockoff rows/s with inputs resident in HBM; `e2e` = the same through the
-host-pointer C-ABI call kb_modelx_gaussian_knockoffs with pinned host buffers (H2D of X, D2H of X~
-inside the timed region).  Multi-GPU: rows are sharded (weak scaling: n rows per GPU), the CCD solve is
-replicated on every rank ("replicas only"), no collective on the data path.
+A "step" is one pass of the hot path over one batch of synthetic input, for BOTH methods BASELINE configs[2] names:
+    for method in (:mvr, :sdp_ccd):   s = solve_s(Sigma, method; m)  ->  conditional factor  ->  X~ = condition(X, mu, Sigma, diag(s); m)
+on block-equicorrelated Sigma (blocks of 10, rho = 0.5, gamma = 0.25), p = 5000, n = 100000 rows IN TOTAL, m = 5.
+`value` = knockoff rows/s = (number of methods) * n / step time, inputs resident in HBM.
+`e2e`   = the same through the host-pointer C ABI (kb_solve_s + kb_condition) with pinned HOST buffers: H2D of X and
+          Sigma, D2H of X~ inside the timed region.
+
+Multi-GPU (one process per GPU, NCCL): STRONG scaling by default -- n is fixed, rows are sharded n/N per rank, the
+independent solves (:mvr || :sdp_ccd) run on different ranks (a single CCD solve is sequential: "replicas only"),
+s and the factor blocks are BROADCAST over NVLink (NCCL), sampling needs no collective (counter-based RNG keyed by
+the global row).  `scaling_alt` reports the weak-scaling run (n rows per GPU) next to it.  Three more objects ride
+on the same JSON line: `config5` (row-sharded dosage Gram + ONE NCCL all-reduce of the p x p sums + :maxent +
+sampling), `config4` (group :mvr, LD blocks dealt to ranks, the reduce hook over NCCL) and the CPU baseline.
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
 """
@@ -27,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "knockoff rows/s (solve_s :mvr + conditional factor + sampling, p=5000, m=5)"
+METRIC = "knockoff rows/s (solve_s + conditional factor + sampling, :mvr and :sdp_ccd, p=5000, m=5)"
 UNIT = "rows/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
 # ncu --set full capture (profiles/); None until a capture of this exact configuration exists.
@@ -36,7 +42,6 @@ NCU_TRAFFIC_BYTES = {
     "ccd_stream_kernel": 869.76e9,
     # profiles/r01g_dgemm_dmma_kernel_batched_sampling_ncu_raw.csv: ONE batched launch = all m = 5 copies of one 4096-row
     # chunk (gridDim.z = 5; per copy a lower- and an upper-triangular K = 5000 segment): 6.633 GB read + 0.802 GB written
-    # (algorithmic: ~3.4 GB of operands + 0.82 GB of C; DMMA pipe 93.4 % active, DRAM at 4 % of its bandwidth)
     "dgemm_dmma_kernel": 7.434e9,
 }
 
@@ -48,20 +53,31 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--p", type=int, default=5000)
-    ap.add_argument("--n", type=int, default=100000, help="rows per GPU")
+    ap.add_argument("--n", type=int, default=100000, help="rows in total (strong scaling) / per GPU (weak)")
     ap.add_argument("--m", type=int, default=5)
-    ap.add_argument("--method", default="mvr")
+    ap.add_argument("--methods", default="mvr,sdp_ccd")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true", help="skip the separately timed streaming-kernel sweep")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config4 / config5 / weak-scaling sections")
     ap.add_argument("--chunk", type=int, default=0, help="rows per sampling chunk (0 = library default)")
     ap.add_argument("--refresh-every", type=int, default=-1)
+    ap.add_argument("--c5-rows", type=int, default=500000)
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f"BASELINE configs[2]: block-equicorrelated Sigma (blocks of 10, rho=0.5, gamma=0.25), p={a.p}, "
-            f"n={a.n} rows per GPU, :{a.method}, m={a.m}")
+def methods_of(a):
+    return [x for x in a.methods.split(",") if x]
+
+
+def config_dict(a, world):
+    """The workload description -- IDENTICAL in both arms (no run-dependent keys)."""
+    return {"workload": (f"BASELINE configs[2]: block-equicorrelated Sigma (blocks of 10, rho=0.5, gamma=0.25), p={a.p}, "
+                         f"n={a.n} rows, m={a.m}, methods :{' and :'.join(methods_of(a))}"),
+            "p": a.p, "n": a.n, "m": a.m, "methods": methods_of(a), "n_is": "total rows" if a.scaling == "strong" else "rows per GPU",
+            "l2": "inputs larger than L2 (X 4 GB, 2 GB of factor blocks per method, 200 MB resident inverse rewritten by every "
+                  "rank-256 pass)"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -104,89 +120,133 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle (port of the reference's algorithm) on the host cores, bounded sample
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_step(a, Sigma, sweeps_hint, coords=400, rows=400):
-    """Times a bounded sample of ONE step on the CPU and extrapolates to the full workload.
-    Returns (rows_per_s, detail dict)."""
-    from oracle import c_oracle, knockoffs_oracle as ko
+def host_threads():
+    """Use every host core for the BLAS stages, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+    n = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return n
+
+
+def golden_sweeps(method, p, m):
+    """Sweep counts of the oracle's own FULL solves of this workload (committed fixtures, tests/golden/config_c3_*.npz)."""
+    if p == 5000 and m == 5:
+        path = os.path.join(ROOT, "tests", "golden", f"config_c3_{method}.npz")
+        if os.path.exists(path):
+            z = np.load(path)
+            return int(json.loads(bytes(z["meta"]).decode())["sweeps"])
+    return {"mvr": 5, "maxent": 5, "sdp_ccd": 59}[method]
+
+
+def ccd_stride(steps):
+    """Every k-th coordinate of one whole sweep is timed; k grows with --steps so that the whole reference run stays within
+    a few minutes (one full p = 5000 sweep is ~75 s of one core per method)."""
+    return int(min(160, max(16, 8 * steps)))
+
+
+SAMPLE_ROWS = 4096       # one full chunk of rows for the sampling GEMMs
+
+
+def cpu_reference_step(a, Sigma, sweeps, stride):
+    """Times a bounded sample of ONE step (all methods) on the CPU and extrapolates to the full workload.
+    Returns (rows_per_s, detail dict).  What is measured and how it is scaled:
+      * solve_equi (:mvr): eigvalsh of a leading 2500-block x (p/2500)^3                         (utilities.jl:108)
+      * CCD: every stride-th coordinate of ONE WHOLE sweep (a coordinate's cost depends on its position only),
+        x stride x the sweep count of the oracle's own full solve; one thread, like the reference's BLAS-2 sweep
+      * inv(Sigma): in full, all threads                                                           (modelX.jl:106)
+      * the pm x pm Cholesky of modelX.jl:116-120: dpotrf of a 2p x 2p leading block x (m/2)^3, all threads
+      * sampling on one 4096-row chunk x n/4096: mean GEMM 2 rows p^2, and randn(rows, mp) * L with L LOWER TRIANGULAR
+        (BLAS trmm, modelX.jl:120-121): dtrmm against the 2p x 2p factor x (m/2)^2."""
+    from oracle import c_oracle
     import scipy.linalg as sla
+    from scipy.linalg import blas
     p, m, n = a.p, a.m, a.n
     kap = (m + 1) / m
     det = {}
-    # (a) solve_equi: eigvals of a p_e x p_e leading block, scaled by (p/p_e)^3  (utilities.jl:108)
-    pe = min(p, 2000)
+    rng = np.random.default_rng(0)
+    pe = min(p, 2500)
     t = time.perf_counter()
     lam_e = np.linalg.eigvalsh(Sigma[:pe, :pe]).min()
-    det["equi_s"] = (time.perf_counter() - t) * (p / pe) ** 3
-    # s_init for the CCD sample: exact lambda_min by shift-invert would cost a full eigvalsh; the block
-    # matrices used here have lambda_min independent of p (block structure), so the leading block's is exact.
-    s0 = np.full(p, min(1.0, kap * lam_e))
-    # (b) CCD: `coords` coordinates of the first sweep, single thread like the reference's BLAS-2 sweep
-    r = c_oracle.solve_ccd(Sigma, a.method, m=m, s_init=s0, max_coords=coords, lapack_init=True)
-    if r["rc"] != 0:
-        raise RuntimeError(f"oracle CCD failed rc={r['rc']}")
-    per_coord = r["loop_seconds"] / max(1, min(coords, p))
-    det["ccd_s_per_sweep"] = per_coord * p
-    det["ccd_s"] = det["ccd_s_per_sweep"] * sweeps_hint
-    # (c) conditional factor: inv(Sigma) timed in full (LAPACK, all threads); the pm x pm Cholesky of
-    #     modelX.jl:116-120 extrapolated from a p x p dpotrf as (pm)^3 / p^3
+    t_equi = (time.perf_counter() - t) * (p / pe) ** 3
+    s0 = np.full(p, min(1.0, kap * lam_e))       # block family: lambda_min is p-independent
     t = time.perf_counter()
     Sinv = np.linalg.inv(Sigma)
-    det["inv_s"] = time.perf_counter() - t
-    s_vec = np.full(p, 0.5 * s0[0])
-    C = 2 * np.diag(s_vec) - (s_vec[:, None] * Sinv) * s_vec[None, :]
-    t = time.perf_counter()
-    L = sla.cholesky(C, lower=True, check_finite=False)
-    t_chol = time.perf_counter() - t
-    det["chol_s"] = t_chol * (m ** 3)
-    # (d) sampling GEMMs on `rows` rows: X - (X - mu) SinvS  and  randn(rows, mp) * L_(mp x mp)
-    rng = np.random.default_rng(0)
-    Xs = rng.standard_normal((rows, p))
-    SiS = Sinv * s_vec[None, :]
-    t = time.perf_counter()
-    mui = Xs - Xs @ SiS
-    Z = rng.standard_normal((rows, p))
-    noise = Z @ L
-    t_rows = time.perf_counter() - t            # 2 rows p^2 (mean) + rng + 2 rows p^2 (one p x p block product)
-    # the reference multiplies randn(n, mp) by the dense pm x pm factor: m^2 block products + m rng blocks
-    t_mean = t_rows * 0.5
-    det["sample_s"] = (t_mean + (t_rows - t_mean) * m * m) * (n / rows)
-    del mui, noise
-    total = det["equi_s"] + det["ccd_s"] + det["inv_s"] + det["chol_s"] + det["sample_s"]
+    t_inv = time.perf_counter() - t
+    total = 0.0
+    for method in methods_of(a):
+        d = {}
+        r = c_oracle.solve_ccd(Sigma, method, m=m, s_init=s0, max_sweeps=1, coord_stride=stride, lapack_init=True)
+        if r["rc"] != 0:
+            raise RuntimeError(f"oracle CCD failed rc={r['rc']}")
+        d["equi_s"] = t_equi if method != "sdp_ccd" else 0.0
+        d["ccd_s_per_sweep"] = r["loop_seconds"] * stride
+        d["sweeps"] = sweeps[method]
+        d["ccd_s"] = d["ccd_s_per_sweep"] * sweeps[method]
+        d["inv_s"] = t_inv
+        s_vec = np.full(p, 0.5 * s0[0])
+        C = 2 * np.diag(s_vec) - (s_vec[:, None] * Sinv) * s_vec[None, :]
+        mm = min(m, 2)
+        St = np.empty((mm * p, mm * p))
+        for k in range(mm):
+            for l in range(mm):
+                St[k * p:(k + 1) * p, l * p:(l + 1) * p] = C if k == l else C - np.diag(s_vec)
+        t = time.perf_counter()
+        L = sla.cholesky(St, lower=True, overwrite_a=True, check_finite=False)
+        d["chol_s"] = (time.perf_counter() - t) * (m / mm) ** 3
+        rows = min(SAMPLE_ROWS, n)
+        Xs = rng.standard_normal((rows, p))
+        SiS = Sinv * s_vec[None, :]
+        t = time.perf_counter()
+        mui = Xs - Xs @ SiS
+        t_mean = time.perf_counter() - t
+        Z = np.asfortranarray(rng.standard_normal((rows, mm * p)))
+        t = time.perf_counter()
+        noise = blas.dtrmm(1.0, L, Z, side=1, lower=1, overwrite_b=1)
+        t_noise = (time.perf_counter() - t) * (m / mm) ** 2
+        d["sample_s"] = (t_mean + t_noise) * (n / rows)
+        d["total_s"] = d["equi_s"] + d["ccd_s"] + d["inv_s"] + d["chol_s"] + d["sample_s"]
+        total += d["total_s"]
+        det[method] = d
+        del mui, noise, L, St, Z
     det["total_s_extrapolated"] = total
-    return n / total, det
+    return len(methods_of(a)) * n / total, det
 
 
-def cpu_sample_desc(a, coords=400, rows=400):
-    return (f"oracle port on host cores: eigvalsh on a {min(a.p, 2000)}-block (x(p/pe)^3), {coords} of {a.p} CCD "
-            f"coordinates of sweep 1 (x p x sweeps; 1 thread, like the reference's BLAS-2 sweep), full inv(Sigma), "
-            f"p x p dpotrf (x m^3 for the pm x pm factor), sampling GEMMs on {rows} of {a.n} rows (x n/rows); "
-            f"BLAS stages use all host threads")
+def cpu_sample_desc(a, threads, stride):
+    return (f"oracle port on host cores ({threads} BLAS threads): eigvalsh on a 2500-block (x(p/2500)^3); every {stride}th "
+            f"coordinate of one whole CCD sweep per method (x{stride} x the oracle's full-solve sweep count; 1 thread, like the "
+            f"reference's BLAS-2 sweep); full inv(Sigma); dpotrf of a 2p x 2p block of the pm x pm matrix (x(m/2)^3); sampling on "
+            f"one {SAMPLE_ROWS}-row chunk (x n/{SAMPLE_ROWS}): mean GEMM + dtrmm against the lower-triangular 2p x 2p factor (x(m/2)^2)")
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    threads = host_threads()
     import knockoffs_b200  # noqa: F401  (harness generators only; no GPU object is created on this arm)
     kb = sys.modules["knockoffs_b200"]
     Sigma = kb.harness.block_sigma(a.p, 10, 0.5, 0.25)
-    sweeps_hint = int(os.environ.get("KB_BENCH_SWEEPS_HINT", "5"))
-    for _ in range(max(0, min(a.warmup, 1))):
-        cpu_reference_step(a, Sigma, sweeps_hint, coords=50, rows=50)
+    sweeps = {mth: golden_sweeps(mth, a.p, a.m) for mth in methods_of(a)}
     vals, det = [], {}
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        v, det = cpu_reference_step(a, Sigma, sweeps_hint)
+        v, det = cpu_reference_step(a, Sigma, sweeps, ccd_stride(a.steps))
         vals.append(v)
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
-    cores = os.cpu_count() or 1
+    n_rows = len(methods_of(a)) * a.n
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1000.0 * a.n / v, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": 1000.0 * n_rows / v, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "sweeps_assumed": sweeps_hint},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_desc(a),
-                             "detail": det, "sample_wall_s": wall},
+            "config": config_dict(a, world),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu_sample_desc(a, threads, ccd_stride(a.steps)),
+                             "detail": det, "sample_wall_s": wall, "extrapolated": True,
+                             "note": "the CPU work does not depend on the GPU count: the same value is reported at every N"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -194,58 +254,424 @@ def run_reference(a):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
-def run_ours(a):
-    import torch
-    import torch.distributed as dist
-    import knockoffs_b200  # noqa: F401
-    kb = sys.modules["knockoffs_b200"]
-    dev = kb.dev
+class Env:
+    """Process-wide state of the GPU arm."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def __init__(self, a):
+        import torch
+        import torch.distributed as dist
+        import knockoffs_b200  # noqa: F401
+        self.torch, self.dist = torch, dist
+        self.kb = sys.modules["knockoffs_b200"]
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference)")
+        torch.cuda.set_device(self.local)
+        self.d = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.d)
+        self.ctx = self.kb.Context(self.local)
+        if a.chunk:
+            self.ctx.set_sample_chunk_rows(a.chunk)
+        self.ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.d)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    p, n, m = a.p, a.n, a.m
-    f64 = torch.float64
-    d = torch.device("cuda", local)
-    Sigma_h = kb.harness.block_sigma(p, 10, 0.5, 0.25)
-    dSigma = torch.from_numpy(np.ascontiguousarray(Sigma_h)).to(d)          # symmetric: row/col-major coincide
-    # X = Z0 chol(Sigma)' generated on the device (data generation only), stored column-major as Xt[j, i] = X[i, j]
-    g = torch.Generator(device=d)
-    g.manual_seed(20260003 + rank)
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.d)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def bcast(self, t, src):
+        if self.world > 1:
+            self.dist.broadcast(t, src=src)
+
+    def ev(self):
+        return self.torch.cuda.Event(enable_timing=True)
+
+
+def gen_gaussian_Xt(E, dSigma, p, n, seed):
+    """X = Z0 chol(Sigma)' generated on the device (data generation only), stored column-major as Xt[j, i] = X[i, j]."""
+    torch = E.torch
+    g = torch.Generator(device=E.d)
+    g.manual_seed(seed)
     Lc = torch.linalg.cholesky(dSigma)
-    Xt = torch.empty((p, n), dtype=f64, device=d)
-    step_rows = 16384
-    for r0 in range(0, n, step_rows):
-        r1 = min(n, r0 + step_rows)
-        Xt[:, r0:r1] = Lc @ torch.randn((p, r1 - r0), dtype=f64, device=d, generator=g)
-    del Lc
-    dmu = torch.zeros(p, dtype=f64, device=d)
-    ds = torch.empty(p, dtype=f64, device=d)
-    dSiS = torch.empty((p, p), dtype=f64, device=d)
-    dLb = torch.empty((2 * m - 1, p, p), dtype=f64, device=d)
-    Xko_t = torch.empty((m * p, n), dtype=f64, device=d)
-    torch.cuda.synchronize()
+    Xt = torch.empty((p, n), dtype=torch.float64, device=E.d)
+    for r0 in range(0, n, 16384):
+        r1 = min(n, r0 + 16384)
+        Xt[:, r0:r1] = Lc @ torch.randn((p, r1 - r0), dtype=torch.float64, device=E.d, generator=g)
+    return Xt
 
-    # FP64 tensor peak: MEASURED_PEAKS.json has no f64 entry -> measure cuBLAS DGEMM here (best of 5)
+
+def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
+    """The configs[2] step at E.world GPUs.  Returns a dict of measurements (rank 0 fills the roofline parts)."""
+    torch, kb, dev = E.torch, E.kb, E.kb.dev
+    ctx, ext, world, rank = E.ctx, E.ext, E.world, E.rank
+    p, m, methods = a.p, a.m, methods_of(a)
+    f64 = torch.float64
+    if scaling == "strong":
+        lo, hi = kb.dist.shard_rows(a.n, world, rank)
+        n_total = a.n
+    else:
+        lo, hi = rank * a.n, (rank + 1) * a.n
+        n_total = a.n * world
+    n_loc = hi - lo
+    Sigma_h = kb.harness.block_sigma(p, 10, 0.5, 0.25)
+    dSigma = torch.from_numpy(np.ascontiguousarray(Sigma_h)).to(E.d)          # symmetric: row/col-major coincide
+    Xt = gen_gaussian_Xt(E, dSigma, p, n_loc, 20260003 + rank)
+    dmu = torch.zeros(p, dtype=f64, device=E.d)
+    ds = [torch.empty(p, dtype=f64, device=E.d) for _ in methods]
+    dSiS = [torch.empty((p, p), dtype=f64, device=E.d) for _ in methods]
+    dLb = [torch.empty((2 * m - 1, p, p), dtype=f64, device=E.d) for _ in methods]
+    Xko_t = torch.empty((m * p, n_loc), dtype=f64, device=E.d)
+    torch.cuda.synchronize()
+    owner = [i % world for i in range(len(methods))]
+    st = {"steps": 0, "bcast_ms": 0.0, "sample_ms": 0.0}
+    per = {mth: {"solve_ms": 0.0, "ccd_ms": 0.0, "init_ms": 0.0, "factor_ms": 0.0, "ref_bytes": 0.0, "touched_bytes": 0.0,
+                 "sweeps": 0, "flops": 0.0, "objective": None} for mth in methods}
+
+    def step(record=False):
+        nvtx = torch.cuda.nvtx
+        for i, mth in enumerate(methods):
+            if owner[i] != rank:
+                continue
+            e = [E.ev() for _ in range(3)]
+            e[0].record(ext)
+            nvtx.range_push(f"solve_s:{mth}")
+            info = dev.solve_s_dev(ctx, dSigma.data_ptr(), p, mth, m, ds[i].data_ptr(), refresh_every=a.refresh_every)
+            nvtx.range_pop()
+            e[1].record(ext)
+            nvtx.range_push(f"cond_factor:{mth}")
+            dev.cond_factor_dev(ctx, dSigma.data_ptr(), p, ds[i].data_ptr(), True, m, dSiS[i].data_ptr(), dLb[i].data_ptr())
+            nvtx.range_pop()
+            e[2].record(ext)
+            if record:
+                ext.synchronize()
+                q = per[mth]
+                q["solve_ms"] += e[0].elapsed_time(e[1]); q["factor_ms"] += e[1].elapsed_time(e[2])
+                q["ccd_ms"] += info["solve_ms"]; q["init_ms"] += info["init_ms"]; q["ref_bytes"] += info["ref_bytes"]
+                q["touched_bytes"] += info["touched_bytes"]; q["sweeps"] = info["sweeps"]; q["mode"] = info["mode"]
+                q["flops"] += info["flops"]; q["objective"] = info["objective"]
+        if world > 1:
+            # the step's collectives: s (p doubles) and the factor blocks ((2m) p^2 doubles = 2 GB per method) from the
+            # rank that solved to everyone, NCCL broadcast over NVLink
+            b0, b1 = E.ev(), E.ev()
+            b0.record()
+            for i in range(len(methods)):
+                E.bcast(ds[i], owner[i]); E.bcast(dSiS[i], owner[i]); E.bcast(dLb[i], owner[i])
+            b1.record()
+            torch.cuda.current_stream().synchronize()
+            if record:
+                st["bcast_ms"] += b0.elapsed_time(b1)
+        e0, e1 = E.ev(), E.ev()
+        e0.record(ext)
+        for i, mth in enumerate(methods):
+            nvtx.range_push(f"sample:{mth}")
+            dev.sample_dev(ctx, Xt.data_ptr(), n_loc, n_loc, p, dmu.data_ptr(), dSiS[i].data_ptr(), dLb[i].data_ptr(), m,
+                           Xko_t.data_ptr(), n_loc, seed=20260003 + i, row_offset=lo)
+            nvtx.range_pop()
+        e1.record(ext)
+        if record:
+            ext.synchronize()
+            st["sample_ms"] += e0.elapsed_time(e1)
+            st["steps"] += 1
+
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(E.local) if (sample_clocks and rank == 0) else None
+    E.barrier()
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launches
+    t0, t1 = E.ev(), E.ev()
+    t0.record(ext)
+    for _ in range(steps):
+        step(record=True)
+    t1.record(ext)
+    E.barrier()
+    ext.synchronize()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = E.max_over_ranks(t0.elapsed_time(t1))
+    ms_per_step = total_ms / steps
+    out = {"ms_per_step": ms_per_step, "value": len(methods) * n_total / (ms_per_step * 1e-3), "launches": int(launches),
+           "clocks": clocks, "n_total": n_total, "rows_per_gpu": n_loc, "st": st, "per": per, "owner": owner,
+           "handles": (dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo)}
+    # per-method timings live on their owner: gather them on rank 0
+    if world > 1:
+        gathered = [None] * world
+        E.dist.all_gather_object(gathered, {k: v for k, v in per.items() if owner[methods.index(k)] == rank})
+        for g in gathered:
+            per.update(g)
+        st["sample_ms"] = E.max_over_ranks(st["sample_ms"])
+    return out
+
+
+def run_e2e(E, a, res, steps):
+    """The same step through the host-pointer C ABI: kb_solve_s (on the method's owner rank) -> s broadcast (p doubles) ->
+    kb_condition on this rank's row shard, pinned host buffers, every H2D / D2H inside the timed region."""
+    import ctypes as C
+    import psutil
+    torch, kb = E.torch, E.kb
+    ctx, world, rank = E.ctx, E.world, E.rank
+    p, m, methods = a.p, a.m, methods_of(a)
+    dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo = res["handles"]
+    n_loc = Xt.shape[1]
+    need = (p * n_loc + m * p * n_loc) * 8
+    avail = psutil.virtual_memory().available / max(1, world)
+    n_e = n_loc
+    if need > 0.6 * avail:
+        n_e = max(1024, int(n_loc * 0.6 * avail / need) // 1024 * 1024)
+    Xh_t = torch.empty((p, n_e), dtype=torch.float64, pin_memory=True)
+    Xh_t.copy_(Xt[:, :n_e])
+    Xko_h_t = torch.empty((m * p, n_e), dtype=torch.float64, pin_memory=True)
+    mu_h = np.zeros(p)
+    Sig_f = np.asfortranarray(Sigma_h)
+    s_h = [np.empty(p) for _ in methods]
+    opts = kb.make_opts(refresh_every=a.refresh_every)
+    info = kb.api.SolveInfo()
+    owner = res["owner"]
+
+    def e2e_step():
+        for i, mth in enumerate(methods):
+            if owner[i] == rank:
+                rc = ctx._lib.kb_solve_s(ctx.h, Sig_f.ctypes.data, p, kb.api.METHODS[mth], float(m), C.byref(opts), None,
+                                         s_h[i].ctypes.data, C.byref(info))
+                kb.api.check(ctx.h, rc)
+        if world > 1:
+            for i in range(len(methods)):
+                t = torch.from_numpy(s_h[i]).to(E.d)
+                E.bcast(t, owner[i])
+                s_h[i][:] = t.cpu().numpy()
+        for i, mth in enumerate(methods):
+            rc = ctx._lib.kb_condition(ctx.h, Xh_t.data_ptr(), n_e, p, mu_h.ctypes.data, Sig_f.ctypes.data, s_h[i].ctypes.data, 1, m,
+                                       None, 20260003 + i, lo, Xko_h_t.data_ptr())
+            kb.api.check(ctx.h, rc)
+
+    e2e_step()                     # warm-up
+    E.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    E.barrier()
+    dt = E.max_over_ranks(time.perf_counter() - t0)
+    rows = n_e * world if res["n_total"] != a.n or world == 1 else int(round(a.n * n_e / n_loc))
+    nm = len(methods)
+    out = {"value": nm * rows * steps / dt, "unit": UNIT,
+           "h2d_bytes_per_step": int(nm * (p * n_e + p * p + 2 * p) * 8 + sum(p * p * 8 for i in range(nm) if owner[i] == rank)),
+           "d2h_bytes_per_step": int(nm * (m * p * n_e) * 8 + sum(p * 8 for i in range(nm) if owner[i] == rank)),
+           "rows_per_gpu": n_e, "ms_per_step": 1000.0 * dt / steps,
+           "api": "kb_solve_s + kb_condition (host pointers, pinned); bytes are per rank"}
+    del Xh_t, Xko_h_t
+    return out
+
+
+def run_config5(E, a):
+    """BASELINE configs[4]: genotype-like X (0/1/2 dosages), n = 500000 rows in total sharded over the ranks, p = 5000:
+    local Gram partial (DMMA SYRK) -> ONE NCCL all-reduce of the p x p sums (+ p column sums) -> :maxent solve on rank 0
+    -> s and the factor broadcast -> sampling on every rank's shard (m = 1)."""
+    torch, kb, dev, dist = E.torch, E.kb, E.kb.dev, E.dist
+    ctx, ext, world, rank = E.ctx, E.ext, E.world, E.rank
+    p, n = 5000, a.c5_rows
+    lo, hi = kb.dist.shard_rows(n, world, rank)
+    n_loc = hi - lo
+    f64 = torch.float64
+    g = torch.Generator(device=E.d)
+    g.manual_seed(20260005)                                  # same allele frequencies on every rank
+    freq = 0.05 + 0.45 * torch.rand(p, dtype=f64, device=E.d, generator=g)
+    thr = torch.special.ndtri(freq)[:, None]
+    g.manual_seed(20260005 + 1000 * (rank + 1))
+    Xt = torch.empty((p, n_loc), dtype=f64, device=E.d)
+    for b0 in range(0, p, 50):                               # LD within blocks of 50 through a shared latent
+        b1 = min(p, b0 + 50)
+        acc = torch.zeros((b1 - b0, n_loc), dtype=f64, device=E.d)
+        for _ in range(2):
+            z = torch.randn((1, n_loc), dtype=f64, device=E.d, generator=g)
+            e = torch.randn((b1 - b0, n_loc), dtype=f64, device=E.d, generator=g)
+            acc += ((0.6 ** 0.5) * z + (0.4 ** 0.5) * e < thr[b0:b1]).to(f64)
+        Xt[b0:b1] = acc
+    del acc, z, e
+    G = torch.empty((p, p), dtype=f64, device=E.d)
+    cs = torch.empty(p, dtype=f64, device=E.d)
+    s = torch.empty(p, dtype=f64, device=E.d)
+    SiS = torch.empty((p, p), dtype=f64, device=E.d)
+    Lb = torch.empty((1, p, p), dtype=f64, device=E.d)
+    Xko = torch.empty((p, n_loc), dtype=f64, device=E.d)
+    torch.cuda.synchronize()
+    t = {"gram_ms": 0.0, "allreduce_ms": 0.0, "solve_ms": 0.0, "factor_ms": 0.0, "bcast_ms": 0.0, "sample_ms": 0.0}
+    info = {}
+
+    def step(record):
+        nonlocal info
+        e = [E.ev() for _ in range(2)]
+        e[0].record(ext)
+        dev.gram_partial_dev(ctx, Xt.data_ptr(), n_loc, n_loc, p, G.data_ptr(), cs.data_ptr())
+        e[1].record(ext)
+        ext.synchronize()
+        a0, a1 = E.ev(), E.ev()
+        a0.record()
+        if world > 1:
+            dist.all_reduce(G, op=dist.ReduceOp.SUM)
+            dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+        a1.record()
+        torch.cuda.current_stream().synchronize()
+        f = [E.ev() for _ in range(4)]
+        f[0].record(ext)
+        dev.gram_finish_dev(ctx, G.data_ptr(), cs.data_ptr(), n, p, True, 0.0)
+        if rank == 0:
+            info = dev.solve_s_dev(ctx, G.data_ptr(), p, "maxent", 1, s.data_ptr())
+        f[1].record(ext)
+        if rank == 0:
+            dev.cond_factor_dev(ctx, G.data_ptr(), p, s.data_ptr(), True, 1, SiS.data_ptr(), Lb.data_ptr())
+        f[2].record(ext)
+        ext.synchronize()
+        b0, b1 = E.ev(), E.ev()
+        b0.record()
+        E.bcast(s, 0); E.bcast(SiS, 0); E.bcast(Lb, 0)
+        b1.record()
+        torch.cuda.current_stream().synchronize()
+        c0, c1 = E.ev(), E.ev()
+        c0.record(ext)
+        dev.sample_dev(ctx, Xt.data_ptr(), n_loc, n_loc, p, cs.data_ptr(), SiS.data_ptr(), Lb.data_ptr(), 1, Xko.data_ptr(), n_loc,
+                       seed=20260005, row_offset=lo)
+        c1.record(ext)
+        ext.synchronize()
+        if record:
+            t["gram_ms"] += e[0].elapsed_time(e[1]); t["allreduce_ms"] += a0.elapsed_time(a1)
+            t["solve_ms"] += f[0].elapsed_time(f[1]); t["factor_ms"] += f[1].elapsed_time(f[2])
+            t["bcast_ms"] += b0.elapsed_time(b1); t["sample_ms"] += c0.elapsed_time(c1)
+
+    step(False)
+    E.barrier()
+    l0 = ctx.launches
+    t0, t1 = E.ev(), E.ev()
+    t0.record(ext)
+    K = 2
+    for _ in range(K):
+        step(True)
+    t1.record(ext)
+    E.barrier()
+    ext.synchronize()
+    ms = E.max_over_ranks(t0.elapsed_time(t1)) / K
+    for k in t:
+        t[k] = E.max_over_ranks(t[k] / K)
+    out = {"workload": f"BASELINE configs[4]: dosage X n={n} rows in total (sharded x{world}), p={p}, Gram + NCCL all-reduce + :maxent + "
+                       f"sampling m=1", "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "stages_ms": t,
+           "gram_tflops_per_gpu": n_loc * p * (p + 1.0) / (t["gram_ms"] * 1e-3) / 1e12 if t["gram_ms"] > 0 else None,
+           "allreduce_bytes": (p * p + p) * 8 if world > 1 else 0,
+           "allreduce_busbw_gbs": (2.0 * (world - 1) / world * (p * p + p) * 8 / (t["allreduce_ms"] * 1e-3) / 1e9)
+           if (world > 1 and t["allreduce_ms"] > 0) else None,
+           "sweeps": info.get("sweeps") if rank == 0 else None, "gpu_launches": int((ctx.launches - l0) / K), "steps": K}
+    del Xt, Xko, G, SiS, Lb
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_config4(E, a):
+    """BASELINE configs[3]: group :mvr knockoff solve, p = 10000 = 8 independent LD blocks of 1250 variables (groups of 5),
+    LD blocks dealt round-robin to the ranks.  All blocks sweep in lockstep; the reference's GLOBAL decisions (shared equi
+    gamma, per-sweep convergence on the summed objective / max delta) go through the library's reduce hook: a barrier
+    between this rank's host threads (one context per LD block) and one NCCL all-reduce of a few doubles between ranks."""
+    torch, kb, dist = E.torch, E.kb, E.dist
+    world, rank = E.world, E.rank
+    nblocks, pb = 8, 1250
+    mine = list(range(rank, nblocks, world))
+    blocks, groups = {}, {}
+    for b in mine:
+        g = np.repeat(np.arange(1, pb // 5 + 1), 5)
+        rho = 0.7 + 0.02 * b                         # blocks differ, so the global gamma really is a min over blocks
+        S = np.where(g[:, None] == g[None, :], rho, rho * 0.25).astype(float)
+        np.fill_diagonal(S, 1.0)
+        blocks[b], groups[b] = np.asfortranarray(S), g
+    ctxs = {b: kb.Context(E.local) for b in mine}
+    nth = len(mine)
+    bar = threading.Barrier(nth) if nth > 1 else None
+    slots = {}
+    result = {}
+    ops = {0: dist.ReduceOp.MIN, 1: dist.ReduceOp.SUM, 2: dist.ReduceOp.MAX}
+    ncoll = [0]
+
+    def make_reduce(b):
+        def reduce(op, vals):
+            slots[b] = vals.copy()
+            if bar is not None:
+                bar.wait(timeout=600)
+            if b == mine[0]:
+                both = np.stack([slots[x] for x in mine])
+                loc = both.min(0) if op == 0 else (both.sum(0) if op == 1 else both.max(0))
+                if world > 1:
+                    t = torch.from_numpy(loc).to(E.d)
+                    dist.all_reduce(t, op=ops[op])
+                    loc = t.cpu().numpy()
+                    ncoll[0] += 1
+                slots["res"] = loc
+            if bar is not None:
+                bar.wait(timeout=600)
+            vals[:] = slots["res"]
+        return reduce
+
+    def worker(b, small):
+        try:
+            torch.cuda.set_device(E.local)
+            Sg, gg = (blocks[b][:50, :50], groups[b][:50]) if small else (blocks[b], groups[b])
+            result[b] = kb.solve_s_group_sharded(Sg, gg, "mvr", make_reduce(b), m=1, ctx=ctxs[b])
+        except Exception as ex:      # noqa: BLE001
+            result[b] = ex
+            if bar is not None:
+                bar.abort()
+
+    def run(small):
+        th = [threading.Thread(target=worker, args=(b, small), daemon=True) for b in mine]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join(900)
+        for b in mine:
+            if isinstance(result.get(b), Exception):
+                raise result[b]
+
+    run(True)                        # warm-up on 50-variable corners
+    E.barrier()
+    ncoll[0] = 0
+    t0 = time.perf_counter()
+    run(False)
+    E.barrier()
+    wall = E.max_over_ranks(time.perf_counter() - t0)
+    obj = np.array([sum(result[b][1] for b in mine)])
+    tt = torch.from_numpy(obj).to(E.d)
+    if world > 1:
+        dist.all_reduce(tt)
+    infos = [result[b][2] for b in mine]
+    out = {"workload": f"BASELINE configs[3]: group :mvr, p={nblocks * pb} = {nblocks} LD blocks of {pb} (groups of 5), m=1, blocks dealt to "
+                       f"{world} rank(s), lockstep sweeps", "solve_wall_s": wall, "objective": float(tt.item()),
+           "inner_sweeps": infos[0]["inner_sweeps"], "steps_per_block": infos[0]["steps"], "device_ms_per_block": [i["solve_ms"] for i in infos],
+           "nccl_allreduces": ncoll[0], "blocks_per_rank": len(mine), "timing": "host wall clock around the lockstep solve, max over ranks"}
+    for c in ctxs.values():
+        c.close() if hasattr(c, "close") else None
+    return out
+
+
+def run_ours(a):
+    E = Env(a)
+    torch, kb, dev = E.torch, E.kb, E.kb.dev
+    world, rank, ctx = E.world, E.rank, E.ctx
+    p, m, methods = a.p, a.m, methods_of(a)
+
+    # FP64 tensor peak: MEASURED_PEAKS.json has no f64 entry -> measure cuBLAS DGEMM here (best of 6)
     fp64_peak = None
     if rank == 0:
-        A = torch.randn((8192, 8192), dtype=f64, device=d)
-        B = torch.randn((8192, 8192), dtype=f64, device=d)
+        A = torch.randn((8192, 8192), dtype=torch.float64, device=E.d)
+        B = torch.randn((8192, 8192), dtype=torch.float64, device=E.d)
         best = 1e9
         for _ in range(6):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0, e1 = E.ev(), E.ev()
             e0.record(); torch.matmul(A, B); e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         fp64_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
@@ -257,67 +683,9 @@ def run_ours(a):
     except Exception:
         pass
 
-    ctx = kb.Context(local)
-    if a.chunk:
-        ctx.set_sample_chunk_rows(a.chunk)
-    ext = torch.cuda.ExternalStream(ctx.stream, device=d)
-    row_offset = rank * n
-    stage = {"solve_ms": 0.0, "ccd_ms": 0.0, "init_ms": 0.0, "factor_ms": 0.0, "sample_ms": 0.0, "ref_bytes": 0.0,
-             "touched_bytes": 0.0, "sweeps": 0, "steps": 0}
-
-    def device_step(record=False):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        nvtx = torch.cuda.nvtx
-        ev[0].record(ext)
-        nvtx.range_push("solve_s")
-        info = dev.solve_s_dev(ctx, dSigma.data_ptr(), p, a.method, m, ds.data_ptr(), refresh_every=a.refresh_every)
-        nvtx.range_pop()
-        ev[1].record(ext)
-        nvtx.range_push("cond_factor")
-        dev.cond_factor_dev(ctx, dSigma.data_ptr(), p, ds.data_ptr(), True, m, dSiS.data_ptr(), dLb.data_ptr())
-        nvtx.range_pop()
-        ev[2].record(ext)
-        nvtx.range_push("sample")
-        dev.sample_dev(ctx, Xt.data_ptr(), n, n, p, dmu.data_ptr(), dSiS.data_ptr(), dLb.data_ptr(), m,
-                       Xko_t.data_ptr(), n, seed=20260003, row_offset=row_offset)
-        nvtx.range_pop()
-        ev[3].record(ext)
-        if record:
-            ext.synchronize()
-            stage["solve_ms"] += ev[0].elapsed_time(ev[1])
-            stage["factor_ms"] += ev[1].elapsed_time(ev[2])
-            stage["sample_ms"] += ev[2].elapsed_time(ev[3])
-            stage["ccd_ms"] += info["solve_ms"]
-            stage["init_ms"] += info["init_ms"]
-            stage["ref_bytes"] += info["ref_bytes"]
-            stage["touched_bytes"] += info["touched_bytes"]
-            stage["sweeps"] = info["sweeps"]
-            stage["mode"] = info["mode"]
-            stage["steps"] += 1
-        return info
-
-    for _ in range(a.warmup):
-        device_step()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launches
-    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_ev0.record(ext)
-    for _ in range(a.steps):
-        device_step(record=True)
-    t_ev1.record(ext)
-    barrier()
-    ext.synchronize()
-    launches = ctx.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([t_ev0.elapsed_time(t_ev1)], dtype=f64, device=d)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    ms_per_step = total_ms / a.steps
-    value = world * n / (ms_per_step * 1e-3)
+    res = run_pipeline(E, a, a.scaling, a.steps, a.warmup, sample_clocks=True)
+    dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo = res["handles"]
+    n_loc = res["rows_per_gpu"]
 
     # ---- the memory-bound formulation, timed alone (outside the step): ONE sweep of the rank-1 streaming kernel
     #      (8 p (p+1)^2 algorithmic bytes) -> achieved HBM GB/s of ccd_stream_kernel
@@ -325,125 +693,110 @@ def run_ours(a):
     if rank == 0 and not a.no_stream:
         best = None
         for _ in range(2):
-            inf = dev.solve_s_dev(ctx, dSigma.data_ptr(), p, a.method, m, ds.data_ptr(), mode="stream", niter=1)
+            inf = dev.solve_s_dev(ctx, dSigma.data_ptr(), p, "mvr", m, ds[0].data_ptr(), mode="stream", niter=1, objective=False)
             if best is None or inf["solve_ms"] < best["solve_ms"]:
                 best = inf
         gbs = best["ref_bytes"] / (best["solve_ms"] * 1e-3) / 1e9
-        stream_roof = {"kernel": "ccd_stream_kernel (KB_MODE_STREAM, one sweep, timed alone)", "bound": "hbm", "achieved": gbs,
+        stream_roof = {"kernel": "ccd_stream_kernel (KB_MODE_STREAM, one :mvr sweep, timed alone)", "bound": "hbm", "achieved": gbs,
                        "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES["ccd_stream_kernel"],
                        "peak_source": peak_src, "algorithmic_bytes_per_launch": best["ref_bytes"],
                        "touched_bytes_per_launch": best["touched_bytes"], "launch_ms": best["solve_ms"]}
 
-    # ---- end to end through the host-pointer C ABI (pinned host buffers; H2D + D2H inside the timed region)
     e2e = None
     if not a.no_e2e:
-        import psutil
-        need = (p * n + m * p * n) * 8
-        n_e = n
-        avail = psutil.virtual_memory().available / max(1, world)
-        if need > 0.6 * avail:
-            n_e = max(1024, int(n * 0.6 * avail / need) // 1024 * 1024)
-        Xh_t = torch.empty((p, n_e), dtype=f64, pin_memory=True)
-        Xh_t.copy_(Xt[:, :n_e])
-        Xko_h_t = torch.empty((m * p, n_e), dtype=f64, pin_memory=True)
-        s_h = np.empty(p)
-        mu_h = np.zeros(p)
-        Sig_f = np.asfortranarray(Sigma_h)
-        import ctypes as C
-        opts = kb.make_opts(refresh_every=a.refresh_every)
-        info = kb.api.SolveInfo()
+        e2e = run_e2e(E, a, res, min(a.steps, 10))
 
-        def e2e_step():
-            rc = ctx._lib.kb_modelx_gaussian_knockoffs(
-                ctx.h, Xh_t.data_ptr(), n_e, p, mu_h.ctypes.data, Sig_f.ctypes.data, kb.api.METHODS[a.method], m,
-                C.byref(opts), None, None, 20260003, row_offset, Xko_h_t.data_ptr(), s_h.ctypes.data, C.byref(info))
-            kb.api.check(ctx.h, rc)
-
-        e2e_step()                     # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            e2e_step()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=f64, device=d)
+    alt = None
+    del res["handles"], dSigma, Xt, ds, dSiS, dLb, Xko_t
+    torch.cuda.empty_cache()
+    extra = {}
+    if not a.no_extra:
         if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n_e * a.steps / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int((p * n_e + p * p + p) * 8), "d2h_bytes_per_step": int((m * p * n_e + p) * 8),
-               "rows_per_gpu": n_e, "ms_per_step": 1000.0 * float(dt.item()) / a.steps,
-               "api": "kb_modelx_gaussian_knockoffs (host pointers, pinned)"}
-        del Xh_t, Xko_h_t
+            try:
+                other = "weak" if a.scaling == "strong" else "strong"
+                r2 = run_pipeline(E, a, other, max(1, min(a.steps, 2)), 1)
+                alt = {"scaling": other, "value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"], "n_total": r2["n_total"],
+                       "rows_per_gpu": r2["rows_per_gpu"], "sampling_ms": r2["st"]["sample_ms"] / max(1, r2["st"]["steps"]),
+                       "bcast_ms": r2["st"]["bcast_ms"] / max(1, r2["st"]["steps"])}
+                del r2
+                torch.cuda.empty_cache()
+            except Exception as ex:     # noqa: BLE001
+                alt = {"error": repr(ex)}
+        for name, fn in (("config5", run_config5), ("config4", run_config4)):
+            try:
+                extra[name] = fn(E, a)
+            except Exception as ex:     # noqa: BLE001
+                extra[name] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
 
     if rank == 0:
-        k = max(1, stage["steps"])
-        ccd_ms, sample_ms = stage["ccd_ms"] / k, stage["sample_ms"] / k
-        ccd_gbs = stage["ref_bytes"] / k / (ccd_ms * 1e-3) / 1e9 if ccd_ms > 0 else 0.0
-        # sampling flops.  SURVEY 8(d) counts 3 m n p^2 (mean GEMM 2 n p^2; per copy a triangular Z_k L_kk, n p^2, and a dense
-        # (sum_{i>k} Z_i) M_k, 2 n p^2).  For Diagonal(s) every M_k = L_kk + (upper triangular N_k), so a copy is two triangular
-        # products, S_k L_kk + S_{k+1} N_k: the algorithmic minimum and what is executed is (2 m + 1) n p^2.
+        k = max(1, res["st"]["steps"])
+        per, st = res["per"], res["st"]
+        sample_ms = st["sample_ms"] / k
+        n_s = n_loc                                            # rows this rank sampled per method
         structured = m > 1 and os.environ.get("KB_SAMPLE_STRUCTURED", "1") != "0"
-        survey_flops = 3.0 * m * n * float(p) ** 2
-        sample_flops = (2.0 * m + 1.0) * n * float(p) ** 2 if structured else survey_flops
+        # sampling flops per method.  SURVEY 8(d) counts 3 m n p^2; for Diagonal(s) every M_k = L_kk + (upper triangular N_k), so a
+        # copy is two triangular products: executed = algorithmic minimum = (2 m + 1) n p^2.
+        survey_flops = len(methods) * 3.0 * m * n_s * float(p) ** 2
+        sample_flops = len(methods) * (2.0 * m + 1.0) * n_s * float(p) ** 2 if structured else survey_flops
         sample_tfs = sample_flops / (sample_ms * 1e-3) / 1e12 if sample_ms > 0 else 0.0
-        # CCD sweeps as run inside the step: the blocked kernels (64 coordinates per sequential kernel, the triangle
-        # updated once per 256 coordinates by a SYRK-shaped DMMA GEMM: p^3 flops per sweep).  Their time is set by the
-        # chain of sequential kernels, not by a roofline; the algorithmic-bytes figure of SURVEY 8(d) is reported as
-        # the HBM bandwidth a rank-1 streaming implementation would need to match it.
-        sweeps = max(1, stage["sweeps"])
-        ccd_tfs = float(p) ** 3 * sweeps / (ccd_ms * 1e-3) / 1e12 if ccd_ms > 0 else 0.0
-        roof_ccd = {"kernel": "ccd_block (ccd_block_seq_kernel + dgemm_dmma_kernel rank-256 updates)", "bound": "tensor",
-                    "achieved": ccd_tfs, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ccd_tfs / fp64_peak if fp64_peak else None,
-                    "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run",
-                    "algorithmic_flops_per_sweep": float(p) ** 3, "sweep_ms": ccd_ms / sweeps, "sweeps_per_step": stage["sweeps"],
-                    "algorithmic_bytes_per_sweep": stage["ref_bytes"] / k / sweeps,
-                    "touched_bytes_per_sweep": stage["touched_bytes"] / k / sweeps,
-                    "hbm_equivalent_gbs": ccd_gbs, "mode": stage.get("mode")}
-        roof_gemm = {"kernel": "dgemm_dmma_kernel (sampling)", "bound": "tensor", "achieved": sample_tfs, "peak": fp64_peak,
+        roof_gemm = {"kernel": "dgemm_dmma_kernel (sampling, both methods)", "bound": "tensor", "achieved": sample_tfs, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": sample_tfs / fp64_peak if fp64_peak else None,
                      "traffic": NCU_TRAFFIC_BYTES["dgemm_dmma_kernel"],
                      "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, best of 6",
                      "algorithmic_flops_per_step": sample_flops, "stage_ms": sample_ms,
-                     "flop_count": "(2m+1) n p^2: two triangular products per copy (M_k = L_kk + upper N_k for diagonal S)" if structured
-                     else "3 m n p^2 (SURVEY 8d)",
+                     "flop_count": "(2m+1) n p^2 per method: two triangular products per copy (M_k = L_kk + upper N_k for diagonal S)"
+                     if structured else "3 m n p^2 (SURVEY 8d)",
                      "survey_3mnp2_equivalent_tflops": survey_flops / (sample_ms * 1e-3) / 1e12 if sample_ms > 0 else 0.0}
-        # conditional-covariance factor (modelX.jl:106-120).  SURVEY 8(d) algorithmic flops for diagonal S: p^3/3 + p^3
-        # (inverse) + m p^3/3 + (m-1)(p^3 + p^3) (structured factor).  Executed: p^3 + m p^3/3 + (m-1) 2p^3/3 -- for diagonal S
-        # the off-diagonal blocks are M_k = L_kk - S inv(L_kk)' and A_{k+1} = 2S - S inv(A_k) S (no p^3 GEMMs).
-        factor_ms = stage["factor_ms"] / k
-        fl_alg = float(p) ** 3 * (4.0 / 3.0 + m / 3.0 + 2.0 * (m - 1))
-        fl_exe = float(p) ** 3 * (1.0 + m / 3.0 + (m - 1) * 2.0 / 3.0)
-        roof_factor = {"kernel": "cond_factor (potrf_diag_kernel + dgemm_dmma_kernel trailing updates / trtri / syrk)", "bound": "tensor",
-                       "achieved": fl_alg / (factor_ms * 1e-3) / 1e12 if factor_ms > 0 else 0.0, "peak": fp64_peak, "unit": "TFLOP/s",
-                       "frac": (fl_alg / (factor_ms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and factor_ms > 0) else None,
-                       "algorithmic_flops_per_step": fl_alg, "executed_flops_per_step": fl_exe,
-                       "executed_tflops": fl_exe / (factor_ms * 1e-3) / 1e12 if factor_ms > 0 else 0.0, "stage_ms": factor_ms,
-                       "peak_source": "cuBLAS DGEMM 8192^3 measured in this run"}
-        dominant = roof_ccd if ccd_ms >= sample_ms else roof_gemm
-        other = roof_gemm if dominant is roof_ccd else roof_ccd
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (X 4 GB per GPU, 2 GB of factor blocks, "
-                           "200 MB resident inverse rewritten by every rank-256 pass)", "sweeps": stage["sweeps"], "refresh_every": a.refresh_every,
-                           "parallelism": f"rows sharded x{world}, solve replicated"},
-                "clocks": clocks, "gpu_launches": int(launches),
-                "stages_ms": {"solve_s": stage["solve_ms"] / k, "ccd_kernel": ccd_ms, "inverse_refresh": stage["init_ms"] / k,
-                              "cond_factor": stage["factor_ms"] / k, "sampling": sample_ms},
-                "solve_s_seconds": stage["solve_ms"] / k / 1e3,
-                "roofline": dominant, "roofline_secondary": other}
-        line["roofline_cond_factor"] = roof_factor
+        solve = {}
+        for mth in methods:
+            q = per[mth]
+            sw = max(1, q["sweeps"])
+            ccd_ms = q["ccd_ms"] / k
+            fl_alg = float(p) ** 3 * (4.0 / 3.0 + m / 3.0 + 2.0 * (m - 1))
+            fl_exe = float(p) ** 3 * (1.0 + m / 3.0 + (m - 1) * 2.0 / 3.0)
+            fms = q["factor_ms"] / k
+            solve[mth] = {"solve_s_seconds": q["solve_ms"] / k / 1e3, "sweeps": q["sweeps"], "ccd_kernel_ms": ccd_ms,
+                          "sweep_ms": ccd_ms / sw, "inverse_builds_ms": q["init_ms"] / k, "objective": q["objective"],
+                          "tensor_flops_per_solve": q["flops"] / k,
+                          "ccd_tflops_p3_per_sweep": float(p) ** 3 * sw / (ccd_ms * 1e-3) / 1e12 if ccd_ms > 0 else None,
+                          "algorithmic_bytes_per_sweep": q["ref_bytes"] / k / sw,
+                          "hbm_equivalent_gbs": q["ref_bytes"] / k / (ccd_ms * 1e-3) / 1e9 if ccd_ms > 0 else None,
+                          "cond_factor_ms": fms,
+                          "cond_factor_executed_tflops": fl_exe / (fms * 1e-3) / 1e12 if fms > 0 else None,
+                          "cond_factor_frac_of_peak_executed": (fl_exe / (fms * 1e-3) / 1e12 / fp64_peak) if (fp64_peak and fms > 0) else None,
+                          "cond_factor_survey_count_tflops": fl_alg / (fms * 1e-3) / 1e12 if fms > 0 else None,
+                          "mode": q.get("mode"), "owner_rank": res["owner"][methods.index(mth)]}
+        cfg = config_dict(a, world)
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg,
+                "parallelism": (f"rows sharded x{world} ({n_loc} per GPU), solves of the {len(methods)} methods on different ranks, "
+                                f"s + factor blocks NCCL-broadcast" if world > 1 else "single GPU"),
+                "clocks": res["clocks"], "gpu_launches": res["launches"],
+                "stages_ms": {"solve_and_factor_critical_path": max(per[x]["solve_ms"] + per[x]["factor_ms"] for x in methods) / k
+                              if world > 1 else sum(per[x]["solve_ms"] + per[x]["factor_ms"] for x in methods) / k,
+                              "broadcast": st["bcast_ms"] / k, "sampling": sample_ms},
+                "sampling_stage_rows_per_s": len(methods) * res["n_total"] / (sample_ms * 1e-3) if sample_ms > 0 else None,
+                "solve": solve, "solve_s_seconds": {x: solve[x]["solve_s_seconds"] for x in methods},
+                "roofline": roof_gemm}
         if stream_roof is not None:
             line["roofline_ccd_stream"] = stream_roof
         if e2e is not None:
             line["e2e"] = e2e
+        if alt is not None:
+            line["scaling_alt"] = alt
+        line.update(extra)
         if not a.no_cpu and world == 1:
-            v, det = cpu_reference_step(a, Sigma_h, max(1, stage["sweeps"]))
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": cpu_sample_desc(a), "detail": det}
+            threads = host_threads()
+            sweeps = {x: (per[x]["sweeps"] or golden_sweeps(x, p, m)) for x in methods}
+            v, det = cpu_reference_step(a, Sigma_h, sweeps, 24)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": cpu_sample_desc(a, threads, 24), "detail": det, "extrapolated": True}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        E.dist.barrier()
+        E.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -216,6 +216,15 @@ int kb_sample(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* 
               const double* SigmaInvS, const double* Lblocks, int32_t m, const double* Z,
               uint64_t seed, int64_t row_offset, double* Xko_out);
 
+/* `condition(X, μ, Σ, S; m)` (modelX.jl:96-122) in one call: conditional factor + sampling with every intermediate
+ * (Σ⁻¹S, the 2m−1 factor blocks) kept on the device.  S is a length-p vector (Diagonal(s), the single-knockoff path,
+ * modelX.jl:64) if s_is_diag, else dense p x p (group knockoffs, group.jl:125).  X / Xko_out may be a ROW SHARD of the
+ * data (n local rows, row_offset = global index of the first one): with the device RNG (Z == NULL) the union of the
+ * shards equals the single call on all rows. */
+int kb_condition(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* mu, const double* Sigma,
+                 const double* S, int32_t s_is_diag, int32_t m, const double* Z, uint64_t seed, int64_t row_offset,
+                 double* Xko_out);
+
 /* ---- one-shot entry points ----------------------------------------------------------------------
  * kb_modelx_gaussian_knockoffs replaces `modelX_gaussian_knockoffs(X, method, μ, Σ; m, kwargs...)`
  * (modelX.jl:53-66): s = solve_s(...), Xko = condition(X, μ, Σ, Diagonal(s); m); all
@@ -334,6 +343,41 @@ int kb_modelx_gaussian_rep_group_knockoffs(kb_ctx* ctx, const double* X, int64_t
                                            const double* Z, uint64_t seed, double* Xko_out, int64_t* group_reps_out,
                                            int64_t* n_reps_out, double* S11_out, double* D_out, double* obj_out,
                                            kb_group_info* info);
+
+/* ---- (8) several GPUs behind one handle (SURVEY 8b `kb_create(ctx**, const int* devs, int ndev)`, 8e) -----------------
+ * One host process, one kb_ctx and one host thread per listed device (a device may be listed more than once: two contexts
+ * on it).  Only the naturally data-parallel pieces are partitioned; a single CCD solve is sequential and stays on one device.
+ * All pointers are HOST pointers, as in the single-device calls above; results equal the single-device calls
+ * (sampling: bit for bit with the device RNG or an injected Z; Gram: to summation order). */
+typedef struct kb_multi kb_multi;
+int kb_create_multi(kb_multi** mc, const int* devices, int32_t ndev);
+void kb_destroy_multi(kb_multi* mc);
+int32_t kb_multi_size(const kb_multi* mc);
+kb_ctx* kb_multi_ctx(kb_multi* mc, int32_t i);              /* the i-th device's context (owned by mc) */
+const char* kb_multi_last_error(const kb_multi* mc);
+/* kb_gram with the rows of X sharded over the devices: per-device DMMA SYRK, then ONE all-reduce of the p x p sums done by
+ * a peer-to-peer kernel over NVLink (each device reduces one slice of every peer's buffer and stores it back to all). */
+int kb_multi_gram(kb_multi* mc, const double* X, int64_t n, int64_t p, int32_t center, double denom, double* G_out,
+                  double* colmean_out);
+/* kb_condition with the rows of X / Z / Xko sharded over the devices (no exchange: the RNG is keyed by the global row). */
+int kb_multi_condition(kb_multi* mc, const double* X, int64_t n, int64_t p, const double* mu, const double* Sigma,
+                       const double* S, int32_t s_is_diag, int32_t m, const double* Z, uint64_t seed, double* Xko_out);
+/* kb_modelx_gaussian_knockoffs: the solve on device 0, `condition` row-sharded over all devices. */
+int kb_multi_modelx_gaussian_knockoffs(kb_multi* mc, const double* X, int64_t n, int64_t p, const double* mu,
+                                       const double* Sigma, int32_t method, int32_t m, const kb_solve_opts* opts,
+                                       const double* s_init, const double* Z, uint64_t seed, double* Xko_out, double* s_out,
+                                       kb_solve_info* info);
+/* "replicas only": nprob independent solve_s problems on the same Sigma (methods[q], ms[q]) dealt round-robin to the devices
+ * (configs[2]: :sdp_ccd and :mvr side by side).  s_out: p x nprob column-major; infos: nprob entries or NULL. */
+int kb_multi_solve_s_many(kb_multi* mc, const double* Sigma, int64_t p, int32_t nprob, const int32_t* methods,
+                          const double* ms, const kb_solve_opts* opts, double* s_out, kb_solve_info* infos);
+/* solve_s_group on a BLOCK-DIAGONAL Sigma = blockdiag(Sigma_blocks[0..nblocks-1]) (no group straddles blocks; configs[3]):
+ * block b on device b mod ndev, lockstep sweeps, the global decisions of kb_solve_s_group_sharded reduced in-process.
+ * Sigma_blocks[b]: p_blocks[b] x p_blocks[b]; groups[b]: p_blocks[b] ids; S_out[b]: p_blocks[b] x p_blocks[b];
+ * obj_out: the summed objective; infos: nblocks entries or NULL. */
+int kb_multi_solve_s_group_blockdiag(kb_multi* mc, int32_t nblocks, const double* const* Sigma_blocks,
+                                     const int64_t* p_blocks, const int64_t* const* groups, int32_t method, double m,
+                                     const kb_group_opts* opts, double* const* S_out, double* obj_out, kb_group_info* infos);
 
 /* ---- test hooks (exercised by tests/, not part of the reference interface) -------------------- */
 /* C (M x N, col-major) = alpha * op(A) * op(B) + beta * C on the hand-written DMMA kernel.

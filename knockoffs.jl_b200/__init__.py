@@ -10,7 +10,7 @@ from .api import (Context, GaussianGroupKnockoff, GaussianKnockoff, make_group_o
                   modelX_gaussian_knockoffs, sample, solve_equi, solve_s, threshold, mk_threshold, MK_statistics,
                   marginal_stats, fit_marginal, MarginalKnockoffFilter, approx_modelX_gaussian_knockoffs,
                   ApproxGaussianKnockoff, feasible_gamma, choose_group_reps, cond_indep_corr,
-                  solve_s_graphical_group, modelX_gaussian_rep_group_knockoffs, GaussianRepGroupKnockoff)
+                  solve_s_graphical_group, modelX_gaussian_rep_group_knockoffs, GaussianRepGroupKnockoff, MultiContext)
 from . import harness, dev, dist  # noqa: F401
 
 __all__ = ["Context", "GaussianKnockoff", "KnockoffsError", "PosDefException", "cond_factor", "condition", "eigmin",

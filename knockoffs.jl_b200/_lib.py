@@ -75,6 +75,7 @@ SIGNATURES = {
     "kb_cond_factor": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "kb_cond_factor_dev": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "kb_sample": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _u64, _i64, _vp]),
+    "kb_condition": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _u64, _i64, _vp]),
     "kb_sample_dev": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _u64, _i64, _vp, _i64]),
     "kb_modelx_gaussian_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, C.POINTER(SolveOpts), _vp,
                                                _vp, _u64, _i64, _vp, _vp, C.POINTER(SolveInfo)]),
@@ -101,6 +102,17 @@ SIGNATURES = {
     "kb_modelx_gaussian_rep_group_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _d, _i32,
                                                          C.POINTER(GroupOpts), _vp, _i64, _vp, _i64, _vp, _u64, _vp, _vp,
                                                          C.POINTER(_i64), _vp, _vp, c_double_p, C.POINTER(GroupInfo)]),
+    "kb_create_multi": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int), _i32]),
+    "kb_destroy_multi": (None, [_vp]),
+    "kb_multi_size": (_i32, [_vp]),
+    "kb_multi_ctx": (_vp, [_vp, _i32]),
+    "kb_multi_last_error": (C.c_char_p, [_vp]),
+    "kb_multi_gram": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _d, _vp, _vp]),
+    "kb_multi_condition": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _u64, _vp]),
+    "kb_multi_modelx_gaussian_knockoffs": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _i32, _i32, C.POINTER(SolveOpts), _vp, _vp,
+                                                     _u64, _vp, _vp, C.POINTER(SolveInfo)]),
+    "kb_multi_solve_s_many": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, C.POINTER(SolveOpts), _vp, _vp]),
+    "kb_multi_solve_s_group_blockdiag": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _d, C.POINTER(GroupOpts), _vp, c_double_p, _vp]),
     "kb_test_dgemm": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_dgemm_dev": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_factor_band": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_int32)]),

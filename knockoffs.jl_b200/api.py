@@ -234,13 +234,30 @@ def sample(X, mu, SigmaInvS, Lblocks, m=1, Z=None, seed=0, row_offset=0, ctx: Op
     return Xko
 
 
-def condition(X, mu, Sigma, S, m=1, Z=None, seed=0, ctx: Optional[Context] = None):
-    """``condition(X, μ, Σ, S; m)`` -- src/modelX.jl:96-122."""
+def condition(X, mu, Sigma, S, m=1, Z=None, seed=0, row_offset=0, ctx: Optional[Context] = None):
+    """``condition(X, μ, Σ, S; m)`` -- src/modelX.jl:96-122, one library call (kb_condition): Σ⁻¹S and the factor
+    blocks never leave the device.  ``S``: vector (``Diagonal(s)``) or dense p x p.  ``X`` may be a row shard
+    (``row_offset`` = global index of its first row)."""
+    ctx = ctx or default_context()
     m = int(m)
     if m < 1:
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
-    SiS, Lb = cond_factor(Sigma, S, m=m, ctx=ctx)
-    return sample(X, mu, SiS, Lb, m=m, Z=Z, seed=seed, ctx=ctx)
+    X = _f(X)
+    n, p = X.shape
+    Sigma = _f(Sigma)
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    S = np.asarray(S, dtype=np.float64)
+    is_diag = S.ndim == 1
+    S = np.ascontiguousarray(S) if is_diag else _f(S)
+    if Sigma.shape != (p, p) or mu.shape != (p,) or S.shape != ((p,) if is_diag else (p, p)):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "dimension mismatch between X, mu, Sigma and S")
+    Zf = None if Z is None else _f(Z)
+    if Zf is not None and Zf.shape != (n, m * p):
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
+    Xko = np.empty((n, m * p), order="F")
+    check(ctx.h, ctx._lib.kb_condition(ctx.h, _ptr(X), n, p, _ptr(mu), _ptr(Sigma), _ptr(S), int(is_diag), m, _ptr(Zf),
+                                       int(seed), int(row_offset), _ptr(Xko)))
+    return Xko
 
 
 @dataclass
@@ -861,3 +878,124 @@ def hook_randn(seed, row_offset, n, ncols, ctx: Optional[Context] = None):
     Z = np.empty((n, ncols), order="F")
     check(ctx.h, ctx._lib.kb_test_randn(ctx.h, int(seed), int(row_offset), int(n), int(ncols), _ptr(Z)))
     return Z
+
+
+# ---- several GPUs behind one handle (kb_create_multi) -----------------------------------
+class MultiContext:
+    """``kb_create_multi(devices)``: one host process, one context + one host thread per listed device.  Rows of X are
+    sharded for the Gram (one peer-to-peer all-reduce over NVLink) and for ``condition``; independent solves and LD
+    blocks of a block-diagonal group problem are dealt to the devices; a single CCD solve stays on one device."""
+
+    def __init__(self, devices):
+        self._lib = _lib.load()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        rc = self._lib.kb_create_multi(C.byref(h), devs, len(devices))
+        if rc != 0:
+            raise _lib.KnockoffsError(rc, f"kb_create_multi({list(devices)}) failed (knockoffs_b200 has no CPU fallback)")
+        self.h = h
+        self.devices = [int(d) for d in devices]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.kb_destroy_multi(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = (self._lib.kb_multi_last_error(self.h) or b"").decode(errors="replace")
+            if rc == _lib.KB_ERR_NOT_PD:
+                raise _lib.PosDefException(rc, msg)
+            raise _lib.KnockoffsError(rc, msg)
+
+    @property
+    def launches(self) -> int:
+        return sum(int(self._lib.kb_launch_count(self._lib.kb_multi_ctx(self.h, i))) for i in range(len(self.devices)))
+
+    def gram(self, X, center=True, denom=None):
+        X = _f(X)
+        n, p = X.shape
+        G = np.empty((p, p), order="F")
+        mu = np.empty(p)
+        self._check(self._lib.kb_multi_gram(self.h, _ptr(X), n, p, int(bool(center)), float(denom or 0.0), _ptr(G), _ptr(mu)))
+        return G, mu
+
+    def condition(self, X, mu, Sigma, S, m=1, Z=None, seed=0):
+        X = _f(X)
+        n, p = X.shape
+        Sigma = _f(Sigma)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        S = np.asarray(S, dtype=np.float64)
+        is_diag = S.ndim == 1
+        S = np.ascontiguousarray(S) if is_diag else _f(S)
+        if Sigma.shape != (p, p) or mu.shape != (p,) or S.shape != ((p,) if is_diag else (p, p)):
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "dimension mismatch between X, mu, Sigma and S")
+        Zf = None if Z is None else _f(Z)
+        if Zf is not None and Zf.shape != (n, int(m) * p):
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {int(m) * p}")
+        Xko = np.empty((n, int(m) * p), order="F")
+        self._check(self._lib.kb_multi_condition(self.h, _ptr(X), n, p, _ptr(mu), _ptr(Sigma), _ptr(S), int(is_diag), int(m),
+                                                 _ptr(Zf), int(seed), _ptr(Xko)))
+        return Xko
+
+    def modelX_gaussian_knockoffs(self, X, method, mu, Sigma, m=1, Z=None, seed=0, s_init=None, **kwargs) -> "GaussianKnockoff":
+        X = _f(X)
+        n, p = X.shape
+        Sigma = _f(Sigma)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        if Sigma.shape != (p, p) or mu.shape != (p,):
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "dimension mismatch between X, mu and Sigma")
+        opts = make_opts(**kwargs)
+        info = SolveInfo()
+        Zf = None if Z is None else _f(Z)
+        si = None if s_init is None else np.ascontiguousarray(s_init, dtype=np.float64)
+        if si is not None and si.shape != (p,):
+            raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "s_init must have length p")
+        Xko = np.empty((n, int(m) * p), order="F")
+        s = np.empty(p)
+        self._check(self._lib.kb_multi_modelx_gaussian_knockoffs(self.h, _ptr(X), n, p, _ptr(mu), _ptr(Sigma), _method_id(method),
+                                                                 int(m), C.byref(opts), _ptr(si), _ptr(Zf), int(seed), _ptr(Xko),
+                                                                 _ptr(s), C.byref(info)))
+        Ssym = np.triu(Sigma) + np.triu(Sigma, 1).T
+        return GaussianKnockoff(X, Xko, s, Ssym, str(method).lstrip(":"), int(m), _info_dict(info, str(method).lstrip(":")))
+
+    def solve_s_many(self, Sigma, methods, ms, **kwargs):
+        """Independent ``solve_s(Σ, methods[q]; m = ms[q])`` problems dealt round-robin to the devices ("replicas only")."""
+        Sigma = _f(Sigma)
+        p = Sigma.shape[0]
+        nprob = len(methods)
+        mids = np.array([_method_id(x) for x in methods], dtype=np.int32)
+        mf = np.array([float(x) for x in ms], dtype=np.float64)
+        opts = make_opts(**kwargs)
+        infos = (SolveInfo * nprob)()
+        s = np.empty((p, nprob), order="F")
+        self._check(self._lib.kb_multi_solve_s_many(self.h, _ptr(Sigma), p, nprob, _ptr(mids), _ptr(mf), C.byref(opts), _ptr(s),
+                                                    C.cast(infos, C.c_void_p)))
+        return [s[:, q].copy() for q in range(nprob)], [_info_dict(infos[q], str(methods[q]).lstrip(":")) for q in range(nprob)]
+
+    def solve_s_group_blockdiag(self, Sigma_blocks, groups_blocks, method, m=1, **kwargs):
+        """``solve_s_group`` on Σ = blockdiag(Sigma_blocks): block b on device b mod ndev, lockstep sweeps, the reference's
+        global decisions reduced in-process.  Returns (list of S blocks, summed objective, list of info dicts)."""
+        nb = len(Sigma_blocks)
+        Sb = [_f(x) for x in Sigma_blocks]
+        gb = [np.ascontiguousarray(g, dtype=np.int64) for g in groups_blocks]
+        for x, g in zip(Sb, gb):
+            if x.ndim != 2 or x.shape[0] != x.shape[1] or g.shape != (x.shape[0],):
+                raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "every block needs a square Sigma and one group id per variable")
+        pb = np.array([x.shape[0] for x in Sb], dtype=np.int64)
+        out = [np.empty((x.shape[0], x.shape[0]), order="F") for x in Sb]
+        arr = lambda lst: (C.c_void_p * nb)(*[x.ctypes.data for x in lst])       # noqa: E731
+        opts = make_group_opts(**kwargs)
+        infos = (GroupInfo * nb)()
+        obj = C.c_double()
+        self._check(self._lib.kb_multi_solve_s_group_blockdiag(self.h, nb, arr(Sb), _ptr(pb), arr(gb), _group_method_id(method),
+                                                               float(m), C.byref(opts), arr(out), C.byref(obj),
+                                                               C.cast(infos, C.c_void_p)))
+        name = str(method).lstrip(":")
+        return out, obj.value, [_group_info_dict(infos[b], name) for b in range(nb)]

@@ -7,6 +7,7 @@
 #include "stats.cuh"
 #include "approx.cuh"
 #include "rep.cuh"
+#include "hostpipe.cuh"
 #include <algorithm>
 #include <unordered_map>
 #include <cstring>
@@ -15,52 +16,23 @@
 
 using namespace kb;
 
-namespace {
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
-int bad_ctx() { return KB_ERR_INVALID; }
-
-// column-major host matrix (rows x cols, ld hld) <-> device (ld dld)
-int h2d_matrix(kb_ctx* ctx, const double* h, long hld, double* d, long dld, long rows, long cols, cudaStream_t st) {
-    KB_CUDA(ctx, cudaMemcpy2DAsync(d, dld * sizeof(double), h, hld * sizeof(double), rows * sizeof(double), cols,
-                                   cudaMemcpyHostToDevice, st));
-    return KB_OK;
-}
-int d2h_matrix(kb_ctx* ctx, const double* d, long dld, double* h, long hld, long rows, long cols, cudaStream_t st) {
-    KB_CUDA(ctx, cudaMemcpy2DAsync(h, hld * sizeof(double), d, dld * sizeof(double), rows * sizeof(double), cols,
-                                   cudaMemcpyDeviceToHost, st));
-    return KB_OK;
-}
+namespace kb {
 
 // Marginal-statistic accumulators fed by the sampling pipeline chunk by chunk (fit_marginal: X̃ is consumed
 // while it is still on the device).
-struct StatsHook {
-    const double* dys;   // y_std, n doubles on the device
-    double* dacc_x;      // STATS_ACC * p
-    double* dacc_ko;     // STATS_ACC * m p
-};
 
 // Row-chunk pipeline for host-resident X / Z / X̃: H2D of chunk i+1 and D2H of chunk i-1 overlap the
 // GEMMs of chunk i (three streams, double-buffered device slabs).  Xko == NULL: X̃ is not copied back.
 int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const double* dmu, const double* dSiS,
                          const double* dLb, long ldo, int m, const double* Z, uint64_t seed, int64_t row_offset,
-                         double* Xko, const StatsHook* hook = nullptr) {
+                         double* Xko, const StatsHook* hook, long hld) {
     if (n <= 0) return KB_OK;
+    if (hld < n) hld = n;            // leading dimension of the HOST matrices X, Z, Xko (> n: a row shard of larger matrices)
     long chunk = ctx->sample_chunk_rows > 0 ? ctx->sample_chunk_rows : 4096;
     if (chunk > n) chunk = n;
     chunk = (chunk + 1) & ~1L;
     Scope sc(ctx);
+    StreamDrain drain(ctx);          // error paths: nothing may still be in flight when the slabs go back to the pool
     SamplePlan plan;
     KB_TRY(sample_plan_create(ctx, sc, p, m, dmu, dSiS, dLb, ldo, chunk, Z == nullptr, &plan));
     double *dXc[2], *dZc[2] = {nullptr, nullptr}, *dOut[2];
@@ -78,8 +50,8 @@ int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const doub
         const int b = (int)(i & 1);
         const long rows = std::min(chunk, n - r0);
         if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
-        KB_TRY(h2d_matrix(ctx, X + r0, n, dXc[b], chunk, rows, p, ctx->stream_h2d));
-        if (Z) KB_TRY(h2d_matrix(ctx, Z + r0, n, dZc[b], chunk, rows, (long)p * m, ctx->stream_h2d));
+        KB_TRY(h2d_matrix(ctx, X + r0, hld, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        if (Z) KB_TRY(h2d_matrix(ctx, Z + r0, hld, dZc[b], chunk, rows, (long)p * m, ctx->stream_h2d));
         KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
         KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
         if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[b], 0));
@@ -91,7 +63,7 @@ int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const doub
         }
         KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
         KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ev_comp[b], 0));
-        if (Xko) KB_TRY(d2h_matrix(ctx, dOut[b], chunk, Xko + r0, n, rows, (long)p * m, ctx->stream_d2h));
+        if (Xko) KB_TRY(d2h_matrix(ctx, dOut[b], chunk, Xko + r0, hld, rows, (long)p * m, ctx->stream_d2h));
         KB_CUDA(ctx, cudaEventRecord(ev_d2h[b], ctx->stream_d2h));
     }
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
@@ -100,10 +72,77 @@ int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const doub
     return KB_OK;
 }
 
+// G (ld x p, lower tiles) += X_rows' X_rows and colsum += 1' X_rows for `n` rows of a HOST matrix (leading dimension hld),
+// streamed in row chunks: H2D of chunk i + 1 overlaps the DMMA SYRK of chunk i.  dG / dcs must be zeroed by the caller.
+int gram_accumulate_host_rows(kb_ctx* ctx, const double* X, long n, long hld, int p, double* dG, long ld, double* dcs) {
+    if (n <= 0) return KB_OK;
+    Scope sc(ctx);
+    StreamDrain drain(ctx);
+    long chunk = 65536;
+    if (chunk > n) chunk = (n + 1) & ~1L;
+    double* dXc[2];
+    for (int b = 0; b < 2; ++b) KB_TRY(sc.alloc(&dXc[b], (size_t)chunk * p));
+    cudaEvent_t* ev_h2d = ctx->pipe_ev;
+    cudaEvent_t* ev_comp = ctx->pipe_ev + 2;
+    long i = 0;
+    for (long r0 = 0; r0 < n; r0 += chunk, ++i) {
+        const int b = (int)(i & 1);
+        const long rows = std::min(chunk, n - r0);
+        if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
+        KB_TRY(h2d_matrix(ctx, X + r0, hld, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
+        KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
+        KB_TRY(gram_partial_dev(ctx, dXc[b], rows, chunk, p, dG, ld, dcs, 1));
+        KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
+// condition(X, μ, Σ, S; m) (modelX.jl:96-122) on host matrices; X / Z / Xko are n rows of matrices with leading dimension hld.
+int condition_host(kb_ctx* ctx, const double* X, long n, long hld, int p, const double* mu, const double* Sigma, const double* S,
+                   int s_is_diag, int m, const double* Z, uint64_t seed, int64_t row_offset, double* Xko) {
+    if (m < 1) return set_error(ctx, KB_ERR_INVALID, "m should be 1 or larger but was %d.", m);   // modelX.jl:105
+    Scope sc(ctx);
+    const size_t pp = (size_t)p * p;
+    const size_t nblk = (size_t)(2 * m - 1);
+    double *dSig, *dS, *dmu, *dSiS, *dLb;
+    KB_TRY(sc.alloc(&dSig, pp));
+    KB_TRY(sc.alloc(&dS, s_is_diag ? (size_t)p : pp));
+    KB_TRY(sc.alloc(&dmu, p));
+    KB_TRY(sc.alloc(&dSiS, pp));
+    KB_TRY(sc.alloc(&dLb, pp * nblk));
+    KB_CUDA(ctx, cudaMemcpyAsync(dSig, Sigma, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dS, S, sizeof(double) * (s_is_diag ? (size_t)p : pp), cudaMemcpyHostToDevice, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(dmu, mu, sizeof(double) * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(cond_factor_dev(ctx, dSig, (long)p, p, dS, (long)p, s_is_diag, m, dSiS, dLb, (long)p));
+    return sample_host_pipeline(ctx, X, n, p, dmu, dSiS, dLb, (long)p, m, Z, seed, row_offset, Xko, nullptr, hld);
+}
+
+}  // namespace kb
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int bad_ctx() { return KB_ERR_INVALID; }
+
 // Accumulate the marginal-statistic sums of a HOST matrix A (n x ncols, ld n) against dys: row chunks, H2D of
 // chunk i+1 overlapping the reduction of chunk i.
 int host_marginal_accumulate(kb_ctx* ctx, const double* A, long n, long ncols, const double* dys, double* dacc) {
     Scope sc(ctx);
+    StreamDrain drain(ctx);
     long chunk = (long)(((size_t)256 << 20) / (sizeof(double) * (size_t)std::max(1L, ncols)));   // ~256 MB slabs
     chunk = std::max(1024L, std::min(chunk, n));
     if (chunk > n) chunk = n;
@@ -258,11 +297,17 @@ int kb_create(kb_ctx** out, int device) {
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
         ok = coop != 0;
     }
-    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // The main stream carries the latency-bound chains (single-CTA diagonal / sequential kernels); the auxiliary stream
+    // carries throughput work that runs beside them (look-ahead trailing updates, the blocked CCD's rank-256 passes).
+    // Highest priority for the main stream, lowest for the auxiliary one: a freed SM slot goes to the chain first.
+    int prio_least = 0, prio_greatest = 0;
+    if (ok) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    ok = ok && cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->stream_aux, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_least) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->ccd_ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
     for (int i = 0; i < 6 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->pipe_ev[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
@@ -285,6 +330,8 @@ void kb_destroy(kb_ctx* ctx) {
         if (ctx->stream_aux) { cudaStreamSynchronize(ctx->stream_aux); cudaStreamDestroy(ctx->stream_aux); }
         for (int i = 0; i < 2; ++i)
             if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
+        for (int i = 0; i < 3; ++i)
+            if (ctx->ccd_ev[i]) cudaEventDestroy(ctx->ccd_ev[i]);
         if (ctx->ev0) cudaEventDestroy(ctx->ev0);
         if (ctx->ev1) cudaEventDestroy(ctx->ev1);
         for (int i = 0; i < 6; ++i)
@@ -445,27 +492,12 @@ int kb_gram(kb_ctx* ctx, const double* X, int64_t n, int64_t p, int32_t center, 
     DeviceGuard g(ctx->device);
     Scope sc(ctx);
     const long ld = (p + 1) & ~1L;
-    long chunk = 65536;
-    if (chunk > n) chunk = (n + 1) & ~1L;
-    double *dG, *dcs, *dXc[2];
+    double *dG, *dcs;
     KB_TRY(sc.alloc(&dG, (size_t)ld * p));
     KB_TRY(sc.alloc(&dcs, p));
-    for (int b = 0; b < 2; ++b) KB_TRY(sc.alloc(&dXc[b], (size_t)chunk * p));
     KB_TRY(fill_zero(ctx, dG, (size_t)ld * p));
     KB_TRY(fill_zero(ctx, dcs, p));
-    cudaEvent_t* ev_h2d = ctx->pipe_ev;
-    cudaEvent_t* ev_comp = ctx->pipe_ev + 2;
-    long i = 0;
-    for (long r0 = 0; r0 < n; r0 += chunk, ++i) {
-        const int b = (int)(i & 1);
-        const long rows = std::min(chunk, (long)n - r0);
-        if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
-        KB_TRY(h2d_matrix(ctx, X + r0, n, dXc[b], chunk, rows, p, ctx->stream_h2d));
-        KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
-        KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
-        KB_TRY(gram_partial_dev(ctx, dXc[b], rows, chunk, (int)p, dG, ld, dcs, 1));
-        KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
-    }
+    KB_TRY(gram_accumulate_host_rows(ctx, X, (long)n, (long)n, (int)p, dG, ld, dcs));
     KB_TRY(gram_finish_dev(ctx, dG, ld, dcs, (long)n, (int)p, center, denom));
     KB_TRY(d2h_matrix(ctx, dG, ld, G_out, p, p, p, ctx->stream));
     if (colmean_out) KB_CUDA(ctx, cudaMemcpyAsync(colmean_out, dcs, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
@@ -482,6 +514,7 @@ int kb_cov_shrink_lw(kb_ctx* ctx, const double* X, int64_t n, int64_t p, double*
     if (!X || !Sigma_out || p < 1 || n < 2) return set_error(ctx, KB_ERR_INVALID, "cov_shrink_lw: bad arguments");
     DeviceGuard g(ctx->device);
     Scope sc(ctx);
+    StreamDrain drain(ctx);
     const long ld = (p + 1) & ~1L;
     long chunk = 32768;
     if (chunk > n) chunk = (n + 1) & ~1L;
@@ -585,6 +618,15 @@ int kb_sample(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* 
     KB_CUDA(ctx, cudaMemcpyAsync(dSiS, SigmaInvS, sizeof(double) * pp, cudaMemcpyHostToDevice, ctx->stream));
     KB_CUDA(ctx, cudaMemcpyAsync(dLb, Lblocks, sizeof(double) * pp * nblk, cudaMemcpyHostToDevice, ctx->stream));
     return sample_host_pipeline(ctx, X, (long)n, (int)p, dmu, dSiS, dLb, (long)p, m, Z, seed, row_offset, Xko_out);
+}
+
+int kb_condition(kb_ctx* ctx, const double* X, int64_t n, int64_t p, const double* mu, const double* Sigma,
+                 const double* S, int32_t s_is_diag, int32_t m, const double* Z, uint64_t seed, int64_t row_offset,
+                 double* Xko_out) {
+    if (!ctx) return bad_ctx();
+    if (!X || !mu || !Sigma || !S || !Xko_out || p < 1 || n < 0) return set_error(ctx, KB_ERR_INVALID, "condition: bad arguments");
+    DeviceGuard g(ctx->device);
+    return condition_host(ctx, X, (long)n, (long)n, (int)p, mu, Sigma, S, s_is_diag, m, Z, seed, row_offset, Xko_out);
 }
 
 // ---- one-shot ---------------------------------------------------------------------------------------

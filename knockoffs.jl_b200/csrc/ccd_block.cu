@@ -302,7 +302,7 @@ size_t ccd_block_work_doubles(int p) {
     const long ld = ccd_stream_ld(p);
     const long nslab = (ld + SLAB - 1) / SLAB;
     const long wo = (long)BW * outer_blocks();
-    return (size_t)ld * wo * 3              // PO, U_all, Uc_all
+    return (size_t)ld * wo * 5              // PO, 2 x (U_all, Uc_all): ping-pong so a rank-256 pass can run beside the next block
            + (size_t)nslab * BW * BW        // partial Grams
            + 2 * BW * BW + 64;              // TT
 }
@@ -316,16 +316,22 @@ int ccd_block_run(kb_ctx* ctx, const CcdParams& P, double* work) {
     const int NIN = outer_blocks();
     const long wo = (long)BW * NIN;
     double* PO = work;
-    double* Uall = PO + (size_t)ld * wo;
-    double* Ucall = Uall + (size_t)ld * wo;
-    double* Gpart = Ucall + (size_t)ld * wo;
+    double* Ubuf[2] = {PO + (size_t)ld * wo, PO + 3 * (size_t)ld * wo};
+    double* Ucbuf[2] = {PO + 2 * (size_t)ld * wo, PO + 4 * (size_t)ld * wo};
+    double* Gpart = PO + 5 * (size_t)ld * wo;
     double* TT = Gpart + (size_t)nslab * BW * BW;
     const bool mvr = (P.method == KB_METHOD_MVR);
     const size_t gsmem = (size_t)BW * GPITCH * sizeof(double);
     KB_CUDA(ctx, raise_max_dynamic_smem((const void*)ccd_block_gram_kernel, gsmem));
     const int nblk = (p + BW - 1) / BW;
-    // KB_BLOCK_PHASES=1: CUDA events around every phase of the sweep, per-phase totals on stderr (diagnostics)
+    // KB_BLOCK_PHASES=1: CUDA events around every phase of the sweep, per-phase totals on stderr (diagnostics; serial order)
     static const bool phases = getenv("KB_BLOCK_PHASES") != nullptr;
+    // Overlap (default): the rank-256 pass over the triangle of outer block ob runs on the low-priority auxiliary stream
+    // WHILE the main stream walks outer block ob + 1, whose panel is formed from the not-yet-updated triangle plus the
+    // same rank-256 term restricted to its 256 columns (a p x 256 x 256 GEMM).  The single-CTA sequential kernels then
+    // no longer leave the other SMs idle.  KB_CCD_OVERLAP=0 restores the serial order.
+    static const bool overlap_env = [] { const char* e = getenv("KB_CCD_OVERLAP"); return !(e && e[0] == '0'); }();
+    const bool overlap = overlap_env && !phases;
     enum { PH_GATHER, PH_GRAM, PH_SEQ, PH_PT, PH_INNER, PH_BIG, PH_N };
     std::vector<cudaEvent_t> ev;
     std::vector<int> ev_phase;
@@ -337,16 +343,24 @@ int ccd_block_run(kb_ctx* ctx, const CcdParams& P, double* work) {
         ev.push_back(e);
         ev_phase.push_back(phase);
     };
+    cudaStream_t s0 = ctx->stream, s1 = ctx->stream_aux;
+    cudaEvent_t ev_u = ctx->ccd_ev[0], ev_g = ctx->ccd_ev[1], ev_big = ctx->ccd_ev[2];
     // rows p..ld-1 of U_all / Uc_all are never written by the GEMMs (M = p) but are read as operand rows of the panel
     // update: keep them zero
-    KB_CUDA(ctx, cudaMemsetAsync(Uall, 0, sizeof(double) * 2 * (size_t)ld * wo, ctx->stream));
+    KB_CUDA(ctx, cudaMemsetAsync(Ubuf[0], 0, sizeof(double) * 4 * (size_t)ld * wo, s0));
     mark(-1);
-    for (int ob = 0; ob * NIN < nblk; ++ob) {
+    bool big_pending = false;
+    const int nouter = (nblk + NIN - 1) / NIN;
+    for (int ob = 0; ob < nouter; ++ob) {
         const int o0 = ob * NIN * BW;
         const int nin = (nblk - ob * NIN < NIN) ? nblk - ob * NIN : NIN;
-        ccd_block_gather_kernel<<<dim3(nslab, nin), BLK_THREADS, 0, ctx->stream>>>(P.M, ld, p, o0, PO);
-        ctx->launches++;
-        mark(PH_GATHER);
+        double* Uall = Ubuf[ob & 1];
+        double* Ucall = Ucbuf[ob & 1];
+        if (ob == 0 || !overlap) {
+            ccd_block_gather_kernel<<<dim3(nslab, nin), BLK_THREADS, 0, s0>>>(P.M, ld, p, o0, PO);
+            ctx->launches++;
+            mark(PH_GATHER);
+        }   // else: PO was formed at the end of the previous iteration
         for (int k = 0; k < nin; ++k) {
             const int blk = ob * NIN + k;
             const int j0 = blk * BW;
@@ -354,16 +368,16 @@ int ccd_block_run(kb_ctx* ctx, const CcdParams& P, double* work) {
             const int first = (blk == 0), last = (blk == nblk - 1);
             double* Pk = PO + (size_t)k * BW * ld;
             if (mvr) {
-                ccd_block_gram_kernel<<<nslab, BLK_THREADS, gsmem, ctx->stream>>>(Pk, ld, Gpart);
+                ccd_block_gram_kernel<<<nslab, BLK_THREADS, gsmem, s0>>>(Pk, ld, Gpart);
                 ctx->launches++;
                 mark(PH_GRAM);
             }
             if (P.method == KB_METHOD_MVR)
-                ccd_block_seq_kernel<KB_METHOD_MVR><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
+                ccd_block_seq_kernel<KB_METHOD_MVR><<<1, BLK_THREADS, 0, s0>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
             else if (P.method == KB_METHOD_MAXENT)
-                ccd_block_seq_kernel<KB_METHOD_MAXENT><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
+                ccd_block_seq_kernel<KB_METHOD_MAXENT><<<1, BLK_THREADS, 0, s0>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
             else
-                ccd_block_seq_kernel<KB_METHOD_SDP_CCD><<<1, BLK_THREADS, 0, ctx->stream>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
+                ccd_block_seq_kernel<KB_METHOD_SDP_CCD><<<1, BLK_THREADS, 0, s0>>>(P, j0, bw, Pk, Gpart, nslab, TT, first, last);
             ctx->launches++;
             KB_CUDA(ctx, cudaGetLastError());
             mark(PH_SEQ);
@@ -386,10 +400,34 @@ int ccd_block_run(kb_ctx* ctx, const CcdParams& P, double* work) {
                 mark(PH_INNER);
             }
         }
-        // M (lower tiles) += Uc_all · U_allᵀ   (K = 64 nin)
-        KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, nin * BW, 1.0, Ucall, ld, Uall, ld, 1.0, P.M, ld, 0, 1, 0));
-        mark(PH_BIG);
+        if (!overlap) {
+            // M (lower tiles) += Uc_all · U_allᵀ   (K = 64 nin)
+            KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, nin * BW, 1.0, Ucall, ld, Uall, ld, 1.0, P.M, ld, 0, 1, 0));
+            mark(PH_BIG);
+            continue;
+        }
+        if (ob + 1 < nouter) {
+            // next panel = (triangle with the passes up to ob − 1 applied) + this block's rank-256 term on its columns
+            const int o1 = (ob + 1) * NIN * BW;
+            const int nin1 = (nblk - (ob + 1) * NIN < NIN) ? nblk - (ob + 1) * NIN : NIN;
+            if (big_pending) KB_CUDA(ctx, cudaStreamWaitEvent(s0, ev_big, 0));
+            ccd_block_gather_kernel<<<dim3(nslab, nin1), BLK_THREADS, 0, s0>>>(P.M, ld, p, o1, PO);
+            ctx->launches++;
+            KB_CUDA(ctx, cudaEventRecord(ev_g, s0));
+            KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, nin1 * BW, nin * BW, 1.0, Ucall, ld, Uall + (size_t)o1, ld, 1.0, PO, ld));
+            KB_CUDA(ctx, cudaStreamWaitEvent(s1, ev_g, 0));
+        } else {
+            KB_CUDA(ctx, cudaEventRecord(ev_u, s0));
+            KB_CUDA(ctx, cudaStreamWaitEvent(s1, ev_u, 0));
+        }
+        ctx->stream = s1;
+        const int rc = gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, nin * BW, 1.0, Ucall, ld, Uall, ld, 1.0, P.M, ld, 0, 1, 0);
+        ctx->stream = s0;
+        KB_TRY(rc);
+        KB_CUDA(ctx, cudaEventRecord(ev_big, s1));
+        big_pending = true;
     }
+    if (big_pending) KB_CUDA(ctx, cudaStreamWaitEvent(s0, ev_big, 0));
     if (phases) {
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         double t[PH_N] = {0, 0, 0, 0, 0, 0};

@@ -29,6 +29,7 @@ struct kb_ctx {
     cudaStream_t stream_d2h = nullptr;
     cudaStream_t stream_aux = nullptr;   // look-ahead stream of the blocked Cholesky (trailing update || next panel)
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
+    cudaEvent_t ccd_ev[3] = {nullptr, nullptr, nullptr};   // blocked CCD: panel ready / gather done / rank-256 update done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string last_error;
     unsigned long long launches = 0;     // kernels launched by this library since creation

@@ -28,7 +28,7 @@ def lib():
         dp = C.POINTER(C.c_double)
         _LIB.ko_solve_ccd.restype = C.c_int
         _LIB.ko_solve_ccd.argtypes = [C.c_int, dp, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double,
-                                      C.c_double, C.c_double, C.c_int, dp, dp, C.POINTER(C.c_int), dp, dp, C.c_int, C.c_int64, dp]
+                                      C.c_double, C.c_double, C.c_int, dp, dp, C.POINTER(C.c_int), dp, dp, C.c_int, C.c_int64, dp, C.c_int64]
     return _LIB
 
 
@@ -37,8 +37,9 @@ def _dp(a):
 
 
 def solve_ccd(Sigma, method, m=1, niter=100, tol=1e-6, lambda_min=1e-6, sdp_lambda=0.5, sdp_mu=0.8,
-              robust=False, s_init=None, max_sweeps=0, max_coords=0, lapack_init=False):
-    """Returns dict(s, sweeps, trace, touched_entries, n_updates, rc)."""
+              robust=False, s_init=None, max_sweeps=0, max_coords=0, lapack_init=False, coord_stride=1):
+    """Returns dict(s, sweeps, trace, touched_entries, n_updates, rc).  coord_stride > 1: timing sample only (every
+    coord_stride-th coordinate of a sweep; s is then not a solution), see ccd_oracle.c."""
     Sigma = np.asfortranarray(Sigma, dtype=np.float64)
     p = Sigma.shape[0]
     s = np.zeros(p)
@@ -57,6 +58,6 @@ def solve_ccd(Sigma, method, m=1, niter=100, tol=1e-6, lambda_min=1e-6, sdp_lamb
     si = None if s_init is None else np.ascontiguousarray(s_init, dtype=np.float64)
     rc = lib().ko_solve_ccd(METHODS[method], _dp(Sigma), p, float(m), int(niter), float(tol), float(lambda_min),
                             float(sdp_lambda), float(sdp_mu), int(robust), _dp(si), _dp(s), C.byref(sw),
-                            _dp(trace), _dp(stats), int(max_sweeps), int(max_coords), _dp(U0))
+                            _dp(trace), _dp(stats), int(max_sweeps), int(max_coords), _dp(U0), int(coord_stride))
     return dict(s=s, sweeps=sw.value, trace=trace[:sw.value].copy(), touched_entries=stats[0],
                 n_updates=stats[1], loop_seconds=stats[2], rc=rc)

@@ -182,12 +182,15 @@ static inline double sym(const double *Sigma, int64_t p, int64_t i, int64_t j) {
  * U_init (optional): row-major upper factor of the initial matrix computed by the caller with LAPACK
  * dpotrf (what the reference's `cholesky` calls, utilities.jl:140); NULL = factor here.
  * stats[3]: [2] = seconds spent in the sweep loop (excludes the initial factorisation).
+ * coord_stride (> 1): TIMING SAMPLE ONLY -- visit every coord_stride-th coordinate of the sweep.  A coordinate's cost
+ * depends on its position j (the e_j solves and the rank-1 update touch rows j..p only), not on the state, so an evenly
+ * spaced subset x coord_stride is an unbiased estimate of one whole sweep; the returned s is NOT a solution.
  */
 int ko_solve_ccd(int method, const double *Sigma, int64_t p, double m, int niter, double tol,
                  double lambda_min, double sdp_lambda, double sdp_mu, int robust,
                  const double *s_init, double *s_out, int *sweeps_out, double *trace,
                  double *stats, int max_sweeps_override, int64_t max_coords_override,
-                 const double *U_init) {
+                 const double *U_init, int64_t coord_stride) {
     if (p < 1 || m < 1.0 || niter < 0) return -1;
     if (method == 2 && (!(sdp_mu >= 0.0 && sdp_mu <= 1.0) || !(sdp_lambda > 0.0))) return -1;
     if (method != 2 && !s_init) return -1;
@@ -218,7 +221,7 @@ int ko_solve_ccd(int method, const double *Sigma, int64_t p, double m, int niter
     for (int l = 0; l < niter && rc == 0; ++l) {
         ++sweeps;
         double max_delta = 0.0;
-        for (int64_t j = 0; j < p && rc == 0; ++j) {
+        for (int64_t j = 0; j < p && rc == 0; j += (coord_stride > 1 ? coord_stride : 1)) {
             if (max_coords_override > 0 && ncoord >= max_coords_override) { stop = 1; break; }
             ++ncoord;
             double delta;      /* signed change used for the factor: A <- A - delta e_j e_j' */
