@@ -123,7 +123,11 @@ class ClockSampler:
 def host_threads():
     """Use every host core for the BLAS stages, also under torchrun (which exports OMP_NUM_THREADS=1)."""
     n = os.cpu_count() or 1
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(n)                      # for BLAS copies that are loaded after this point
     try:
+        import scipy.linalg  # noqa: F401  (scipy ships its own OpenBLAS: it must be loaded before the limits are raised)
+        import scipy.linalg.blas  # noqa: F401
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=n)
     except Exception:
@@ -283,6 +287,12 @@ class Env:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def min_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.d)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return float(t.item())
+
     def max_over_ranks(self, x: float) -> float:
         t = self.torch.tensor([x], dtype=self.torch.float64, device=self.d)
         if self.world > 1:
@@ -411,6 +421,9 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
         for g in gathered:
             per.update(g)
         st["sample_ms"] = E.max_over_ranks(st["sample_ms"])
+        # a rank that arrives early WAITS inside the collective for the slowest solve: the transfer time itself is what the
+        # last rank to arrive measures, i.e. the minimum over ranks
+        st["bcast_ms"] = E.min_over_ranks(st["bcast_ms"])
     return out
 
 
@@ -561,7 +574,7 @@ def run_config5(E, a):
     ext.synchronize()
     ms = E.max_over_ranks(t0.elapsed_time(t1)) / K
     for k in t:
-        t[k] = E.max_over_ranks(t[k] / K)
+        t[k] = (E.min_over_ranks if k in ("bcast_ms", "allreduce_ms") else E.max_over_ranks)(t[k] / K)   # collectives: see run_pipeline
     out = {"workload": f"BASELINE configs[4]: dosage X n={n} rows in total (sharded x{world}), p={p}, Gram + NCCL all-reduce + :maxent + "
                        f"sampling m=1", "value": n / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "stages_ms": t,
            "gram_tflops_per_gpu": n_loc * p * (p + 1.0) / (t["gram_ms"] * 1e-3) / 1e12 if t["gram_ms"] > 0 else None,

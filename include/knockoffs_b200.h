@@ -120,6 +120,10 @@ void kb_default_solve_opts(kb_solve_opts* opts);
 uint64_t kb_launch_count(const kb_ctx* ctx);
 /* the cudaStream_t all of ctx's kernels are launched on (for CUDA-event timing by the caller) */
 void* kb_stream(const kb_ctx* ctx);
+/* SMs the context's auxiliary stream is confined to (CUDA green context: the latency-bound single-CTA chain kernels of
+ * the main stream always find a free SM beside the throughput work); 0 = no partition.  KB_GREEN_SMS=<n> sets the number of
+ * SMs kept free (default 16, 0 disables). */
+int32_t kb_aux_sms(const kb_ctx* ctx);
 int kb_synchronize(kb_ctx* ctx);
 /* release the device workspace the context keeps between calls */
 int kb_trim(kb_ctx* ctx);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "kb_default_solve_opts": (None, [C.POINTER(SolveOpts)]),
     "kb_launch_count": (_u64, [_vp]),
     "kb_stream": (_vp, [_vp]),
+    "kb_aux_sms": (_i32, [_vp]),
     "kb_synchronize": (C.c_int, [_vp]),
     "kb_trim": (C.c_int, [_vp]),
     "kb_set_sample_chunk_rows": (C.c_int, [_vp, _i64]),

@@ -62,6 +62,11 @@ class Context:
     def stream(self) -> int:
         return int(self._lib.kb_stream(self.h) or 0)
 
+    @property
+    def aux_sms(self) -> int:
+        """SMs the auxiliary stream is confined to (green context), 0 = no partition."""
+        return int(self._lib.kb_aux_sms(self.h))
+
     def set_sample_chunk_rows(self, rows: int):
         check(self.h, self._lib.kb_set_sample_chunk_rows(self.h, int(rows)))
 

@@ -8,11 +8,13 @@
 #include "approx.cuh"
 #include "rep.cuh"
 #include "hostpipe.cuh"
+#include <cuda.h>
 #include <algorithm>
 #include <unordered_map>
 #include <cstring>
 #include <cstdlib>
 #include <new>
+#include <thread>
 
 using namespace kb;
 
@@ -20,6 +22,62 @@ namespace kb {
 
 // Marginal-statistic accumulators fed by the sampling pipeline chunk by chunk (fit_marginal: X̃ is consumed
 // while it is still on the device).
+
+bool host_is_pageable(const void* ptr) {
+    if (!ptr) return false;
+    static const bool enabled = [] { const char* e = getenv("KB_PAGEABLE_STAGING"); return !(e && e[0] == '0'); }();
+    if (!enabled) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_pinned(kb_ctx* ctx, int idx, size_t bytes, double** out) {
+    if (ctx->pinned_cap[idx] < bytes) {
+        if (ctx->pinned[idx]) cudaFreeHost(ctx->pinned[idx]);
+        ctx->pinned[idx] = nullptr;
+        ctx->pinned_cap[idx] = 0;
+        KB_CUDA(ctx, cudaHostAlloc(&ctx->pinned[idx], bytes, cudaHostAllocDefault));
+        ctx->pinned_cap[idx] = bytes;
+    }
+    *out = static_cast<double*>(ctx->pinned[idx]);
+    return KB_OK;
+}
+
+void release_pinned(kb_ctx* ctx) {
+    for (int i = 0; i < 6; ++i) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        ctx->pinned[i] = nullptr;
+        ctx->pinned_cap[i] = 0;
+    }
+}
+
+void parallel_copy2d(double* dst, long dld, const double* src, long sld, long rows, long cols) {
+    static const int nthreads = [] {
+        const char* e = getenv("KB_HOST_COPY_THREADS");
+        int t = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 4;
+        return t < 1 ? 1 : (t > 16 ? 16 : t);
+    }();
+    auto work = [=](long c0, long c1) {
+        for (long c = c0; c < c1; ++c) memcpy(dst + c * dld, src + c * sld, sizeof(double) * (size_t)rows);
+    };
+    const int nt = (int)std::min<long>(nthreads, std::max<long>(1, (rows * cols) >> 16));
+    if (nt <= 1) { work(0, cols); return; }
+    std::vector<std::thread> th;
+    const long per = (cols + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) th.emplace_back(work, std::min(cols, per * t), std::min(cols, per * (t + 1)));
+    work(0, std::min(cols, per));
+    for (auto& x : th) x.join();
+}
+
+// Joins the scatter threads of the pageable-output path however the pipeline function is left.
+struct ThreadJoiner {
+    std::thread t[2];
+    ~ThreadJoiner() {
+        for (auto& x : t)
+            if (x.joinable()) x.join();
+    }
+};
 
 // Row-chunk pipeline for host-resident X / Z / X̃: H2D of chunk i+1 and D2H of chunk i-1 overlap the
 // GEMMs of chunk i (three streams, double-buffered device slabs).  Xko == NULL: X̃ is not copied back.
@@ -41,17 +99,42 @@ int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const doub
         if (Z) KB_TRY(sc.alloc(&dZc[b], (size_t)chunk * p * m));
         KB_TRY(sc.alloc(&dOut[b], (size_t)chunk * p * m));
     }
+    // PAGEABLE host matrices (what a Julia or numpy caller passes): cudaMemcpy2DAsync from / to pageable memory is staged
+    // by the driver synchronously and chunk by chunk.  Instead the rows of a chunk are gathered into / scattered from pinned
+    // bounce buffers by a few host threads (32 KB contiguous per column), so the copies stay asynchronous and overlap the GEMMs.
+    const bool x_page = host_is_pageable(X), z_page = Z && host_is_pageable(Z), o_page = Xko && host_is_pageable(Xko);
+    double *sX[2] = {nullptr, nullptr}, *sZ[2] = {nullptr, nullptr}, *sO[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; ++b) {
+        if (x_page) KB_TRY(ensure_pinned(ctx, b, sizeof(double) * (size_t)chunk * p, &sX[b]));
+        if (z_page) KB_TRY(ensure_pinned(ctx, 2 + b, sizeof(double) * (size_t)chunk * p * m, &sZ[b]));
+        if (o_page) KB_TRY(ensure_pinned(ctx, 4 + b, sizeof(double) * (size_t)chunk * p * m, &sO[b]));
+    }
+    ThreadJoiner scatter;                      // declared after `drain`: joined first, then the streams are drained
     cudaEvent_t* ev_h2d = ctx->pipe_ev;        // [2]
     cudaEvent_t* ev_comp = ctx->pipe_ev + 2;   // [2]
     cudaEvent_t* ev_d2h = ctx->pipe_ev + 4;    // [2]
+    const int device = ctx->device;
     // the plan's constants were enqueued on ctx->stream; the copy streams only touch their own slabs
     long i = 0;
     for (long r0 = 0; r0 < n; r0 += chunk, ++i) {
         const int b = (int)(i & 1);
         const long rows = std::min(chunk, n - r0);
         if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
-        KB_TRY(h2d_matrix(ctx, X + r0, hld, dXc[b], chunk, rows, p, ctx->stream_h2d));
-        if (Z) KB_TRY(h2d_matrix(ctx, Z + r0, hld, dZc[b], chunk, rows, (long)p * m, ctx->stream_h2d));
+        if ((x_page || z_page) && i >= 2) KB_CUDA(ctx, cudaEventSynchronize(ev_h2d[b]));   // bounce buffers b are free again
+        if (x_page) {
+            parallel_copy2d(sX[b], chunk, X + r0, hld, rows, p);
+            KB_TRY(h2d_matrix(ctx, sX[b], chunk, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        } else {
+            KB_TRY(h2d_matrix(ctx, X + r0, hld, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        }
+        if (Z) {
+            if (z_page) {
+                parallel_copy2d(sZ[b], chunk, Z + r0, hld, rows, (long)p * m);
+                KB_TRY(h2d_matrix(ctx, sZ[b], chunk, dZc[b], chunk, rows, (long)p * m, ctx->stream_h2d));
+            } else {
+                KB_TRY(h2d_matrix(ctx, Z + r0, hld, dZc[b], chunk, rows, (long)p * m, ctx->stream_h2d));
+            }
+        }
         KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
         KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
         if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_d2h[b], 0));
@@ -63,9 +146,26 @@ int sample_host_pipeline(kb_ctx* ctx, const double* X, long n, int p, const doub
         }
         KB_CUDA(ctx, cudaEventRecord(ev_comp[b], ctx->stream));
         KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_d2h, ev_comp[b], 0));
-        if (Xko) KB_TRY(d2h_matrix(ctx, dOut[b], chunk, Xko + r0, hld, rows, (long)p * m, ctx->stream_d2h));
-        KB_CUDA(ctx, cudaEventRecord(ev_d2h[b], ctx->stream_d2h));
+        if (Xko && o_page) {
+            if (scatter.t[b].joinable()) scatter.t[b].join();                 // chunk i − 2 has left bounce buffer b
+            KB_TRY(d2h_matrix(ctx, dOut[b], chunk, sO[b], chunk, rows, (long)p * m, ctx->stream_d2h));
+            KB_CUDA(ctx, cudaEventRecord(ev_d2h[b], ctx->stream_d2h));
+            cudaEvent_t evb = ev_d2h[b];
+            double* src = sO[b];
+            double* dst = Xko + r0;
+            const long cols = (long)p * m;
+            scatter.t[b] = std::thread([=] {
+                cudaSetDevice(device);
+                cudaEventSynchronize(evb);
+                parallel_copy2d(dst, hld, src, chunk, rows, cols);
+            });
+        } else {
+            if (Xko) KB_TRY(d2h_matrix(ctx, dOut[b], chunk, Xko + r0, hld, rows, (long)p * m, ctx->stream_d2h));
+            KB_CUDA(ctx, cudaEventRecord(ev_d2h[b], ctx->stream_d2h));
+        }
     }
+    for (auto& t : scatter.t)
+        if (t.joinable()) t.join();
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_h2d));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream_d2h));
@@ -78,10 +178,14 @@ int gram_accumulate_host_rows(kb_ctx* ctx, const double* X, long n, long hld, in
     if (n <= 0) return KB_OK;
     Scope sc(ctx);
     StreamDrain drain(ctx);
-    long chunk = 65536;
+    const bool x_page = host_is_pageable(X);
+    long chunk = x_page ? 16384 : 65536;       // pageable input goes through pinned bounce buffers: smaller chunks
     if (chunk > n) chunk = (n + 1) & ~1L;
-    double* dXc[2];
-    for (int b = 0; b < 2; ++b) KB_TRY(sc.alloc(&dXc[b], (size_t)chunk * p));
+    double *dXc[2], *sX[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; ++b) {
+        KB_TRY(sc.alloc(&dXc[b], (size_t)chunk * p));
+        if (x_page) KB_TRY(ensure_pinned(ctx, b, sizeof(double) * (size_t)chunk * p, &sX[b]));
+    }
     cudaEvent_t* ev_h2d = ctx->pipe_ev;
     cudaEvent_t* ev_comp = ctx->pipe_ev + 2;
     long i = 0;
@@ -89,7 +193,13 @@ int gram_accumulate_host_rows(kb_ctx* ctx, const double* X, long n, long hld, in
         const int b = (int)(i & 1);
         const long rows = std::min(chunk, n - r0);
         if (i >= 2) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_h2d, ev_comp[b], 0));
-        KB_TRY(h2d_matrix(ctx, X + r0, hld, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        if (x_page) {
+            if (i >= 2) KB_CUDA(ctx, cudaEventSynchronize(ev_h2d[b]));
+            parallel_copy2d(sX[b], chunk, X + r0, hld, rows, p);
+            KB_TRY(h2d_matrix(ctx, sX[b], chunk, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        } else {
+            KB_TRY(h2d_matrix(ctx, X + r0, hld, dXc[b], chunk, rows, p, ctx->stream_h2d));
+        }
         KB_CUDA(ctx, cudaEventRecord(ev_h2d[b], ctx->stream_h2d));
         KB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_h2d[b], 0));
         KB_TRY(gram_partial_dev(ctx, dXc[b], rows, chunk, p, dG, ld, dcs, 1));
@@ -137,6 +247,79 @@ struct DeviceGuard {
 };
 
 int bad_ctx() { return KB_ERR_INVALID; }
+
+// SM partition for the auxiliary stream (CUDA green context, driver API resolved through the runtime -- no libcuda link):
+// stream_aux may use all SMs but `reserve` of them, so the single-CTA chain kernels of the main stream (blocked CCD
+// sequential kernel: 256 threads x 192 registers, i.e. it needs an SM that holds NO tensor-core GEMM CTA; Cholesky diagonal
+// kernel) always find a free SM while a rank-256 pass / trailing update runs beside them.  Without the partition the block
+// scheduler back-fills every freed slot with GEMM CTAs and the chain kernel waits for the GEMM grid to drain.
+// Returns false (and leaves ctx untouched) if the driver refuses any step; the caller then creates an ordinary stream.
+bool make_green_aux_stream(kb_ctx* ctx, int reserve, int priority) {
+    auto get = [](const char* name) -> void* {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint(name, &f, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return f;
+    };
+    typedef CUresult (*fn_devget)(CUdevice*, int);
+    typedef CUresult (*fn_getres)(CUdevice, CUdevResource*, CUdevResourceType);
+    typedef CUresult (*fn_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+    typedef CUresult (*fn_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+    typedef CUresult (*fn_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*fn_gstream)(CUstream*, CUgreenCtx, unsigned int, int);
+    typedef CUresult (*fn_gdestroy)(CUgreenCtx);
+    auto devget = (fn_devget)get("cuDeviceGet");
+    auto getres = (fn_getres)get("cuDeviceGetDevResource");
+    auto split = (fn_split)get("cuDevSmResourceSplitByCount");
+    auto mkdesc = (fn_desc)get("cuDevResourceGenerateDesc");
+    auto gcreate = (fn_gcreate)get("cuGreenCtxCreate");
+    auto gstream = (fn_gstream)get("cuGreenCtxStreamCreate");
+    auto gdestroy = (fn_gdestroy)get("cuGreenCtxDestroy");
+    if (!devget || !getres || !split || !mkdesc || !gcreate || !gstream || !gdestroy) return false;
+    CUdevice dev;
+    if (devget(&dev, ctx->device) != CUDA_SUCCESS) return false;
+    CUdevResource all, grp[1], rest;
+    if (getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    unsigned int ngroups = 1;
+    if (split(grp, &ngroups, &all, &rest, 0, (unsigned)reserve) != CUDA_SUCCESS || ngroups != 1) return false;
+    if (rest.sm.smCount < 32) return false;
+    CUdevResourceDesc desc;
+    if (mkdesc(&desc, &rest, 1) != CUDA_SUCCESS) return false;
+    CUgreenCtx g;
+    if (gcreate(&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    CUstream st;
+    if (gstream(&st, g, CU_STREAM_NON_BLOCKING, priority) != CUDA_SUCCESS) { gdestroy(g); return false; }
+    // events of the primary context must order work across the two kinds of streams: check it once, here
+    cudaEvent_t e = nullptr;
+    bool ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventRecord(e, (cudaStream_t)st) == cudaSuccess;
+    ok = ok && cudaStreamWaitEvent(ctx->stream, e, 0) == cudaSuccess;
+    ok = ok && cudaEventRecord(e, ctx->stream) == cudaSuccess;
+    ok = ok && cudaStreamWaitEvent((cudaStream_t)st, e, 0) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize((cudaStream_t)st) == cudaSuccess && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    if (e) cudaEventDestroy(e);
+    if (!ok) {
+        cudaGetLastError();
+        cudaStreamDestroy((cudaStream_t)st);
+        gdestroy(g);
+        return false;
+    }
+    ctx->stream_aux = (cudaStream_t)st;
+    ctx->green_ctx = (void*)g;
+    ctx->aux_sms = (int)rest.sm.smCount;
+    return true;
+}
+void destroy_green(kb_ctx* ctx) {
+    if (!ctx->green_ctx) return;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &f, cudaEnableDefault, &st) == cudaSuccess && f)
+        ((CUresult(*)(CUgreenCtx))f)((CUgreenCtx)ctx->green_ctx);
+    ctx->green_ctx = nullptr;
+}
 
 // Accumulate the marginal-statistic sums of a HOST matrix A (n x ncols, ld n) against dys: row chunks, H2D of
 // chunk i+1 overlapping the reduction of chunk i.
@@ -305,7 +488,13 @@ int kb_create(kb_ctx** out, int device) {
     ok = ok && cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_least) == cudaSuccess;
+    if (ok) {
+        // KB_GREEN_SMS = SMs kept free of auxiliary-stream work (default 16; 0 = no partition)
+        const char* e = getenv("KB_GREEN_SMS");
+        const int reserve = e ? atoi(e) : 16;
+        if (!(reserve > 0 && make_green_aux_stream(ctx, reserve, prio_least)))
+            ok = cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_least) == cudaSuccess;
+    }
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->ccd_ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
@@ -325,9 +514,11 @@ void kb_destroy(kb_ctx* ctx) {
         if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
         for (auto& b : ctx->pool_free) cudaFree(b.ptr);
         ctx->pool_free.clear();
+        release_pinned(ctx);
         if (ctx->stream_h2d) cudaStreamDestroy(ctx->stream_h2d);
         if (ctx->stream_d2h) cudaStreamDestroy(ctx->stream_d2h);
         if (ctx->stream_aux) { cudaStreamSynchronize(ctx->stream_aux); cudaStreamDestroy(ctx->stream_aux); }
+        destroy_green(ctx);
         for (int i = 0; i < 2; ++i)
             if (ctx->aux_ev[i]) cudaEventDestroy(ctx->aux_ev[i]);
         for (int i = 0; i < 3; ++i)
@@ -344,6 +535,7 @@ const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->last_error.c_st
 void kb_default_solve_opts(kb_solve_opts* o) { if (o) default_solve_opts(o); }
 uint64_t kb_launch_count(const kb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* kb_stream(const kb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int32_t kb_aux_sms(const kb_ctx* ctx) { return ctx ? ctx->aux_sms : 0; }
 int kb_set_sample_chunk_rows(kb_ctx* ctx, int64_t rows) {
     if (!ctx || rows < 0) return KB_ERR_INVALID;
     ctx->sample_chunk_rows = rows;
@@ -356,6 +548,7 @@ int kb_trim(kb_ctx* ctx) {
     for (auto& b : ctx->pool_free) cudaFree(b.ptr);
     ctx->pool_free.clear();
     ctx->pool_bytes = 0;
+    release_pinned(ctx);
     return KB_OK;
 }
 int kb_synchronize(kb_ctx* ctx) {

@@ -16,6 +16,14 @@ static inline int d2h_matrix(kb_ctx* ctx, const double* d, long dld, double* h, 
     return KB_OK;
 }
 
+// true if `ptr` is ordinary pageable host memory (neither cudaHostAlloc'ed nor cudaHostRegister'ed nor managed)
+bool host_is_pageable(const void* ptr);
+// pinned bounce buffer `idx` of ctx with at least `bytes` bytes (grown on demand, kept between calls)
+int ensure_pinned(kb_ctx* ctx, int idx, size_t bytes, double** out);
+void release_pinned(kb_ctx* ctx);
+// dst(ld dld) <- src(ld sld), rows x cols doubles, split by columns over a few host threads
+void parallel_copy2d(double* dst, long dld, const double* src, long sld, long rows, long cols);
+
 // Declared first in a function that enqueues work on ctx's three pipeline streams: whatever way the function is left
 // (KB_TRY / KB_CUDA early returns included), every stream is drained BEFORE the Scope declared above it hands the device
 // slabs back to the pool and before the caller may release the host buffers the copies read or write.

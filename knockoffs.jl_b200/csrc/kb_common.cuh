@@ -28,6 +28,8 @@ struct kb_ctx {
     cudaStream_t stream_h2d = nullptr;   // copy streams for the row-chunk pipeline
     cudaStream_t stream_d2h = nullptr;
     cudaStream_t stream_aux = nullptr;   // look-ahead stream of the blocked Cholesky (trailing update || next panel)
+    void* green_ctx = nullptr;           // CUgreenCtx that stream_aux belongs to (SM partition), or NULL
+    int aux_sms = 0;                     // SMs stream_aux may use (0 = all: no partition)
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     cudaEvent_t ccd_ev[3] = {nullptr, nullptr, nullptr};   // blocked CCD: panel ready / gather done / rank-256 update done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -44,6 +46,10 @@ struct kb_ctx {
     std::vector<PoolBlock> pool_free;
     size_t pool_bytes = 0;
     cudaEvent_t pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // pinned bounce buffers for PAGEABLE host matrices (a Julia Matrix{Float64} / numpy array is pageable): kept between calls,
+    // released by kb_trim / kb_destroy.  [0,1] input X chunks, [2,3] input Z chunks, [4,5] output chunks
+    void* pinned[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t pinned_cap[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace kb {

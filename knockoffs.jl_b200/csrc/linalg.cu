@@ -20,9 +20,11 @@ int set_error(kb_ctx* ctx, int code, const char* fmt, ...) {
 
 cudaError_t raise_max_dynamic_smem(const void* func, size_t bytes) {
     static std::mutex mu;
-    static std::map<const void*, size_t> current;
+    static std::map<std::pair<int, const void*>, size_t> current;     // the attribute is per DEVICE and per function
+    int dev = 0;
+    cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
-    size_t& cur = current[func];
+    size_t& cur = current[std::make_pair(dev, func)];
     if (bytes <= cur || bytes <= 48 * 1024) return cudaSuccess;
     const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) cur = bytes;

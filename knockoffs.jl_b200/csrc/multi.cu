@@ -14,6 +14,7 @@
 #include "hostpipe.cuh"
 #include <algorithm>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -90,12 +91,17 @@ int run_on_all(kb_multi* mc, int nthreads, const std::function<int(int)>& fn, co
             rc[(size_t)i] = fn(i);
         });
     for (auto& t : th) t.join();
+    // report the root cause, not the "another device failed" echo of the threads that were waiting for it
+    int first = -1;
     for (int i = 0; i < nthreads; ++i)
         if (rc[(size_t)i] != KB_OK) {
-            mc->last_error = "device thread " + std::to_string(i) + ": " + ctx_of(i)->last_error;
-            return rc[(size_t)i];
+            if (first < 0) first = i;
+            if (ctx_of(i)->last_error.find("another device failed") == std::string::npos &&
+                ctx_of(i)->last_error.find("reduce hook failed") == std::string::npos) { first = i; break; }
         }
-    return KB_OK;
+    if (first < 0) return KB_OK;
+    mc->last_error = "device thread " + std::to_string(first) + ": " + ctx_of(first)->last_error;
+    return rc[(size_t)first];
 }
 
 int merr(kb_multi* mc, int code, const char* msg) {
@@ -231,9 +237,20 @@ int kb_multi_gram(kb_multi* mc, const double* X, int64_t n, int64_t p, int32_t c
             // slice i of the p x p sums (and of the column sums): peer loads + peer stores over NVLink
             const long per = ((count / nd) + 1) & ~1L;
             const long e0 = std::min(count, per * i), e1 = (i == nd - 1) ? count : std::min(count, per * (i + 1));
+            static const bool trace = getenv("KB_MULTI_TRACE") != nullptr;
+            if (trace) cudaEventRecord(ctx->ev0, ctx->stream);
             if (e1 > e0) {
                 p2p_allreduce_slice_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(G, e0, e1);
                 ctx->launches++;
+            }
+            if (trace) {
+                cudaEventRecord(ctx->ev1, ctx->stream);
+                cudaEventSynchronize(ctx->ev1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+                // each device reads its slice from nd buffers and writes it to nd buffers
+                fprintf(stderr, "[multi_gram dev %d] p2p all-reduce slice: %ld doubles x %d peers, %.3f ms, %.1f GB/s read + %.1f GB/s written\n",
+                        ctx->device, e1 - e0, nd, ms, (e1 - e0) * 8.0 * nd / ms / 1e6, (e1 - e0) * 8.0 * nd / ms / 1e6);
             }
             if (i == 0) {
                 p2p_allreduce_slice_kernel<<<8, 256, 0, ctx->stream>>>(CS, 0, (long)p);

@@ -595,3 +595,38 @@ def _blockdiag_rect(V1, V2):
     out[:V1.shape[0], :V1.shape[1]] = V1
     out[V1.shape[0]:, V1.shape[1]:] = V2
     return out
+
+
+def test_pinned_and_pageable_host_buffers_give_identical_results(kb, ctx):
+    """The host-pointer entry points detect PAGEABLE matrices (numpy / Julia arrays) and route them through pinned bounce
+    buffers; page-locked buffers are copied directly.  Same bits either way, ragged last chunk and m > 1 included."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(31)
+    n, p, m = 9001, 96, 2
+    Sigma = toeplitz(p, 0.4)
+    X = np.asfortranarray(rng.standard_normal((n, p)) @ np.linalg.cholesky(Sigma).T)
+    mu = rng.standard_normal(p) * 0.1
+    s = kb.solve_s(Sigma, "maxent", m=m, ctx=ctx)
+    Z = np.asfortranarray(rng.standard_normal((n, m * p)))
+    ctx.set_sample_chunk_rows(2048)
+    try:
+        outs = []
+        for pinned in (False, True):
+            if pinned:
+                Xt = torch.empty((p, n), dtype=torch.float64, pin_memory=True); Xt.numpy()[:] = X.T
+                Zt = torch.empty((m * p, n), dtype=torch.float64, pin_memory=True); Zt.numpy()[:] = Z.T
+                Ot = torch.empty((m * p, n), dtype=torch.float64, pin_memory=True)
+                xp, zp, op = Xt.data_ptr(), Zt.data_ptr(), Ot.data_ptr()
+            else:
+                O = np.empty((n, m * p), order="F")
+                xp, zp, op = X.ctypes.data, Z.ctypes.data, O.ctypes.data
+            for zz in (zp, None):
+                rc = ctx._lib.kb_condition(ctx.h, xp, n, p, mu.ctypes.data, Sigma.ctypes.data, s.ctypes.data, 1, m, zz, 5, 0, op)
+                kb.api.check(ctx.h, rc)
+                outs.append(Ot.numpy().T.copy() if pinned else O.copy())
+        assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+        want = ko.condition(X, mu, Sigma, s, m=m, Z=Z)
+        assert np.max(np.abs(outs[0] - want)) < XKO_TOL
+    finally:
+        ctx.set_sample_chunk_rows(0)
