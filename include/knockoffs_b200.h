@@ -60,7 +60,7 @@ typedef struct {
     int32_t verbose;     /* per-sweep trace is always returned in kb_solve_info */
     int32_t mode;        /* KB_MODE_* */
     int32_t refresh_every; /* rebuild the device-resident inverse from the current diagonal every k sweeps
-                              (-1 = default: 1 in KB_MODE_STREAM, 4 in KB_MODE_BLOCK; 0 = never) */
+                              (-1 = default: 1 in KB_MODE_STREAM; in KB_MODE_BLOCK after the first sweep, then every 8th; 0 = never) */
     int32_t objective;   /* 1 (default): evaluate kb_solve_info.objective at exit (one extra factorisation of κΣ − S);
                             0: skip it */
 } kb_solve_opts;
@@ -127,6 +127,14 @@ int32_t kb_aux_sms(const kb_ctx* ctx);
 int kb_synchronize(kb_ctx* ctx);
 /* release the device workspace the context keeps between calls */
 int kb_trim(kb_ctx* ctx);
+/* `condition` factors with cholesky(PositiveFactorizations.Positive, ·) (modelX.jl:111, :120), which never throws: a
+ * non-positive pivot is replaced instead.  That package is not vendored with the reference, so its algorithm is RESTATED
+ * from its published description (csrc/positive.cu; parity unpinned) and is opt-in: on != 0 makes the conditional-factor
+ * stage fall back to it when the ordinary Cholesky fails (e.g. :equi, whose κΣ − S is exactly singular); the default
+ * (off) keeps returning KB_ERR_NOT_PD.  For positive definite input both give the ordinary factor.
+ * kb_positive_modified: pivots replaced by the last kb_cond_factor / kb_condition / one-shot call on ctx (0 = none). */
+int kb_set_positive_cholesky(kb_ctx* ctx, int32_t on);
+int32_t kb_positive_modified(const kb_ctx* ctx);
 /* rows per chunk of the sampling pipeline (0 = default 4096) */
 int kb_set_sample_chunk_rows(kb_ctx* ctx, int64_t rows);
 
@@ -399,6 +407,8 @@ int kb_test_factor_band(kb_ctx* ctx, const double* Lblocks, int64_t p, int32_t m
 /* lower Cholesky factor (potrf) and inverse of an SPD matrix on the device kernels. */
 int kb_test_potrf(kb_ctx* ctx, const double* A, int64_t p, double* L_out);
 int kb_test_spd_inverse(kb_ctx* ctx, const double* A, int64_t p, double* Ainv_out);
+/* the restated cholesky(Positive, Symmetric(A)) of csrc/positive.cu: L_out p x p lower, d_out p signs (+1 / -1 / 0). */
+int kb_test_potrf_positive(kb_ctx* ctx, const double* A, int64_t p, double* L_out, double* d_out, int32_t* modified_out);
 /* n x ncols block of the device Gaussian stream (what kb_sample uses when Z == NULL). */
 int kb_test_randn(kb_ctx* ctx, uint64_t seed, int64_t row_offset, int64_t n, int64_t ncols, double* Z_out);
 

@@ -6,7 +6,7 @@ The directory is named ``knockoffs.jl_b200`` (not importable by name because of 
 from ._lib import KnockoffsError, PosDefException, LIB_PATH, SIGNATURES, load  # noqa: F401
 from .api import (Context, GaussianGroupKnockoff, GaussianKnockoff, make_group_opts, modelX_gaussian_group_knockoffs,
                   solve_s_group, solve_s_group_sharded, cond_factor, condition, cov_shrink_lw, default_context, dense_factor_from_blocks,  # noqa: F401
-                  eigmin, gram, hook_dgemm, hook_factor_band, hook_potrf, hook_randn, hook_spd_inverse, make_opts,
+                  eigmin, gram, hook_dgemm, hook_factor_band, hook_potrf, hook_potrf_positive, hook_randn, hook_spd_inverse, make_opts,
                   modelX_gaussian_knockoffs, sample, solve_equi, solve_s, threshold, mk_threshold, MK_statistics,
                   marginal_stats, fit_marginal, MarginalKnockoffFilter, approx_modelX_gaussian_knockoffs,
                   ApproxGaussianKnockoff, feasible_gamma, choose_group_reps, cond_indep_corr,

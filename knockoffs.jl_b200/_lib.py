@@ -56,6 +56,8 @@ SIGNATURES = {
     "kb_stream": (_vp, [_vp]),
     "kb_aux_sms": (_i32, [_vp]),
     "kb_synchronize": (C.c_int, [_vp]),
+    "kb_set_positive_cholesky": (C.c_int, [_vp, _i32]),
+    "kb_positive_modified": (_i32, [_vp]),
     "kb_trim": (C.c_int, [_vp]),
     "kb_set_sample_chunk_rows": (C.c_int, [_vp, _i64]),
     "kb_solve_s": (C.c_int, [_vp, _vp, _i64, _i32, _d, C.POINTER(SolveOpts), _vp, _vp, C.POINTER(SolveInfo)]),
@@ -118,6 +120,7 @@ SIGNATURES = {
     "kb_test_dgemm_dev": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_factor_band": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_int32)]),
     "kb_test_potrf": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "kb_test_potrf_positive": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.POINTER(C.c_int32)]),
     "kb_test_spd_inverse": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_randn": (C.c_int, [_vp, _u64, _i64, _i64, _i64, _vp]),
 }

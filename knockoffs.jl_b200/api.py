@@ -67,6 +67,14 @@ class Context:
         """SMs the auxiliary stream is confined to (green context), 0 = no partition."""
         return int(self._lib.kb_aux_sms(self.h))
 
+    def set_positive_cholesky(self, on: bool = True):
+        """Opt in to the restated ``cholesky(Positive, ·)`` fallback of ``condition`` (parity unpinned, see the header)."""
+        check(self.h, self._lib.kb_set_positive_cholesky(self.h, int(bool(on))))
+
+    @property
+    def positive_modified(self) -> int:
+        return int(self._lib.kb_positive_modified(self.h))
+
     def set_sample_chunk_rows(self, rows: int):
         check(self.h, self._lib.kb_set_sample_chunk_rows(self.h, int(rows)))
 
@@ -868,6 +876,18 @@ def hook_potrf(A, ctx: Optional[Context] = None):
     L = np.empty_like(A, order="F")
     check(ctx.h, ctx._lib.kb_test_potrf(ctx.h, _ptr(A), A.shape[0], _ptr(L)))
     return L
+
+
+def hook_potrf_positive(A, ctx: Optional[Context] = None):
+    """(L, d, modified) of the restated cholesky(Positive, Symmetric(A)) (csrc/positive.cu)."""
+    ctx = ctx or default_context()
+    A = _f(A)
+    p = A.shape[0]
+    L = np.empty((p, p), order="F")
+    d = np.empty(p)
+    mod = C.c_int32()
+    check(ctx.h, ctx._lib.kb_test_potrf_positive(ctx.h, _ptr(A), p, _ptr(L), _ptr(d), C.byref(mod)))
+    return L, d, mod.value
 
 
 def hook_spd_inverse(A, ctx: Optional[Context] = None):

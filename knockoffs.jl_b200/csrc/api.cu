@@ -8,6 +8,7 @@
 #include "approx.cuh"
 #include "rep.cuh"
 #include "hostpipe.cuh"
+#include "positive.cuh"
 #include <cuda.h>
 #include <algorithm>
 #include <unordered_map>
@@ -541,6 +542,12 @@ int kb_set_sample_chunk_rows(kb_ctx* ctx, int64_t rows) {
     ctx->sample_chunk_rows = rows;
     return KB_OK;
 }
+int kb_set_positive_cholesky(kb_ctx* ctx, int32_t on) {
+    if (!ctx) return KB_ERR_INVALID;
+    ctx->positive_cholesky = on ? 1 : 0;
+    return KB_OK;
+}
+int32_t kb_positive_modified(const kb_ctx* ctx) { return ctx ? ctx->positive_modified : 0; }
 int kb_trim(kb_ctx* ctx) {
     if (!ctx) return bad_ctx();
     DeviceGuard g(ctx->device);
@@ -1280,6 +1287,27 @@ int kb_test_factor_band(kb_ctx* ctx, const double* Lblocks, int64_t p, int32_t m
     int band = 0;
     KB_TRY(factor_band_dev(ctx, dLb, (long)p, (int)p, m, &band));
     *band_out = band;
+    return KB_OK;
+}
+
+int kb_test_potrf_positive(kb_ctx* ctx, const double* A, int64_t p, double* L_out, double* d_out, int32_t* modified_out) {
+    if (!ctx) return bad_ctx();
+    if (!A || !L_out || !d_out || p < 1) return set_error(ctx, KB_ERR_INVALID, "test_potrf_positive: bad arguments");
+    DeviceGuard g(ctx->device);
+    Scope sc(ctx);
+    const long ld = (p + 1) & ~1L;
+    double *dA, *dL, *dd;
+    KB_TRY(sc.alloc(&dA, (size_t)p * p));
+    KB_TRY(sc.alloc(&dL, (size_t)ld * p));
+    KB_TRY(sc.alloc(&dd, (size_t)p));
+    KB_CUDA(ctx, cudaMemcpyAsync(dA, A, sizeof(double) * p * p, cudaMemcpyHostToDevice, ctx->stream));
+    KB_TRY(sym_upper_to_full_dev(ctx, dA, (long)p, (int)p, dL, ld));      // Symmetric(A), uplo = :U
+    int modified = 0;
+    KB_TRY(potrf_positive_lower(ctx, dL, ld, (int)p, dd, &modified));
+    KB_TRY(d2h_matrix(ctx, dL, ld, L_out, (long)p, (long)p, (long)p, ctx->stream));
+    KB_CUDA(ctx, cudaMemcpyAsync(d_out, dd, sizeof(double) * p, cudaMemcpyDeviceToHost, ctx->stream));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (modified_out) *modified_out = modified;
     return KB_OK;
 }
 

@@ -37,6 +37,9 @@ struct kb_ctx {
     unsigned long long launches = 0;     // kernels launched by this library since creation
     double flops = 0.0;                  // FP64 flops issued to the DMMA GEMM kernel since creation (clipped k-ranges counted as clipped)
     long sample_chunk_rows = 0;          // 0 = default (4096)
+    int positive_cholesky = 0;           // 1: a failed Cholesky in the conditional-factor stage falls back to the restated
+                                         //    cholesky(Positive, ·) (positive.cu, parity unpinned) instead of KB_ERR_NOT_PD
+    int positive_modified = 0;           // pivots the last conditional-factor call replaced (0 = ordinary Cholesky factors)
     size_t l2_persist_max = 0;           // cudaDevAttrMaxPersistingL2CacheSize
     size_t l2_window_max = 0;            // cudaDevAttrMaxAccessPolicyWindowSize
     size_t l2_size = 0;

@@ -1,6 +1,7 @@
 // Stages (2)-(4) on the device: Gram, conditional-covariance factor, fused sampling GEMM, RNG.
 // Reference: src/modelX.jl:96-122 (condition), :39-51 (2-arg entry: cov + column means).
 #include "pipeline.cuh"
+#include "positive.cuh"
 #include "linalg.cuh"
 #include <algorithm>
 #include <cmath>
@@ -179,6 +180,17 @@ __global__ void next_A_diag_kernel(const double* __restrict__ Ainv, long ldi, co
     }
 }
 
+// C = 2S − S·(Σ⁻¹S) for diagonal S from the stored Σ⁻¹S (used when the conditional-factor stage has to restart)
+__global__ void next_A_from_SiS_kernel(const double* __restrict__ SiS, long lds, const double* __restrict__ s, int p,
+                                       double* __restrict__ C, long ldc) {
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)p * p;
+    for (; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % p), k = (int)(idx / p);
+        C[i + (long)k * ldc] = ((i == k) ? 2.0 * s[i] : 0.0) - s[i] * SiS[i + (long)k * lds];
+    }
+}
+
 static int check_fail(kb_ctx* ctx, int* d_fail, const char* what) {
     int f = 0;
     KB_CUDA(ctx, cudaMemcpyAsync(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -281,12 +293,36 @@ int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const do
     ctx->launches++;
 
     const size_t bstride = (size_t)ldo * p;
+    ctx->positive_modified = 0;
     if (m == 1) {
         KB_TRY(copy_matrix(ctx, C, ld, dLb, ldo, p, p));
         KB_CUDA(ctx, cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
         KB_TRY(potrf_lower(ctx, dLb, ldo, p, invdiag, d_fail));
-        return check_fail(ctx, d_fail, "the conditional covariance 2S - S*inv(Sigma)*S");
+        if (!ctx->positive_cholesky) return check_fail(ctx, d_fail, "the conditional covariance 2S - S*inv(Sigma)*S");
+        int f = 0;
+        KB_CUDA(ctx, cudaMemcpyAsync(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (f == 0) return KB_OK;
+        // cholesky(Positive, Symmetric(C)) (modelX.jl:111), restated: see positive.cu
+        double* dsign;
+        KB_TRY(sc.alloc(&dsign, (size_t)p));
+        KB_TRY(copy_matrix(ctx, C, ld, dLb, ldo, p, p));
+        return potrf_positive_lower(ctx, dLb, ldo, p, dsign, &ctx->positive_modified);
     }
+    // Every factorisation below is an ordinary Cholesky; when one of them fails and the caller opted in
+    // (kb_set_positive_cholesky), the whole block recursion is redone with the restated cholesky(Positive, ·) of the
+    // pm x pm matrix (modelX.jl:120) in its LDLᵀ block form -- cond_factor_positive() at the end of this function.
+    auto fail_or_positive = [&](const char* what) -> int {
+        int f = 0;
+        KB_CUDA(ctx, cudaMemcpyAsync(&f, d_fail, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (f == 0) return KB_OK;
+        if (!ctx->positive_cholesky)
+            return set_error(ctx, KB_ERR_NOT_PD, "PosDefException: %s is not positive definite; Cholesky factorization "
+                                                 "failed at pivot %d.", what, f);
+        return 1;     // > 0: redo with the Positive restatement
+    };
+    bool redo_positive = false;
     if (s_is_diag) {
         // Diagonal S (the single-knockoff path): with W = L_kk^{-1},
         //     M_k = (L_kk L_kk' − S) L_kk^{-T} = L_kk − S W'                 (elementwise)
@@ -298,7 +334,11 @@ int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const do
             KB_TRY(copy_matrix(ctx, C, ld, Lkk, ldo, p, p));
             KB_CUDA(ctx, cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
             KB_TRY(potrf_lower(ctx, Lkk, ldo, p, invdiag, d_fail));
-            KB_TRY(check_fail(ctx, d_fail, "the conditional covariance of the multiple-knockoff model"));
+            {
+                const int rc = fail_or_positive("the conditional covariance of the multiple-knockoff model");
+                if (rc < 0) return rc;
+                if (rc > 0) { redo_positive = true; break; }
+            }
             if (k == m - 1) break;
             double* Mk = dLb + (size_t)(2 * k + 1) * bstride;
             KB_TRY(trtri_lower(ctx, Lkk, ldo, p, invdiag, W, ld, work));
@@ -310,20 +350,31 @@ int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const do
             ctx->launches++;
         }
         KB_CUDA(ctx, cudaGetLastError());
-        return KB_OK;
+        if (!redo_positive) return KB_OK;
     }
     KB_TRY(sc.alloc(&B, (size_t)ld * p));
     const double* Sptr = s_is_diag ? dS : Sfull;
     const long Sld = s_is_diag ? 0 : ld;
+    if (redo_positive) {
+        // the diagonal-S recursion overwrote C with a later A_k: rebuild A_1 = C = 2S − S Σ⁻¹S (Σ⁻¹S is still in dSiS)
+        next_A_from_SiS_kernel<<<eg, 256, 0, ctx->stream>>>(dSiS, ldo, dS, p, C, ld);
+        ctx->launches++;
+        symmetrize_from_upper_kernel<<<tgrid, tblock, 0, ctx->stream>>>(C, ld, p);
+        ctx->launches++;
+    }
     sub_S_kernel<<<eg, 256, 0, ctx->stream>>>(C, ld, Sptr, Sld, s_is_diag, p, -1.0, B, ld);   // B_1 = C − S
     ctx->launches++;
     // A_1 = C (already in C); C doubles as the A_k buffer
-    for (int k = 0; k < m; ++k) {
+    for (int k = 0; k < m && !redo_positive; ++k) {
         double* Lkk = dLb + (size_t)(2 * k) * bstride;
         KB_TRY(copy_matrix(ctx, C, ld, Lkk, ldo, p, p));
         KB_CUDA(ctx, cudaMemsetAsync(d_fail, 0, sizeof(int), ctx->stream));
         KB_TRY(potrf_lower(ctx, Lkk, ldo, p, invdiag, d_fail));
-        KB_TRY(check_fail(ctx, d_fail, "the conditional covariance of the multiple-knockoff model"));
+        {
+            const int rc = fail_or_positive("the conditional covariance of the multiple-knockoff model");
+            if (rc < 0) return rc;
+            if (rc > 0) { redo_positive = true; break; }
+        }
         if (k == m - 1) break;
         double* Mk = dLb + (size_t)(2 * k + 1) * bstride;
         KB_TRY(trtri_lower(ctx, Lkk, ldo, p, invdiag, W, ld, work));
@@ -345,6 +396,51 @@ int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const do
         sub_S_kernel<<<eg, 256, 0, ctx->stream>>>(B, ld, Sptr, Sld, s_is_diag, p, +1.0, C, ld);
         ctx->launches++;
     }
+    KB_CUDA(ctx, cudaGetLastError());
+    if (!redo_positive) return KB_OK;
+
+    // ---- cholesky(Positive, Symmetric(Σ̃)) of the pm x pm matrix (modelX.jl:116-120), restated (positive.cu) in block
+    //      form: with A_1 = C, B_1 = C − S and, per block column k, the LDLᵀ-with-sign factor (L_kk, D_k) of A_k,
+    //          M_k = B_k L_kk⁻ᵀ D_k⁻¹,   B_{k+1} = B_k − M_k D_k M_kᵀ,   A_{k+1} = B_{k+1} + S
+    //      (every sub-diagonal block of block column k equals M_k, exactly as in the ordinary factor).
+    if (!s_is_diag) {
+        // dense S: C was consumed by the loop above; rebuild A_1 = 2S − S·(Σ⁻¹S)
+        GemmParams P{};
+        P.M = p; P.N = p; P.nseg = 1;
+        P.seg[0] = GemmSeg{Sfull, ld, dSiS, ldo, p, 0};
+        P.C = C; P.ldc = ld; P.Cin = Sfull; P.ldcin = ld; P.alpha = -1.0; P.beta = 2.0;
+        KB_TRY(gemm(ctx, A_MCONTIG, B_KCONTIG, P));
+        symmetrize_from_upper_kernel<<<tgrid, tblock, 0, ctx->stream>>>(C, ld, p);
+        ctx->launches++;
+    } else {
+        next_A_from_SiS_kernel<<<eg, 256, 0, ctx->stream>>>(dSiS, ldo, dS, p, C, ld);
+        ctx->launches++;
+        symmetrize_from_upper_kernel<<<tgrid, tblock, 0, ctx->stream>>>(C, ld, p);
+        ctx->launches++;
+    }
+    sub_S_kernel<<<eg, 256, 0, ctx->stream>>>(C, ld, Sptr, Sld, s_is_diag, p, -1.0, B, ld);
+    ctx->launches++;
+    double *dsign, *XD;
+    KB_TRY(sc.alloc(&dsign, (size_t)p));
+    KB_TRY(sc.alloc(&XD, (size_t)ld * p));
+    int modified_total = 0;
+    for (int k = 0; k < m; ++k) {
+        double* Lkk = dLb + (size_t)(2 * k) * bstride;
+        KB_TRY(copy_matrix(ctx, C, ld, Lkk, ldo, p, p));
+        int modified = 0;
+        KB_TRY(potrf_positive_lower(ctx, Lkk, ldo, p, dsign, &modified));
+        modified_total += modified;
+        if (k == m - 1) break;
+        double* Mk = dLb + (size_t)(2 * k + 1) * bstride;
+        KB_TRY(copy_matrix(ctx, B, ld, Mk, ldo, p, p));
+        KB_TRY(trsm_right_ldlt(ctx, Mk, ldo, p, Lkk, ldo, dsign, p));
+        KB_TRY(scale_columns(ctx, Mk, ldo, p, p, dsign, XD, ld));
+        KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, p, -1.0, XD, ld, Mk, ldo, 1.0, B, ld, 0, 1, 0));
+        KB_TRY(mirror_lower_to_upper(ctx, B, ld, p));
+        sub_S_kernel<<<eg, 256, 0, ctx->stream>>>(B, ld, Sptr, Sld, s_is_diag, p, +1.0, C, ld);
+        ctx->launches++;
+    }
+    ctx->positive_modified = modified_total;
     KB_CUDA(ctx, cudaGetLastError());
     return KB_OK;
 }

@@ -294,7 +294,35 @@ def solve_s(Sigma, method, m=1, **kw):
 # --------------------------------------------------------------------------
 # conditional sampling (src/modelX.jl:96-122), Z injected
 # --------------------------------------------------------------------------
-def cond_factor(Sigma, S, m=1, lean=False):
+def cholesky_positive(A):
+    """cholesky(PositiveFactorizations.Positive, Symmetric(A)).L  (src/modelX.jl:111, :120).
+
+    PARITY UNPINNED: PositiveFactorizations.jl is not under /root/reference.  Restated from its published algorithm as
+    recalled: unpivoted LDL' with d_j in {+1, -1, 0}; |pivot| > tol: d_j = sign(pivot), L_jj = sqrt|pivot|,
+    L_ij = B_ij d_j / L_jj, trailing B -= d_j l l'; otherwise d_j = 0, L_jj = 1, column dropped; tol = 10 n eps max|diag A|;
+    the returned factor is L (D replaced by the identity).  For positive definite A this IS the Cholesky factor.
+    Returns (L, d)."""
+    A = np.asarray(A, dtype=np.float64)
+    n = A.shape[0]
+    B = np.triu(A) + np.triu(A, 1).T
+    L = np.zeros((n, n))
+    d = np.zeros(n)
+    tol = 10.0 * n * np.finfo(float).eps * np.max(np.abs(np.diag(B)))
+    for j in range(n):
+        Bjj = B[j, j]
+        if abs(Bjj) > tol:
+            d[j] = np.sign(Bjj)
+            sj = np.sqrt(abs(Bjj))
+            L[j, j] = sj
+            l = B[j + 1:, j] * (d[j] / sj)
+            L[j + 1:, j] = l
+            B[j + 1:, j + 1:] -= d[j] * np.outer(l, l)
+        else:
+            L[j, j] = 1.0
+    return L, d
+
+
+def cond_factor(Sigma, S, m=1, lean=False, positive=False):
     """Returns (SigmaInvS, L) of src/modelX.jl:106-120.  S: vector (Diagonal) or dense matrix.
     L is the *lower* factor of C (m = 1) or of the pm x pm Sigma-tilde (m > 1)."""
     p = Sigma.shape[0]
@@ -305,6 +333,11 @@ def cond_factor(Sigma, S, m=1, lean=False):
     C = 2 * Smat - Smat @ SiS                            # :108
     if m == 1:
         Csym = np.triu(C) + np.triu(C, 1).T              # Symmetric(C)
+        if positive:
+            try:
+                return SiS, np.linalg.cholesky(Csym)
+            except np.linalg.LinAlgError:
+                return SiS, cholesky_positive(Csym)[0]
         return SiS, np.linalg.cholesky(Csym)
     if lean:
         # same matrix as below without the 4 pm x pm temporaries (pm = 25000 at BASELINE configs[2]): Symmetric(St)
@@ -322,10 +355,15 @@ def cond_factor(Sigma, S, m=1, lean=False):
     for k in range(m):
         St[k * p:(k + 1) * p, k * p:(k + 1) * p] += Smat # :117
     St = np.triu(St) + np.triu(St, 1).T
+    if positive:
+        try:
+            return SiS, np.linalg.cholesky(St)
+        except np.linalg.LinAlgError:
+            return SiS, cholesky_positive(St)[0]
     return SiS, np.linalg.cholesky(St)
 
 
-def condition(X, mu, Sigma, S, m=1, Z=None, rng=None, lean=False):
+def condition(X, mu, Sigma, S, m=1, Z=None, rng=None, lean=False, positive=False):
     """src/modelX.jl:96-122 with Z = randn(n, m*p) injected.  Note quirk Q1:
     the noise is Z @ L with L *lower* (literal reference)."""
     n, p = X.shape
@@ -334,7 +372,7 @@ def condition(X, mu, Sigma, S, m=1, Z=None, rng=None, lean=False):
         raise ValueError(f"m should be 1 or larger but was {m}.")
     if Z is None:
         Z = (rng or np.random.default_rng()).standard_normal((n, m * p))
-    SiS, L = cond_factor(Sigma, S, m, lean=lean)
+    SiS, L = cond_factor(Sigma, S, m, lean=lean, positive=positive)
     mui = X - (X - mu[None, :]) @ SiS
     if m == 1:
         return mui + Z @ L                               # :112
