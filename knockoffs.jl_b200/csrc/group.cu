@@ -24,6 +24,7 @@
 #include "group.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -178,6 +179,148 @@ __device__ __forceinline__ void diag_mvr_roots(double m, double ajj, double bjj,
 // step types
 enum : int { STEP_PCA = 0, STEP_DIAG = 1, STEP_OFFDIAG = 2 };
 
+// The scalars a 1-D step needs (reference: the triangular solves of group.jl:1127-1133, 1241-1251, 1283-1296 ...):
+// with V = [v1 v2] supported on the group,  a = V'D⁻¹V,  b = V'S⁻¹V,  c = (S⁻¹V)'(S⁻¹V),  d = (D⁻¹V)'(D⁻¹V)  (2 x 2, symmetric;
+// rank-1 steps use the 11 entries only).
+struct StepScalars {
+    double a11, a12, a22, b11, b12, b22, c11, c12, c22, d11, d12, d22;
+};
+struct StepDecision {
+    bool accept;
+    double delta, change;
+    double q11, q12, q22;      // D⁻¹ += (D⁻¹V) q (D⁻¹V)'
+    double t11, t12, t22;      // S⁻¹ −= (S⁻¹V) t (S⁻¹V)'
+};
+
+// One line search -- shared by the per-step kernel and the per-group (delayed update) kernel, so both take identical
+// decisions from identical scalars.  v: the PCA direction inside the group (STEP_PCA); Sb / Sg: the group's S and Σ blocks.
+__device__ __forceinline__ StepDecision group_line_search(const GroupDev& G, int type, int g, int gs, int ia, int ib,
+                                                          const StepScalars& sc, const double* v, const double* Sb, int ldb,
+                                                          const double* Sg, int ldg) {
+    const double m = G.m, eps = G.eps;
+    const int method = G.method;
+    double delta = 0.0, change = 0.0;
+    bool accept = false;
+    double q11 = 0.0, q12 = 0.0, q22 = 0.0, t11 = 0.0, t12 = 0.0, t22 = 0.0;
+    if (type != STEP_OFFDIAG) {
+        const double a = sc.a11, b = sc.b11, c = sc.c11, d = sc.d11;
+        const double lb = -1.0 / b + eps, ub = 1.0 / a - eps;
+        if (!(lb >= ub)) {
+            if (method == KB_METHOD_MAXENT) {
+                // group.jl:1391-1404 / :1483-1490
+                delta = clampd((m * b - a) / ((m + 1) * a * b), lb, ub);
+                change = log(1.0 - delta * a) + m * log(1.0 + delta * b);
+                accept = !(change < 0.0 || bad_delta(delta));
+            } else if (method == KB_METHOD_MVR) {
+                // group.jl:1253-1259 / :1555-1563
+                double x1, x2;
+                diag_mvr_roots(m, a, b, c, d, x1, x2);
+                delta = (lb < x1 && x1 < ub) ? x1 : ((lb < x2 && x2 < ub) ? x2 : NAN);
+                change = -m * m * delta * c / (1.0 + delta * b) + delta * d / (1.0 - delta * a);
+                accept = !(change > 0.0 || bad_delta(delta));
+            } else if (type == STEP_DIAG) {
+                // SDP diagonal, group.jl:1136-1141
+                const double gap = Sg[ia + (size_t)ia * ldg] - Sb[ia + (size_t)ia * ldb];
+                delta = clampd(gap, lb, ub);
+                change = (fabs(gap - delta) - fabs(gap)) / ((double)gs * gs);
+                accept = !(bad_delta(delta) || change > 0.01);
+            } else {
+                // SDP PCA direction: Brent on the group's block objective, group.jl:1619-1634
+                auto f = [&](double t) {
+                    double acc = 0.0;
+                    for (int j = 0; j < gs; ++j)
+                        for (int i = 0; i < gs; ++i)
+                            acc += fabs(Sg[i + (size_t)j * ldg] - Sb[i + (size_t)j * ldb] - t * v[i] * v[j]);
+                    return acc / ((double)gs * gs);
+                };
+                double xm, fm;
+                brent_min(f, lb, ub, xm, fm);
+                delta = clampd(xm, lb, ub);
+                change = fm - G.gobj[g];
+                accept = !(bad_delta(delta) || change > 0.01);
+                if (accept) G.gobj[g] = fm;
+            }
+        }
+        if (accept) {
+            q11 = delta / (1.0 - delta * a);          // D -> D - δ vv'
+            t11 = delta / (1.0 + delta * b);          // S -> S + δ vv'
+        }
+    } else {
+        // off-diagonal (i, j) = (ia, ib): group.jl:1151-1193, 1267-1322, 1392-1436
+        const double aii = sc.a11, aij = sc.a12, ajj = sc.a22;
+        const double bii = sc.b11, bij = sc.b12, bjj = sc.b22;
+        const double cii = sc.c11, cij = sc.c12, cjj = sc.c22;
+        const double dii = sc.d11, dij = sc.d12, djj = sc.d22;
+        double s1 = (aij - sqrt(aii * ajj)) / (aij * aij - aii * ajj);
+        double s2 = (aij + sqrt(aii * ajj)) / (aij * aij - aii * ajj);
+        double e1 = (-bij - sqrt(bii * bjj)) / (bij * bij - bii * bjj);
+        double e2 = (-bij + sqrt(bii * bjj)) / (bij * bij - bii * bjj);
+        if (s1 > s2) { const double t = s1; s1 = s2; s2 = t; }
+        if (e1 > e2) { const double t = e1; e1 = e2; e2 = t; }
+        double lb, ub;
+        if (method == KB_METHOD_SDP_CCD) {          // ε outside max/min (quirk Q4), group.jl:1176-1177
+            lb = fmax(fmax(s1, e1), -2.0 / (bii + 2 * bij + bjj)) + eps;
+            ub = fmin(fmin(s2, e2), 2.0 / (aii + 2 * aij + ajj)) - eps;
+        } else {                                    // group.jl:1299-1300, 1415-1416
+            lb = fmax(fmax(s1, e1), -2.0 / (bii + 2 * bij + bjj) + eps);
+            ub = fmin(fmin(s2, e2), 2.0 / (aii + 2 * aij + ajj) - eps);
+        }
+        if (!(lb >= ub)) {
+            if (method == KB_METHOD_SDP_CCD) {
+                const double gap = Sg[ia + (size_t)ib * ldg] - Sb[ia + (size_t)ib * ldb];
+                delta = clampd(gap, lb, ub);
+                change = (2 * fabs(gap - delta) - 2 * fabs(gap)) / ((double)gs * gs);
+                accept = !(bad_delta(delta) || change > 0.01);
+            } else if (method == KB_METHOD_MAXENT) {
+                auto f = [&](double t) {              // offdiag_maxent_obj, group.jl:1695-1700 (quirk Q5)
+                    const double in1 = (1 - t * aij) * (1 - t * aij) - t * t * aii * ajj;
+                    const double in2 = (1 + t * bij) * (1 + t * bij) - t * t * bjj * bii;
+                    if (in1 <= 0.0) return (double)NAN;
+                    if (in2 <= 0.0) return -(double)INFINITY;
+                    return -log(in1) - m * log(in2);
+                };
+                double xm, fm;
+                brent_min(f, lb, ub, xm, fm);
+                delta = clampd(xm, lb, ub);
+                change = -fm;
+                accept = !(change < 0.0 || bad_delta(delta));
+            } else {
+                auto f = [&](double t) {              // offdiag_mvr_obj, group.jl:1701-1707
+                    const double denom1 = (1 + t * bij) * (1 + t * bij) - t * t * bii * bjj;
+                    const double denom2 = (1 - t * aij) * (1 - t * aij) - t * t * aii * ajj;
+                    const double numer1 = -m * m * t * ((cij * bij - cjj * bii - cii * bjj + cij * bij) * t + 2 * cij);
+                    const double numer2 = t * ((-dij * aij + djj * aii + dii * ajj - dij * aij) * t + 2 * dij);
+                    return numer1 / denom1 + numer2 / denom2;
+                };
+                double xm, fm;
+                brent_min(f, lb, ub, xm, fm);
+                delta = clampd(xm, lb, ub);
+                change = fm;
+                accept = !(change > 0.0 || bad_delta(delta));
+            }
+        }
+        if (accept) {
+            // D -> D − U K U',  U = [e_i e_j], K = δ [[0,1],[1,0]]:  MD += [w_i w_j] (K^{-1} − A2)^{-1} [w_i w_j]'
+            const double k = 1.0 / delta;
+            {   // Q = inv([[-aii, k - aij], [k - aij, -ajj]])
+                const double m11 = -aii, m12 = k - aij, m22 = -ajj;
+                const double det = m11 * m22 - m12 * m12;
+                q11 = m22 / det; q12 = -m12 / det; q22 = m11 / det;
+            }
+            {   // S -> S + U K U':  MS −= [u_i u_j] (K^{-1} + B2)^{-1} [u_i u_j]'
+                const double m11 = bii, m12 = k + bij, m22 = bjj;
+                const double det = m11 * m22 - m12 * m12;
+                t11 = m22 / det; t12 = -m12 / det; t22 = m11 / det;
+            }
+        }
+    }
+    StepDecision dec;
+    dec.accept = accept; dec.delta = delta; dec.change = change;
+    dec.q11 = q11; dec.q12 = q12; dec.q22 = q22; dec.t11 = t11; dec.t12 = t12; dec.t22 = t22;
+    return dec;
+}
+
+
 __global__ void __launch_bounds__(GSTEP_THREADS, 1)
 group_step_kernel(const GroupDev G, const int type, const int g, const int ia, const int ib) {
     extern __shared__ double gsm[];
@@ -247,141 +390,31 @@ group_step_kernel(const GroupDev G, const int type, const int g, const int ia, c
     if (tid == 0) {
         double d11 = 0.0, d12 = 0.0, d22 = 0.0;
         for (int w = 0; w < GSTEP_WARPS; ++w) { d11 += red[w]; d12 += red[GSTEP_WARPS + w]; d22 += red[2 * GSTEP_WARPS + w]; }
-        const double m = G.m, eps = G.eps;
-        const int method = G.method;
-        double delta = 0.0, change = 0.0;
-        bool accept = false;
-        double q11 = 0.0, q12 = 0.0, q22 = 0.0, t11 = 0.0, t12 = 0.0, t22 = 0.0;
-        if (type != STEP_OFFDIAG) {
-            // a = v'D^{-1}v, b = v'S^{-1}v, c = |S^{-1}v|^2, d = |D^{-1}v|^2
-            double a = 0.0, b = 0.0, c = 0.0;
-            if (type == STEP_PCA) {
-                for (int k = 0; k < gs; ++k) {
-                    a = fma(sh_v[k], w1[o + k], a);
-                    b = fma(sh_v[k], sh_u1[k], b);
-                    c = fma(sh_u1[k], sh_u1[k], c);
-                }
-            } else {
-                a = w1[o + ia];
-                b = sh_u1[ia];
-                for (int k = 0; k < gs; ++k) c = fma(sh_u1[k], sh_u1[k], c);
-            }
-            const double d = d11;
-            const double lb = -1.0 / b + eps, ub = 1.0 / a - eps;
-            if (!(lb >= ub)) {
-                if (method == KB_METHOD_MAXENT) {
-                    // group.jl:1391-1404 / :1483-1490
-                    delta = clampd((m * b - a) / ((m + 1) * a * b), lb, ub);
-                    change = log(1.0 - delta * a) + m * log(1.0 + delta * b);
-                    accept = !(change < 0.0 || bad_delta(delta));
-                } else if (method == KB_METHOD_MVR) {
-                    // group.jl:1253-1259 / :1555-1563
-                    double x1, x2;
-                    diag_mvr_roots(m, a, b, c, d, x1, x2);
-                    delta = (lb < x1 && x1 < ub) ? x1 : ((lb < x2 && x2 < ub) ? x2 : NAN);
-                    change = -m * m * delta * c / (1.0 + delta * b) + delta * d / (1.0 - delta * a);
-                    accept = !(change > 0.0 || bad_delta(delta));
-                } else if (type == STEP_DIAG) {
-                    // SDP diagonal, group.jl:1136-1141
-                    const double gap = Sg[ia + (size_t)ia * gmax] - Sb[ia + (size_t)ia * gmax];
-                    delta = clampd(gap, lb, ub);
-                    change = (fabs(gap - delta) - fabs(gap)) / ((double)gs * gs);
-                    accept = !(bad_delta(delta) || change > 0.01);
-                } else {
-                    // SDP PCA direction: Brent on the group's block objective, group.jl:1619-1634
-                    auto f = [&](double t) {
-                        double acc = 0.0;
-                        for (int j = 0; j < gs; ++j)
-                            for (int i = 0; i < gs; ++i)
-                                acc += fabs(Sg[i + (size_t)j * gmax] - Sb[i + (size_t)j * gmax] - t * sh_v[i] * sh_v[j]);
-                        return acc / ((double)gs * gs);
-                    };
-                    double xm, fm;
-                    brent_min(f, lb, ub, xm, fm);
-                    delta = clampd(xm, lb, ub);
-                    change = fm - G.gobj[g];
-                    accept = !(bad_delta(delta) || change > 0.01);
-                    if (accept) G.gobj[g] = fm;
-                }
-            }
-            if (accept) {
-                q11 = delta / (1.0 - delta * a);          // D -> D - δ vv'
-                t11 = delta / (1.0 + delta * b);          // S -> S + δ vv'
-            }
-        } else {
-            // off-diagonal (i, j) = (ia, ib): group.jl:1151-1193, 1267-1322, 1392-1436
-            const double aii = w1[o + ia], aij = w1[o + ib], ajj = w2[o + ib];
-            const double bii = sh_u1[ia], bij = sh_u1[ib], bjj = sh_u2[ib];
-            double cii = 0.0, cij = 0.0, cjj = 0.0;
+        StepScalars sc{};
+        sc.d11 = d11; sc.d12 = d12; sc.d22 = d22;
+        if (type == STEP_PCA) {
             for (int k = 0; k < gs; ++k) {
-                cii = fma(sh_u1[k], sh_u1[k], cii);
-                cij = fma(sh_u1[k], sh_u2[k], cij);
-                cjj = fma(sh_u2[k], sh_u2[k], cjj);
+                sc.a11 = fma(sh_v[k], w1[o + k], sc.a11);
+                sc.b11 = fma(sh_v[k], sh_u1[k], sc.b11);
+                sc.c11 = fma(sh_u1[k], sh_u1[k], sc.c11);
             }
-            const double dii = d11, dij = d12, djj = d22;
-            double s1 = (aij - sqrt(aii * ajj)) / (aij * aij - aii * ajj);
-            double s2 = (aij + sqrt(aii * ajj)) / (aij * aij - aii * ajj);
-            double e1 = (-bij - sqrt(bii * bjj)) / (bij * bij - bii * bjj);
-            double e2 = (-bij + sqrt(bii * bjj)) / (bij * bij - bii * bjj);
-            if (s1 > s2) { const double t = s1; s1 = s2; s2 = t; }
-            if (e1 > e2) { const double t = e1; e1 = e2; e2 = t; }
-            double lb, ub;
-            if (method == KB_METHOD_SDP_CCD) {          // ε outside max/min (quirk Q4), group.jl:1176-1177
-                lb = fmax(fmax(s1, e1), -2.0 / (bii + 2 * bij + bjj)) + eps;
-                ub = fmin(fmin(s2, e2), 2.0 / (aii + 2 * aij + ajj)) - eps;
-            } else {                                    // group.jl:1299-1300, 1415-1416
-                lb = fmax(fmax(s1, e1), -2.0 / (bii + 2 * bij + bjj) + eps);
-                ub = fmin(fmin(s2, e2), 2.0 / (aii + 2 * aij + ajj) - eps);
-            }
-            if (!(lb >= ub)) {
-                if (method == KB_METHOD_SDP_CCD) {
-                    const double gap = Sg[ia + (size_t)ib * gmax] - Sb[ia + (size_t)ib * gmax];
-                    delta = clampd(gap, lb, ub);
-                    change = (2 * fabs(gap - delta) - 2 * fabs(gap)) / ((double)gs * gs);
-                    accept = !(bad_delta(delta) || change > 0.01);
-                } else if (method == KB_METHOD_MAXENT) {
-                    auto f = [&](double t) {              // offdiag_maxent_obj, group.jl:1695-1700 (quirk Q5)
-                        const double in1 = (1 - t * aij) * (1 - t * aij) - t * t * aii * ajj;
-                        const double in2 = (1 + t * bij) * (1 + t * bij) - t * t * bjj * bii;
-                        if (in1 <= 0.0) return (double)NAN;
-                        if (in2 <= 0.0) return -(double)INFINITY;
-                        return -log(in1) - m * log(in2);
-                    };
-                    double xm, fm;
-                    brent_min(f, lb, ub, xm, fm);
-                    delta = clampd(xm, lb, ub);
-                    change = -fm;
-                    accept = !(change < 0.0 || bad_delta(delta));
-                } else {
-                    auto f = [&](double t) {              // offdiag_mvr_obj, group.jl:1701-1707
-                        const double denom1 = (1 + t * bij) * (1 + t * bij) - t * t * bii * bjj;
-                        const double denom2 = (1 - t * aij) * (1 - t * aij) - t * t * aii * ajj;
-                        const double numer1 = -m * m * t * ((cij * bij - cjj * bii - cii * bjj + cij * bij) * t + 2 * cij);
-                        const double numer2 = t * ((-dij * aij + djj * aii + dii * ajj - dij * aij) * t + 2 * dij);
-                        return numer1 / denom1 + numer2 / denom2;
-                    };
-                    double xm, fm;
-                    brent_min(f, lb, ub, xm, fm);
-                    delta = clampd(xm, lb, ub);
-                    change = fm;
-                    accept = !(change > 0.0 || bad_delta(delta));
-                }
-            }
-            if (accept) {
-                // D -> D − U K U',  U = [e_i e_j], K = δ [[0,1],[1,0]]:  MD += [w_i w_j] (K^{-1} − A2)^{-1} [w_i w_j]'
-                const double k = 1.0 / delta;
-                {   // Q = inv([[-aii, k - aij], [k - aij, -ajj]])
-                    const double m11 = -aii, m12 = k - aij, m22 = -ajj;
-                    const double det = m11 * m22 - m12 * m12;
-                    q11 = m22 / det; q12 = -m12 / det; q22 = m11 / det;
-                }
-                {   // S -> S + U K U':  MS −= [u_i u_j] (K^{-1} + B2)^{-1} [u_i u_j]'
-                    const double m11 = bii, m12 = k + bij, m22 = bjj;
-                    const double det = m11 * m22 - m12 * m12;
-                    t11 = m22 / det; t12 = -m12 / det; t22 = m11 / det;
-                }
+        } else if (type == STEP_DIAG) {
+            sc.a11 = w1[o + ia];
+            sc.b11 = sh_u1[ia];
+            for (int k = 0; k < gs; ++k) sc.c11 = fma(sh_u1[k], sh_u1[k], sc.c11);
+        } else {
+            sc.a11 = w1[o + ia]; sc.a12 = w1[o + ib]; sc.a22 = w2[o + ib];
+            sc.b11 = sh_u1[ia]; sc.b12 = sh_u1[ib]; sc.b22 = sh_u2[ib];
+            for (int k = 0; k < gs; ++k) {
+                sc.c11 = fma(sh_u1[k], sh_u1[k], sc.c11);
+                sc.c12 = fma(sh_u1[k], sh_u2[k], sc.c12);
+                sc.c22 = fma(sh_u2[k], sh_u2[k], sc.c22);
             }
         }
+        const StepDecision dec = group_line_search(G, type, g, gs, ia, ib, sc, sh_v, Sb, gmax, Sg, gmax);
+        const bool accept = dec.accept;
+        const double delta = dec.delta, change = dec.change;
+        const double q11 = dec.q11, q12 = dec.q12, q22 = dec.q22, t11 = dec.t11, t12 = dec.t12, t22 = dec.t22;
         if (accept) {
             G.state[ST_OBJ_NEW] += change;
             if (fabs(delta) > G.state[ST_MAXD]) G.state[ST_MAXD] = fabs(delta);
@@ -452,6 +485,228 @@ __global__ void __launch_bounds__(256) group_apply_kernel(const GroupDev G) {
             v = fma(f1, a0, v);
             if (rank2) v = fma(f2, b0, v);
             *ptr = v;
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Delayed updates, one GROUP at a time (the blocked CCD's idea, ccd_block.cu, with block J = group G).
+// Every 1-D step on group G only needs g x g quantities of D⁻¹: the block A = D⁻¹[G,G] (a-terms) and -- MVR -- the Gram
+// E = D⁻¹[:,G]ᵀD⁻¹[:,G] (d-terms); S⁻¹ is g x g anyway.  A step D⁻¹ += (D⁻¹V) q (D⁻¹V)ᵀ (V = v, e_i or [e_i e_j]) acts on
+// the panel P = D⁻¹[:,G] = P₀·T as T ← T + (TV) q (AV)ᵀ and obeys
+//     A ← A + (AV) q (AV)ᵀ,     E ← (I + V q (AV)ᵀ)ᵀ E (I + V q (AV)ᵀ),     D⁻¹ = D⁻¹₀ + P₀ Q P₀ᵀ,  Q ← Q + (TV) q (TV)ᵀ,
+// so ONE CTA walks all steps of the group (g eigen-directions of a PCA sweep, or the g diagonal + g(g−1)/2 off-diagonal
+// steps of a CCD sweep) in shared memory, and D⁻¹ is streamed ONCE per group -- a rank-g update -- instead of once per
+// step: 3 launches per group instead of 2 per step, and 16p² bytes per group instead of per accepted step.
+// The step order, the line search (group_line_search) and every accept / reject decision are unchanged.
+// ------------------------------------------------------------------------------------------------
+constexpr int GB_MAX = 16;          // largest group the delayed-update path handles (larger groups: per-step kernels)
+constexpr int GB_THREADS = 256;     // = GB_MAX²: one thread per entry of a g x g block
+constexpr int GB_SLAB = 256;        // rows per CTA of the panel kernel
+
+struct GroupRun {
+    int g;        // group
+    int kind;     // 0: PCA directions [j0, j1) (all on group g);  1: the CCD pass of group g
+    int j0, j1;
+};
+
+// Wp (ld x gs) = D⁻¹[:, G];  Epart[slab] = partial Gram of the slab's rows (MVR)
+__global__ void __launch_bounds__(GB_SLAB) group_panel_kernel(const GroupDev G, const int g, double* __restrict__ Wp,
+                                                              double* __restrict__ Epart, const int want_gram) {
+    __shared__ double sm[GB_MAX * GB_SLAB];
+    const int tid = threadIdx.x;
+    const int o = G.goff[g], gs = G.goff[g + 1] - o;
+    const long ld = G.ld;
+    const long r = (long)blockIdx.x * GB_SLAB + tid;
+    for (int k = 0; k < gs; ++k) {
+        const double v = (r < G.p) ? G.MD[r + (long)(o + k) * ld] : 0.0;
+        if (r < ld) Wp[r + (long)k * ld] = v;
+        sm[k * GB_SLAB + tid] = v;
+    }
+    if (!want_gram) return;
+    __syncthreads();
+    for (int e = tid; e < gs * gs; e += GB_SLAB) {
+        const int k = e % gs, l = e / gs;
+        const double* x = sm + k * GB_SLAB;
+        const double* y = sm + l * GB_SLAB;
+        double a0 = 0.0, a1 = 0.0;
+        for (int t = 0; t < GB_SLAB; t += 2) { a0 = fma(x[t], y[t], a0); a1 = fma(x[t + 1], y[t + 1], a1); }
+        Epart[(size_t)blockIdx.x * (GB_MAX * GB_MAX) + e] = a0 + a1;
+    }
+}
+
+__global__ void __launch_bounds__(GB_THREADS, 1)
+group_run_seq_kernel(const GroupDev G, const GroupRun run, const double* __restrict__ Wp, const double* __restrict__ Epart,
+                     const int nslab, double* __restrict__ Qout, int* __restrict__ flag_out) {
+    __shared__ double A[GB_MAX * GB_MAX], E[GB_MAX * GB_MAX], T[GB_MAX * GB_MAX], Q[GB_MAX * GB_MAX];
+    __shared__ double MSs[GB_MAX * GB_MAX], Sbs[GB_MAX * GB_MAX], Sgs[GB_MAX * GB_MAX];
+    __shared__ double V1[GB_MAX], V2[GB_MAX], X1[GB_MAX], X2[GB_MAX], U1[GB_MAX], U2[GB_MAX], TV1[GB_MAX], TV2[GB_MAX],
+        EV1[GB_MAX], EV2[GB_MAX];
+    __shared__ double dec[12];
+    const int tid = threadIdx.x;
+    const int g = run.g, gmax = G.gmax;
+    const int o = G.goff[g], gs = G.goff[g + 1] - o;
+    const long ld = G.ld;
+    const bool mvr = (G.method == KB_METHOD_MVR);
+    double* MS = G.MSblk + (size_t)g * gmax * gmax;
+    double* Sb = G.Sblk + (size_t)g * gmax * gmax;
+    const double* Sg = G.SigBlk + (size_t)g * gmax * gmax;
+    const bool mine = tid < gs * gs;
+    const int k = mine ? tid % gs : 0, l = mine ? tid / gs : 0;
+    if (mine) {
+        A[tid] = Wp[(o + k) + (long)l * ld];
+        double e = 0.0;
+        if (mvr)
+            for (int sl = 0; sl < nslab; ++sl) e += Epart[(size_t)sl * (GB_MAX * GB_MAX) + tid];
+        E[tid] = e;
+        T[tid] = (k == l) ? 1.0 : 0.0;
+        Q[tid] = 0.0;
+        MSs[tid] = MS[k + (size_t)l * gmax];
+        Sbs[tid] = Sb[k + (size_t)l * gmax];
+        Sgs[tid] = Sg[k + (size_t)l * gmax];
+    }
+    __syncthreads();
+    const int nsteps = (run.kind == 0) ? (run.j1 - run.j0) : gs + gs * (gs - 1) / 2;
+    int any = 0;
+    int oi1 = 0, oi2 = 1;                    // off-diagonal enumeration: for i1 in 0..gs-1, i2 in i1+1..gs-1 -> (i, j) = (i2, i1)
+    for (int st = 0; st < nsteps; ++st) {
+        int type, ia = 0, ib = 0;
+        if (run.kind == 0) { type = STEP_PCA; ia = run.j0 + st; }
+        else if (st < gs) { type = STEP_DIAG; ia = st; }
+        else { type = STEP_OFFDIAG; ia = oi2; ib = oi1; }
+        // ---- phase 1: the direction(s) and the four g x g matrix-vector products ----
+        if (tid < gs) {
+            const int r = tid;
+            double v1, v2 = 0.0;
+            if (type == STEP_PCA) v1 = G.vvec[(size_t)ia * gmax + r];
+            else v1 = (r == ia) ? 1.0 : 0.0;
+            if (type == STEP_OFFDIAG) v2 = (r == ib) ? 1.0 : 0.0;
+            V1[r] = v1; V2[r] = v2;
+        }
+        __syncthreads();
+        if (tid < gs) {
+            const int r = tid;
+            double x1 = 0.0, x2 = 0.0, u1 = 0.0, u2 = 0.0, t1 = 0.0, t2 = 0.0, e1 = 0.0, e2 = 0.0;
+            if (type == STEP_PCA) {
+                for (int c = 0; c < gs; ++c) {
+                    const double vc = V1[c];
+                    x1 = fma(A[r + c * gs], vc, x1);
+                    u1 = fma(MSs[r + c * gs], vc, u1);
+                    t1 = fma(T[r + c * gs], vc, t1);
+                    if (mvr) e1 = fma(E[r + c * gs], vc, e1);
+                }
+            } else {
+                x1 = A[r + ia * gs]; u1 = MSs[r + ia * gs]; t1 = T[r + ia * gs]; e1 = E[r + ia * gs];
+                if (type == STEP_OFFDIAG) { x2 = A[r + ib * gs]; u2 = MSs[r + ib * gs]; t2 = T[r + ib * gs]; e2 = E[r + ib * gs]; }
+            }
+            X1[r] = x1; X2[r] = x2; U1[r] = u1; U2[r] = u2; TV1[r] = t1; TV2[r] = t2; EV1[r] = e1; EV2[r] = e2;
+        }
+        __syncthreads();
+        // ---- phase 2: scalars + line search (thread 0) ----
+        if (tid == 0) {
+            StepScalars sc{};
+            for (int c = 0; c < gs; ++c) {
+                sc.a11 = fma(V1[c], X1[c], sc.a11); sc.b11 = fma(V1[c], U1[c], sc.b11);
+                sc.c11 = fma(U1[c], U1[c], sc.c11); sc.d11 = fma(V1[c], EV1[c], sc.d11);
+            }
+            if (type == STEP_OFFDIAG) {
+                for (int c = 0; c < gs; ++c) {
+                    sc.a12 = fma(V1[c], X2[c], sc.a12); sc.a22 = fma(V2[c], X2[c], sc.a22);
+                    sc.b12 = fma(V1[c], U2[c], sc.b12); sc.b22 = fma(V2[c], U2[c], sc.b22);
+                    sc.c12 = fma(U1[c], U2[c], sc.c12); sc.c22 = fma(U2[c], U2[c], sc.c22);
+                    sc.d12 = fma(V1[c], EV2[c], sc.d12); sc.d22 = fma(V2[c], EV2[c], sc.d22);
+                }
+            }
+            const StepDecision d = group_line_search(G, type, g, gs, ia, ib, sc, V1, Sbs, gs, Sgs, gs);
+            if (d.accept) {
+                G.state[ST_OBJ_NEW] += d.change;
+                if (fabs(d.delta) > G.state[ST_MAXD]) G.state[ST_MAXD] = fabs(d.delta);
+                G.state[ST_ACCEPTED] += 1.0;
+            }
+            G.state[ST_STEPS] += 1.0;
+            dec[0] = d.accept ? 1.0 : 0.0; dec[1] = d.delta;
+            dec[2] = d.q11; dec[3] = d.q12; dec[4] = d.q22; dec[5] = d.t11; dec[6] = d.t12; dec[7] = d.t22;
+            dec[8] = sc.d11; dec[9] = sc.d12; dec[10] = sc.d22;
+        }
+        __syncthreads();
+        // ---- phase 3: accepted -> every g x g matrix takes its O(1)-per-entry update ----
+        if (dec[0] != 0.0) {
+            any = 1;
+            if (mine) {
+                const double delta = dec[1], q11 = dec[2], q12 = dec[3], q22 = dec[4], t11 = dec[5], t12 = dec[6], t22 = dec[7];
+                const double d11 = dec[8], d12 = dec[9], d22 = dec[10];
+                // Y = X q  (columns Y1, Y2):  X q Xᵀ = X1 Y1ᵀ + X2 Y2ᵀ
+                const double y1k = q11 * X1[k] + q12 * X2[k], y2k = q12 * X1[k] + q22 * X2[k];
+                const double y1l = q11 * X1[l] + q12 * X2[l], y2l = q12 * X1[l] + q22 * X2[l];
+                MSs[tid] -= t11 * U1[k] * U1[l] + t12 * (U1[k] * U2[l] + U2[k] * U1[l]) + t22 * U2[k] * U2[l];
+                double add = 0.0;
+                if (type == STEP_PCA) add = delta * V1[k] * V1[l];
+                else if (type == STEP_DIAG) add = (k == ia && l == ia) ? delta : 0.0;
+                else add = ((k == ia && l == ib) || (k == ib && l == ia)) ? delta : 0.0;
+                Sbs[tid] += add;
+                A[tid] += X1[k] * y1l + X2[k] * y2l;
+                T[tid] += TV1[k] * y1l + TV2[k] * y2l;
+                Q[tid] += TV1[k] * (q11 * TV1[l] + q12 * TV2[l]) + TV2[k] * (q12 * TV1[l] + q22 * TV2[l]);
+                if (mvr)
+                    E[tid] += y1k * EV1[l] + y2k * EV2[l] + EV1[k] * y1l + EV2[k] * y2l +
+                              y1k * (d11 * y1l + d12 * y2l) + y2k * (d12 * y1l + d22 * y2l);
+            }
+        }
+        __syncthreads();
+        if (type == STEP_OFFDIAG) {
+            if (++oi2 >= gs) { ++oi1; oi2 = oi1 + 1; }
+        }
+    }
+    if (mine) {
+        MS[k + (size_t)l * gmax] = MSs[tid];
+        Sb[k + (size_t)l * gmax] = Sbs[tid];
+        Qout[tid] = Q[tid];
+    }
+    if (tid == 0) *flag_out = any;
+}
+
+// D⁻¹ += Wp Q Wpᵀ over the full matrix (Wp = the panel at the start of the run, Q g x g symmetric)
+__global__ void __launch_bounds__(256) group_run_apply_kernel(const GroupDev G, const int g, const double* __restrict__ Wp,
+                                                              const double* __restrict__ Qm, const int* __restrict__ flag) {
+    if (*flag == 0) return;                                   // no step of the run was accepted
+    __shared__ double Qs[GB_MAX * GB_MAX];
+    const int gs = G.goff[g + 1] - G.goff[g];
+    if (threadIdx.x < gs * gs) Qs[threadIdx.x] = Qm[threadIdx.x];
+    __syncthreads();
+    const int p = G.p;
+    const long ld = G.ld;
+    const int r = (blockIdx.x * 256 + threadIdx.x) * 2;
+    if (r >= p) return;
+    const bool two = r + 1 < p;
+    double y0[GB_MAX], y1[GB_MAX];
+#pragma unroll
+    for (int c = 0; c < GB_MAX; ++c) { y0[c] = 0.0; y1[c] = 0.0; }
+    for (int a = 0; a < gs; ++a) {
+        const double w0 = Wp[r + (long)a * ld], w1 = two ? Wp[r + 1 + (long)a * ld] : 0.0;
+#pragma unroll
+        for (int c = 0; c < GB_MAX; ++c)
+            if (c < gs) { y0[c] = fma(w0, Qs[a + c * gs], y0[c]); y1[c] = fma(w1, Qs[a + c * gs], y1[c]); }
+    }
+    const int c0 = blockIdx.y * GAPPLY_COLS;
+    for (int cc = 0; cc < GAPPLY_COLS; ++cc) {
+        const int c = c0 + cc;
+        if (c >= p) break;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int a = 0; a < GB_MAX; ++a)
+            if (a < gs) {
+                const double wc = Wp[c + (long)a * ld];
+                a0 = fma(y0[a], wc, a0);
+                a1 = fma(y1[a], wc, a1);
+            }
+        double* ptr = G.MD + r + (long)c * ld;
+        if (two) {
+            double2 v = *reinterpret_cast<double2*>(ptr);
+            v.x += a0; v.y += a1;
+            *reinterpret_cast<double2*>(ptr) = v;
+        } else {
+            *ptr += a0;
         }
     }
 }
@@ -742,6 +997,33 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
     KB_TRY(fill_zero(ctx, dcoef, 8));
     KB_TRY(fill_zero(ctx, dWv, (size_t)2 * ld));
 
+    // Delayed updates per group (group_run_* kernels) whenever every group fits; KB_GROUP_MODE=step forces the per-step kernels.
+    static const bool force_step = [] { const char* e = getenv("KB_GROUP_MODE"); return e && e[0] == 's'; }();
+    const bool use_runs = !force_step && gmax <= GB_MAX;
+    double *dWp = nullptr, *dEpart = nullptr, *dQ = nullptr;
+    int* dflag = nullptr;
+    const int nslab = ceil_div(p, GB_SLAB);
+    std::vector<GroupRun> pca_runs;
+    if (use_runs) {
+        KB_TRY(sc.alloc(&dWp, (size_t)ld * GB_MAX));
+        KB_TRY(sc.alloc(&dEpart, (size_t)nslab * GB_MAX * GB_MAX));
+        KB_TRY(sc.alloc(&dQ, (size_t)GB_MAX * GB_MAX));
+        KB_TRY(sc.alloc(&dflag, 4));
+        for (int jv = 0; jv < nv;) {                      // maximal runs of consecutive directions on the same group
+            int j1 = jv + 1;
+            while (j1 < nv && vgrp[j1] == vgrp[jv]) ++j1;
+            pca_runs.push_back(GroupRun{vgrp[jv], 0, jv, j1});
+            jv = j1;
+        }
+    }
+    const dim3 rgrid(ceil_div(ceil_div(p, 2), 256), ceil_div(p, GAPPLY_COLS));
+    const int want_gram = (method == KB_METHOD_MVR) ? 1 : 0;
+    auto run_group = [&](const GroupRun& r) {
+        group_panel_kernel<<<nslab, GB_SLAB, 0, st>>>(G, r.g, dWp, dEpart, want_gram);
+        group_run_seq_kernel<<<1, GB_THREADS, 0, st>>>(G, r, dWp, dEpart, nslab, dQ, dflag);
+        group_run_apply_kernel<<<rgrid, 256, 0, st>>>(G, r.g, dWp, dQ, dflag);
+        ctx->launches += 3;
+    };
     const size_t step_smem = (size_t)(3 * gmax + 3 * GSTEP_WARPS + 8) * sizeof(double);
     if (step_smem > 200 * 1024) return set_error(ctx, KB_ERR_INVALID, "group size %d too large", gmax);
     KB_CUDA(ctx, raise_max_dynamic_smem((const void*)group_step_kernel, step_smem));
@@ -781,7 +1063,8 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
         for (int l = 0; l < opts.inner_pca_iter; ++l) {                       // _X_pca_ccd_iter!
             group_sweep_begin_kernel<<<1, 1, 0, st>>>(G);
             ctx->launches++;
-            for (int jv = 0; jv < nv; ++jv) step(STEP_PCA, vgrp[jv], jv, 0);
+            if (use_runs) for (const GroupRun& r : pca_runs) run_group(r);
+            else for (int jv = 0; jv < nv; ++jv) step(STEP_PCA, vgrp[jv], jv, 0);
             bool c = false;
             KB_TRY(end_sweep(0, &c));
             if (c) { conv1 = true; break; }
@@ -790,6 +1073,7 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
             group_sweep_begin_kernel<<<1, 1, 0, st>>>(G);
             ctx->launches++;
             for (int g = 0; g < ng; ++g) {
+                if (use_runs) { run_group(GroupRun{g, 1, 0, 0}); continue; }
                 const int gs = goff[g + 1] - goff[g];
                 for (int j = 0; j < gs; ++j) step(STEP_DIAG, g, j, 0);
                 for (int i1 = 0; i1 < gs; ++i1)
@@ -823,6 +1107,12 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
         // bytes the reference's formulation moves for the same steps: per accepted rank-1 step two
         // factor updates + the solves; reported as the bytes THIS kernel moves: 16 p² per accepted step
         info->touched_bytes = 16.0 * (double)p * (double)p * hstate[ST_ACCEPTED];
+        if (use_runs) {
+            // delayed updates: D⁻¹ is streamed once per RUN with an accepted step (upper bound: every run), plus the panels
+            double runs = 0.0;
+            for (int i = 0; i < inner_sweeps; ++i) runs += (info->trace_kind[i] == 0) ? (double)pca_runs.size() : (double)ng;
+            info->touched_bytes = runs * (16.0 * (double)p * (double)p + 24.0 * (double)p * gmax);
+        }
     }
     return KB_OK;
 }

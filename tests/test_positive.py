@@ -21,25 +21,34 @@ def pctx(kb):
 
 @pytest.mark.parametrize("p,kind", [(1, "pd"), (63, "pd"), (64, "semidef"), (65, "indef"), (200, "semidef"), (300, "indef"), (130, "pd")])
 def test_positive_factor_matches_restatement(kb, pctx, p, kind):
+    """Well-posed inputs only: an unpivoted LDL' of a singular AND indefinite matrix has rounding-level pivots of arbitrary
+    sign.  pd: ordinary factor.  indef: full rank with 3 negative eigenvalues (d carries the inertia).  semidef: the last 7
+    variables duplicate the first 7 exactly, so their pivots are rounding noise far below tol and are dropped."""
     rng = np.random.default_rng(p)
-    r = p if kind == "pd" else max(1, p - 7)
-    B = rng.standard_normal((p, r))
-    A = B @ B.T / p + (0.3 * np.eye(p) if kind == "pd" else 0.0)
-    if kind == "indef":
-        v = rng.standard_normal((p, 3))
-        A -= v @ v.T / p
+    if kind == "semidef":
+        G = rng.standard_normal((p - 7, p + 5))
+        M = np.vstack([G, G[:7]])
+        A = M @ M.T / p
+    else:
+        B = rng.standard_normal((p, p + 5))
+        A = B @ B.T / p + 0.3 * np.eye(p)
+        if kind == "indef":
+            v = rng.standard_normal((p, 3))
+            A -= 4.0 * v @ v.T / p
     L, d, mod = kb.hook_potrf_positive(A, ctx=pctx)
     Lw, dw = ko.cholesky_positive(A)
     if kind == "pd":
         assert mod == 0 and np.all(d == 1) and np.max(np.abs(L - np.linalg.cholesky(A))) < 1e-11
         return
     assert np.array_equal(d, dw) and mod == int(np.sum(dw != 1))
-    # the factor is only defined to the conditioning of the kept pivots: compare through L D L' = A on the kept columns
-    keep = dw != 0
+    if kind == "indef":
+        assert int(np.sum(d == -1)) == 3 and not np.any(d == 0)          # Sylvester: the inertia of A
+    else:
+        assert int(np.sum(d == 0)) == 7 and np.all(np.diag(L)[d == 0] == 1.0)
+    assert np.max(np.abs(L - Lw)) < 1e-8 * max(1.0, np.abs(Lw).max())
     R = (L * d) @ L.T
-    Rw = (Lw * dw) @ Lw.T
-    assert np.max(np.abs(R - Rw)) < 1e-8 * max(1.0, np.abs(Rw).max())
-    assert np.all(np.diag(L)[~keep] == 1.0)
+    keep = d != 0
+    assert np.max(np.abs(R[np.ix_(keep, keep)] - A[np.ix_(keep, keep)])) < 1e-9 * max(1.0, np.abs(A).max())
 
 
 @pytest.mark.parametrize("m", [1, 3])
