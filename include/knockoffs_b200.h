@@ -401,6 +401,11 @@ int kb_test_dgemm(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_
 int kb_test_dgemm_dev(kb_ctx* ctx, int32_t transa, int32_t transb, int64_t M, int64_t N, int64_t K, double alpha,
                       const double* dA, int64_t lda, const double* dB, int64_t ldb, double beta, double* dC,
                       int64_t ldc);
+/* measurement variant of the same product with TMA-staged operands (cp.async.bulk.tensor + mbarrier ring, 128-byte swizzle;
+ * csrc/dgemm_tma.cu): C = alpha*A*B + beta*C, A M x K with m contiguous, B K x N with k contiguous, device pointers,
+ * 16-byte aligned with even leading dimensions. */
+int kb_test_dgemm_tma_dev(kb_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* dA, int64_t lda,
+                          const double* dB, int64_t ldb, double beta, double* dC, int64_t ldc);
 /* structure of factor blocks as the sampling stage detects it: band_out = 0 (every M_k = L_kk + upper triangular:
  * Diagonal(s)), a multiple of 16 up to 64 (banded below the diagonal: contiguous group blocks) or -1 (general form). */
 int kb_test_factor_band(kb_ctx* ctx, const double* Lblocks, int64_t p, int32_t m, int32_t* band_out);

@@ -118,6 +118,7 @@ SIGNATURES = {
     "kb_multi_solve_s_group_blockdiag": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i32, _d, C.POINTER(GroupOpts), _vp, c_double_p, _vp]),
     "kb_test_dgemm": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_dgemm_dev": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
+    "kb_test_dgemm_tma_dev": (C.c_int, [_vp, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64]),
     "kb_test_factor_band": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_int32)]),
     "kb_test_potrf": (C.c_int, [_vp, _vp, _i64, _vp]),
     "kb_test_potrf_positive": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.POINTER(C.c_int32)]),

@@ -1,0 +1,233 @@
+// TMA + mbarrier variant of the FP64 tensor-core GEMM (measurement variant, VERDICT r01 item 6 / north_star "TMA-staged
+// tiles"): C (M x N) = alpha * A * B + beta * C for the sampling stage's layouts -- A column-major M x K (m contiguous),
+// B column-major K x N (k contiguous) -- with the operand tiles staged by `cp.async.bulk.tensor` (SASS UTMALDG) into
+// 128-byte-swizzled shared memory and a 4-stage full / empty mbarrier ring fed by ONE producer warp, instead of the
+// LDGSTS (cp.async) pipeline + padded rows of dgemm_dmma.cuh.  The math is the same warp-level DMMA (mma.sync m8n8k4.f64;
+// tcgen05 has no f64 kind).
+//
+// Shared-memory layout per stage (16 KB, no padding):
+//   A: BM/16 boxes of {16 m, 16 k}: k-row of 128 bytes, 16-byte chunks XOR-swizzled by (k & 7)     (SWIZZLE_128B)
+//   B: one box {16 k, BN n}:        n-row of 128 bytes, 16-byte chunks XOR-swizzled by (n & 7)
+// A DMMA fragment reads (slot = lane / 4, k = lane % 4).  With the identity slot -> row map the swizzle would leave 2-way
+// bank conflicts, so the 8 slots of a fragment are mapped to rows by a fixed permutation (sigma for A inside a 16-row box,
+// rho for B inside an 8-row group) under which the 16 lanes of a half-warp hit 16 distinct 8-byte banks; the epilogue
+// applies the same permutation to the output coordinates.
+#include "kb_common.cuh"
+#include "dgemm_dmma.cuh"
+#include <cuda.h>
+#include <cstdlib>
+
+namespace kb {
+
+constexpr int TBM = 64, TBN = 64, TBK = 16, TSTAGES = 4;
+constexpr int T_CONSUMER_WARPS = 4, T_THREADS = 32 * (T_CONSUMER_WARPS + 1);
+constexpr int T_A_BYTES = TBM * TBK * 8, T_B_BYTES = TBN * TBK * 8, T_STAGE_BYTES = T_A_BYTES + T_B_BYTES;
+constexpr size_t T_SMEM = (size_t)TSTAGES * T_STAGE_BYTES + 1024 /* alignment slack */ + 2 * TSTAGES * 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// slot -> row permutations (see the header comment)
+__device__ __forceinline__ int sigma16(int slot, int half) { return (slot & 1) + ((slot >> 1) & 1) * 8 + (slot >> 2) * 2 + half * 4; }
+__device__ __forceinline__ int rho8(int slot) { return (slot & 3) * 2 + (slot >> 2); }
+
+__global__ void __launch_bounds__(T_THREADS, 3)
+dgemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int M, int N, int K,
+                 double alpha, double beta, double* __restrict__ C, long ldc) {
+    extern __shared__ unsigned char tsm_raw[];
+    unsigned char* tsm = (unsigned char*)(((uintptr_t)tsm_raw + 1023) & ~(uintptr_t)1023);      // SWIZZLE_128B: 1024-byte aligned
+    unsigned long long* full_bar = (unsigned long long*)(tsm + (size_t)TSTAGES * T_STAGE_BYTES);
+    unsigned long long* empty_bar = full_bar + TSTAGES;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // same grouped rasterisation as dgemm_dmma_kernel
+    int bx, by;
+    {
+        constexpr int GROUP_M = 16;
+        const int num_m = gridDim.x, num_n = gridDim.y;
+        const int pid = blockIdx.x + blockIdx.y * num_m;
+        const int per_group = GROUP_M * num_n;
+        const int first_m = (pid / per_group) * GROUP_M;
+        const int gsz = min(num_m - first_m, GROUP_M);
+        const int in_group = pid % per_group;
+        bx = first_m + in_group % gsz;
+        by = in_group / gsz;
+    }
+    const int m0 = bx * TBM, n0 = by * TBN;
+    const int nkt = (K + TBK - 1) / TBK;
+    if (tid == 0) {
+        for (int s = 0; s < TSTAGES; ++s) {
+            mbar_init(&full_bar[s], 1);                       // the producer's arrive.expect_tx (+ the TMA byte count)
+            mbar_init(&empty_bar[s], T_CONSUMER_WARPS);       // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == T_CONSUMER_WARPS) {
+        // ---- producer warp: one lane feeds the ring ----
+        if (lane == 0) {
+            for (int kt = 0; kt < nkt; ++kt) {
+                const int s = kt % TSTAGES;
+                const unsigned round = (unsigned)(kt / TSTAGES);
+                if (kt >= TSTAGES) mbar_wait(&empty_bar[s], (round - 1) & 1);     // all consumer warps released use `round − 1`
+                unsigned char* As = tsm + (size_t)s * T_STAGE_BYTES;
+                unsigned char* Bs = As + T_A_BYTES;
+                mbar_expect_tx(&full_bar[s], T_STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < TBM / 16; ++j) tma_load_2d(As + j * 2048, &mapA, m0 + 16 * j, kt * TBK, &full_bar[s]);
+                tma_load_2d(Bs, &mapB, kt * TBK, n0, &full_bar[s]);
+            }
+        }
+        return;
+    }
+    // ---- consumer warps: 2 x 2 layout, 32 x 32 per warp = 4 x 4 DMMA tiles ----
+    const int wm = warp >> 1, wn = warp & 1;
+    const int lr = lane >> 2, lc = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // per-thread constant parts of the fragment addresses (in doubles)
+    int a_off[4], a_mm[4], b_off[4], b_n7[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int box = wm * 2 + (i >> 1);
+        const int mm = sigma16(lr, i & 1);
+        a_off[i] = box * 256 + (mm & 1);
+        a_mm[i] = mm >> 1;                       // 16-byte chunk of this row inside the 128-byte k-row
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = wn * 32 + j * 8 + rho8(lr);
+        b_off[j] = n * 16;
+        b_n7[j] = n & 7;
+    }
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int s = kt % TSTAGES;
+        mbar_wait(&full_bar[s], (unsigned)(kt / TSTAGES) & 1);
+        const double* As = (const double*)(tsm + (size_t)s * T_STAGE_BYTES);
+        const double* Bs = As + T_A_BYTES / 8;
+#pragma unroll
+        for (int kk = 0; kk < TBK / 4; ++kk) {
+            const int k = kk * 4 + lc;
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[a_off[i] + k * 16 + ((a_mm[i] ^ (k & 7)) << 1)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bs[b_off[j] + (((k >> 1) ^ b_n7[j]) << 1) + (k & 1)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    // ---- epilogue (permuted coordinates) ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + wm * 32 + (i >> 1) * 16 + sigma16(lr, i & 1);
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = n0 + wn * 32 + j * 8 + rho8(2 * lc + e);
+                if (n >= N) continue;
+                double v = alpha * acc[i][j][e];
+                if (beta != 0.0) v += beta * C[(long)m + (long)n * ldc];
+                C[(long)m + (long)n * ldc] = v;
+            }
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*fn_encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static fn_encode_tiled get_encode() {
+    static fn_encode_tiled f = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (fn_encode_tiled)p;
+    }();
+    return f;
+}
+
+// column-major rows x cols matrix of doubles (leading dimension ld), box {b0 rows, b1 cols}, 128-byte swizzle
+static int make_map(kb_ctx* ctx, CUtensorMap* map, const double* base, long rows, long cols, long ld, int b0, int b1) {
+    fn_encode_tiled enc = get_encode();
+    if (!enc) return set_error(ctx, KB_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    const cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(ctx, KB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return KB_OK;
+}
+
+// C = alpha * A * B + beta * C, A: M x K (m contiguous, lda), B: K x N (k contiguous, ldb); device pointers; enqueued on
+// ctx's stream.  Base pointers 16-byte aligned and leading dimensions even (TMA global strides are multiples of 16 bytes).
+int gemm_tma_nn(kb_ctx* ctx, int M, int N, int K, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
+                double* C, long ldc) {
+    if (M <= 0 || N <= 0 || K <= 0) return KB_OK;
+    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1))
+        return set_error(ctx, KB_ERR_INVALID, "gemm_tma: operands must be 16-byte aligned with even leading dimensions");
+    CUtensorMap mapA, mapB;
+    KB_TRY(make_map(ctx, &mapA, A, M, K, lda, 16, TBK));       // dim0 = m (contiguous), dim1 = k
+    KB_TRY(make_map(ctx, &mapB, B, K, N, ldb, TBK, TBN));      // dim0 = k (contiguous), dim1 = n
+    KB_CUDA(ctx, raise_max_dynamic_smem((const void*)dgemm_tma_kernel, T_SMEM));
+    dim3 grid(ceil_div(M, TBM), ceil_div(N, TBN));
+    dgemm_tma_kernel<<<grid, T_THREADS, T_SMEM, ctx->stream>>>(mapA, mapB, M, N, K, alpha, beta, C, ldc);
+    ctx->launches++;
+    ctx->flops += 2.0 * M * N * (double)K;
+    KB_CUDA(ctx, cudaGetLastError());
+    return KB_OK;
+}
+
+}  // namespace kb
+
+extern "C" int kb_test_dgemm_tma_dev(kb_ctx* ctx, int64_t M, int64_t N, int64_t K, double alpha, const double* dA, int64_t lda,
+                                     const double* dB, int64_t ldb, double beta, double* dC, int64_t ldc) {
+    if (!ctx) return KB_ERR_INVALID;
+    if (!dA || !dB || !dC || M < 0 || N < 0 || K < 0) return kb::set_error(ctx, KB_ERR_INVALID, "test_dgemm_tma: bad arguments");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != ctx->device) cudaSetDevice(ctx->device);
+    const int rc = kb::gemm_tma_nn(ctx, (int)M, (int)N, (int)K, alpha, dA, (long)lda, dB, (long)ldb, beta, dC, (long)ldc);
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+    return rc;
+}
