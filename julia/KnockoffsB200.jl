@@ -29,6 +29,9 @@ mutable struct Context
         rc = ccall((:kb_create, libkb), Cint, (Ptr{Ptr{Cvoid}}, Cint), r, device)
         rc == 0 || error("kb_create failed ($rc): no usable CUDA device")
         ctx = new(r[])
+        # `condition` uses cholesky(Positive, ·) in the reference (modelX.jl:111,120): opt in to the library's restatement
+        # of it (parity unpinned, see include/knockoffs_b200.h) so :equi and boundary solutions return knockoffs here too
+        ccall((:kb_set_positive_cholesky, libkb), Cint, (Ptr{Cvoid}, Int32), ctx.h, 1)
         finalizer(c -> ccall((:kb_destroy, libkb), Cvoid, (Ptr{Cvoid},), c.h), ctx)
     end
 end
@@ -81,6 +84,70 @@ function modelX_gaussian_knockoffs(X::Matrix{Float64}, method::Union{Symbol,Stri
         check(c, rc)
     end
     return GaussianKnockoff(X, Xko, s, Symmetric(Σd), Symbol(method), mi)   # src/struct.jl:6-13, fields unchanged
+end
+
+"Drop-in for `condition(X, μ, Σ, S; m)` (src/modelX.jl:96-122); S::Diagonal or dense.  One call: Σ⁻¹S and the factor stay on the device."
+function condition(X::Matrix{Float64}, μ::Vector{Float64}, Σ::AbstractMatrix{Float64}, S::AbstractMatrix{Float64};
+                   m::Number=1, seed::Integer=rand(UInt64))
+    c = ctx(); n, p = size(X); mi = Int(m)
+    mi < 1 && error("m should be 1 or larger but was $m.")
+    Σd = Matrix{Float64}(Σ isa Symmetric ? Σ.data : Σ)
+    isdiag = S isa Diagonal
+    Sd = isdiag ? Vector{Float64}(S.diag) : Matrix{Float64}(S)
+    Xko = Matrix{Float64}(undef, n, mi * p)
+    GC.@preserve X μ Σd Sd Xko begin
+        rc = ccall((:kb_condition, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{Float64},
+                    UInt64, Int64, Ptr{Float64}),
+                   c.h, X, n, p, μ, Σd, Sd, isdiag, mi, C_NULL, seed, 0, Xko)
+        check(c, rc)
+    end
+    return Xko
+end
+
+# ---- several GPUs behind one handle (kb_create_multi; SURVEY 8b / 8e) ------------------------------------
+# One Julia process drives all GPUs: the library runs one host thread per device.  Rows of X are sharded for `condition`
+# and for the Gram (one peer-to-peer all-reduce over NVLink); the CCD solve itself stays on device 0 (sequential sweep).
+mutable struct MultiContext
+    h::Ptr{Cvoid}
+    function MultiContext(devices::Vector{<:Integer}=collect(0:7))
+        r = Ref{Ptr{Cvoid}}(C_NULL); d = Cint.(devices)
+        rc = ccall((:kb_create_multi, libkb), Cint, (Ptr{Ptr{Cvoid}}, Ptr{Cint}, Int32), r, d, length(d))
+        rc == 0 || error("kb_create_multi failed ($rc)")
+        mc = new(r[])
+        finalizer(x -> ccall((:kb_destroy_multi, libkb), Cvoid, (Ptr{Cvoid},), x.h), mc)
+    end
+end
+function check(mc::MultiContext, rc::Integer)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:kb_multi_last_error, libkb), Cstring, (Ptr{Cvoid},), mc.h))
+    rc == -2 && throw(PosDefException(0))
+    error(msg)
+end
+"`modelX_gaussian_knockoffs` on all GPUs of `mc` (same result as the single-GPU call: the RNG is keyed by the global row)."
+function modelX_gaussian_knockoffs(mc::MultiContext, X::Matrix{Float64}, method::Union{Symbol,String}, μ::Vector{Float64},
+                                   Σ::AbstractMatrix{Float64}; m::Number=1, seed::Integer=rand(UInt64), kwargs...)
+    n, p = size(X); mi = Int(m)
+    Xko = Matrix{Float64}(undef, n, mi * p); s = Vector{Float64}(undef, p)
+    Σd = Matrix{Float64}(Σ isa Symmetric ? Σ.data : Σ)
+    o = Ref(opts(; kwargs...)); info = Ref{SolveInfo}()
+    GC.@preserve X μ Σd Xko s begin
+        rc = ccall((:kb_multi_modelx_gaussian_knockoffs, libkb), Cint,
+                   (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Ptr{SolveOpts},
+                    Ptr{Float64}, Ptr{Float64}, UInt64, Ptr{Float64}, Ptr{Float64}, Ptr{SolveInfo}),
+                   mc.h, X, n, p, μ, Σd, METHODS[Symbol(method)], mi, o, C_NULL, C_NULL, seed, Xko, s, info)
+        check(mc, rc)
+    end
+    return GaussianKnockoff(X, Xko, s, Symmetric(Σd), Symbol(method), mi)
+end
+"Σ̂ = Xc'Xc/n and the column means with the rows of X sharded over the GPUs of `mc`."
+function gram(mc::MultiContext, X::Matrix{Float64})
+    n, p = size(X); G = Matrix{Float64}(undef, p, p); μ = Vector{Float64}(undef, p)
+    GC.@preserve X G μ begin
+        check(mc, ccall((:kb_multi_gram, libkb), Cint,
+                        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int32, Float64, Ptr{Float64}, Ptr{Float64}), mc.h, X, n, p, 1, 0.0, G, μ))
+    end
+    return Symmetric(G), μ
 end
 
 # ---- group knockoffs (src/group.jl:109-127, 348-422) ---------------------------------------------------

@@ -1056,22 +1056,23 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
         ++inner_sweeps;
         return KB_OK;
     };
-    KB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    for (int it = 0; it < opts.outer_iter; ++it) {
-        ++outer_done;
-        bool conv1 = opts.inner_pca_iter == 0, conv2 = opts.inner_ccd_iter == 0;
-        for (int l = 0; l < opts.inner_pca_iter; ++l) {                       // _X_pca_ccd_iter!
-            group_sweep_begin_kernel<<<1, 1, 0, st>>>(G);
-            ctx->launches++;
+    // A sweep is a fixed sequence of launches with fixed arguments: with the per-group runs it is captured ONCE into a
+    // CUDA graph per sweep kind (3 kernels per group) and replayed, so the host pays one graph launch per sweep instead of
+    // 3·ng kernel launches (the solve was launch-bound: 8 LD blocks of configs[3] on one GPU share one driver lock).
+    // KB_GROUP_GRAPH=0 keeps the plain launches.
+    static const bool use_graph_env = [] { const char* e = getenv("KB_GROUP_GRAPH"); return !(e && e[0] == '0'); }();
+    struct SweepGraph {
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long launches = 0;
+        ~SweepGraph() { if (exec) cudaGraphExecDestroy(exec); }
+    } graphs[2];
+    auto sweep_body = [&](int kind) {
+        group_sweep_begin_kernel<<<1, 1, 0, st>>>(G);
+        ctx->launches++;
+        if (kind == 0) {
             if (use_runs) for (const GroupRun& r : pca_runs) run_group(r);
             else for (int jv = 0; jv < nv; ++jv) step(STEP_PCA, vgrp[jv], jv, 0);
-            bool c = false;
-            KB_TRY(end_sweep(0, &c));
-            if (c) { conv1 = true; break; }
-        }
-        for (int l = 0; l < opts.inner_ccd_iter; ++l) {                       // _X_ccd_iter!
-            group_sweep_begin_kernel<<<1, 1, 0, st>>>(G);
-            ctx->launches++;
+        } else {
             for (int g = 0; g < ng; ++g) {
                 if (use_runs) { run_group(GroupRun{g, 1, 0, 0}); continue; }
                 const int gs = goff[g + 1] - goff[g];
@@ -1079,6 +1080,48 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
                 for (int i1 = 0; i1 < gs; ++i1)
                     for (int i2 = i1 + 1; i2 < gs; ++i2) step(STEP_OFFDIAG, g, i2, i1);   // (i, j) = (idx2, idx1)
             }
+        }
+    };
+    auto run_sweep = [&](int kind) -> int {
+        if (!(use_runs && use_graph_env)) { sweep_body(kind); return KB_OK; }
+        SweepGraph& sg = graphs[kind];
+        if (!sg.exec) {
+            const unsigned long long l0 = ctx->launches;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                sweep_body(kind);
+                return KB_OK;
+            }
+            sweep_body(kind);
+            const cudaError_t e1 = cudaStreamEndCapture(st, &graph);
+            sg.launches = ctx->launches - l0;
+            ctx->launches = l0;
+            if (e1 != cudaSuccess || !graph || cudaGraphInstantiate(&sg.exec, graph, 0) != cudaSuccess) {
+                cudaGetLastError();
+                if (graph) cudaGraphDestroy(graph);
+                sg.exec = nullptr;
+                sweep_body(kind);           // capture unavailable: plain launches
+                return KB_OK;
+            }
+            cudaGraphDestroy(graph);
+        }
+        KB_CUDA(ctx, cudaGraphLaunch(sg.exec, st));
+        ctx->launches += sg.launches;
+        return KB_OK;
+    };
+    KB_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    for (int it = 0; it < opts.outer_iter; ++it) {
+        ++outer_done;
+        bool conv1 = opts.inner_pca_iter == 0, conv2 = opts.inner_ccd_iter == 0;
+        for (int l = 0; l < opts.inner_pca_iter; ++l) {                       // _X_pca_ccd_iter!
+            KB_TRY(run_sweep(0));
+            bool c = false;
+            KB_TRY(end_sweep(0, &c));
+            if (c) { conv1 = true; break; }
+        }
+        for (int l = 0; l < opts.inner_ccd_iter; ++l) {                       // _X_ccd_iter!
+            KB_TRY(run_sweep(1));
             bool c = false;
             KB_TRY(end_sweep(1, &c));
             if (c) { conv2 = true; break; }

@@ -11,6 +11,7 @@
 #include "linalg.cuh"
 #include "pipeline.cuh"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <unordered_map>
@@ -201,6 +202,11 @@ int make_perm(kb_ctx* ctx, int p, const std::vector<int>& reps, Perm* P) {
 int choose_group_reps_host(kb_ctx* ctx, const double* Sigma, long lds, int p, const int64_t* groups, double threshold,
                            bool has_prior, const std::vector<int>& prioritize, std::vector<int>* reps_out) {
     SymView S{Sigma, lds};
+    static const bool trace = getenv("KB_REP_TRACE") != nullptr;     // phase timings on stderr
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    };
     for (int i = 0; i < p; ++i)
         if (!isapprox(S(i, i), 1.0))                                 // group.jl:1932
             return set_error(ctx, KB_ERR_INVALID, "Σ must be scaled to a correlation matrix first.");
@@ -251,6 +257,8 @@ int choose_group_reps_host(kb_ctx* ctx, const double* Sigma, long lds, int p, co
         return KB_OK;
     }
     // all columns linearly independent: Σinv on the device (group.jl:1978), then g x g work per group
+    const double t_prepass = since(t_start);
+    const auto t_inv0 = std::chrono::steady_clock::now();
     std::vector<double> Sinv((size_t)p * p);
     {
         Scope sc(ctx);
@@ -263,6 +271,8 @@ int choose_group_reps_host(kb_ctx* ctx, const double* Sigma, long lds, int p, co
         KB_CUDA(ctx, cudaMemcpyAsync(Sinv.data(), dI, sizeof(double) * p * p, cudaMemcpyDeviceToHost, ctx->stream));
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    const double t_inv = since(t_inv0);
+    const auto t_grp0 = std::chrono::steady_clock::now();
     SymView SI{Sinv.data(), (long)p};
     // unique(groups) in order of first appearance, members ascending
     std::unordered_map<int64_t, int> gid;
@@ -321,6 +331,9 @@ int choose_group_reps_host(kb_ctx* ctx, const double* Sigma, long lds, int p, co
     }
     std::sort(reps.begin(), reps.end());
     *reps_out = reps;
+    if (trace)
+        fprintf(stderr, "[choose_group_reps p=%d] dependent-column pre-pass %.3f s, inv(Sigma) on the device + D2H %.3f s, per-group "
+                        "selection %.3f s\n", p, t_prepass, t_inv, since(t_grp0));
     return KB_OK;
 }
 

@@ -62,6 +62,7 @@ del X2
 p3, n3 = 2000, 5000
 groups = np.repeat(np.arange(1, p3 // 5 + 1), 5)
 S3 = np.asfortranarray(ko.simulate_block_covariance(groups, 0.75, 0.25))
+kb.choose_group_reps(S3, groups, threshold=0.5, ctx=ctx)          # warm-up: workspace + module load
 t_reps, reps = timed(lambda: kb.choose_group_reps(S3, groups, threshold=0.5, ctx=ctx))
 X3 = np.asfortranarray(rng.standard_normal((n3, p3)) @ np.linalg.cholesky(S3).T)
 t_all, rr = timed(lambda: kb.modelX_gaussian_rep_group_knockoffs(X3, "maxent", groups, np.zeros(p3), S3, m=1, seed=3,
