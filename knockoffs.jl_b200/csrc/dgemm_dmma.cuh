@@ -8,8 +8,11 @@
 // cp.async (LDGSTS) pipeline, 16-byte transactions, padded rows so that every fragment load is
 // bank-conflict free.
 //
-// CTA tile 128 x 128 x 16, 256 threads = 8 warps laid out 2 (M) x 4 (N); a warp owns 64 x 32 =
-// 8 x 4 DMMA tiles (64 accumulator doubles per thread).
+// Default CTA tile 64 x 64 x 16, 128 threads = 4 warps laid out 2 (M) x 2 (N), a warp owns 32 x 32 = 4 x 4 DMMA tiles
+// (32 accumulator doubles per thread), 3 CTAs per SM (GemmCfg below; the 128 x 128 / 8-warp tile of early round 1 and
+// the 64 x 128 tile are kept as build-time variants, profiles/r01_gemm_variants.md).  A TMA-staged variant of the same
+// inner loop (cp.async.bulk.tensor + mbarrier ring, 128-byte swizzle) lives in dgemm_tma.cu; profiles/r02_gemm_variants.md
+// has the A/B measurement.
 //
 // Up to 3 K-segments (A_i, B_i) are accumulated into one tile so that the sampling stage
 // X̃ = X − X·ΣinvS + Z·L (+ T·M) is ONE fused GEMM.  Each segment may declare triangular

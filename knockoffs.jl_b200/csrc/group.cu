@@ -998,8 +998,14 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
     KB_TRY(fill_zero(ctx, dWv, (size_t)2 * ld));
 
     // Delayed updates per group (group_run_* kernels) whenever every group fits; KB_GROUP_MODE=step forces the per-step kernels.
-    static const bool force_step = [] { const char* e = getenv("KB_GROUP_MODE"); return e && e[0] == 's'; }();
-    const bool use_runs = !force_step && gmax <= GB_MAX;
+    // Group :sdp stays on the per-step kernels by default: its PCA line search is Brent on a piecewise-LINEAR objective whose
+    // minimum is often a flat interval, so which minimiser is returned -- and with it the whole iterate path and, through the
+    // loose relative stopping rule, even the final objective -- depends on rounding-level details (the oracle, a host build
+    // of this very Brent and the GPU already pick three different points on the first step of the runtests.jl:546-625
+    // problem).  The delayed-update recurrences change rounding, hence the path; MVR / ME have smooth line searches and
+    // agree with the oracle at 1e-8 either way.  KB_GROUP_MODE=runs forces the delayed updates for :sdp as well.
+    static const int mode_env = [] { const char* e = getenv("KB_GROUP_MODE"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'r' ? 2 : 0)); }();
+    const bool use_runs = mode_env != 1 && gmax <= GB_MAX && (method != KB_METHOD_SDP_CCD || mode_env == 2);
     double *dWp = nullptr, *dEpart = nullptr, *dQ = nullptr;
     int* dflag = nullptr;
     const int nslab = ceil_div(p, GB_SLAB);
@@ -1058,9 +1064,10 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
     };
     // A sweep is a fixed sequence of launches with fixed arguments: with the per-group runs it is captured ONCE into a
     // CUDA graph per sweep kind (3 kernels per group) and replayed, so the host pays one graph launch per sweep instead of
-    // 3·ng kernel launches (the solve was launch-bound: 8 LD blocks of configs[3] on one GPU share one driver lock).
-    // KB_GROUP_GRAPH=0 keeps the plain launches.
-    static const bool use_graph_env = [] { const char* e = getenv("KB_GROUP_GRAPH"); return !(e && e[0] == '0'); }();
+    // 3·ng kernel launches.  OFF by default: measured on B200 with the 8 LD blocks of configs[3] sweeping concurrently on one
+    // GPU (8 contexts), graph replay was SLOWER than plain launches (568 vs 304-343 ms of device time per block, r02g) --
+    // the eight 750-node graphs overlap worse than eight plain streams.  KB_GROUP_GRAPH=1 enables it.
+    static const bool use_graph_env = [] { const char* e = getenv("KB_GROUP_GRAPH"); return e && e[0] == '1'; }();
     struct SweepGraph {
         cudaGraphExec_t exec = nullptr;
         unsigned long long launches = 0;

@@ -21,17 +21,28 @@ def run(which, M, N, K, A, B, C, lda, ldb, ldc, alpha=1.0, beta=0.0):
 
 
 ok = True
-for (M, N, K) in [(64, 64, 16), (64, 64, 64), (130, 70, 50), (257, 131, 77), (1000, 500, 333), (4096, 5000, 5000)]:
+for (M, N, K) in [(64, 64, 16), (64, 64, 64), (130, 70, 50), (257, 131, 77), (1000, 500, 333), (64, 64, 5000), (2048, 64, 64),
+                  (64, 5000, 64), (1024, 1024, 1024), (4096, 4096, 512), (4096, 5000, 5000)]:
     lda, ldb, ldc = (M + 1) & ~1, (K + 1) & ~1, M
     A = torch.randn((K, lda), dtype=f64, device=d)
     B = torch.randn((N, ldb), dtype=f64, device=d)
     C0 = torch.randn((N, ldc), dtype=f64, device=d)
     C = C0.clone()
+    torch.cuda.synchronize()             # the inputs are produced on torch's stream, the kernel runs on the library's
     run("tma", M, N, K, A, B, C, lda, ldb, ldc, alpha=0.7, beta=-1.3)
     ext.synchronize()
     want = 0.7 * (B[:, :K] @ A[:, :M]) - 1.3 * C0
     err = float((C - want).abs().max() / want.abs().max())
     print(f"check M={M} N={N} K={K}: max rel err {err:.2e}")
+    if err >= 1e-12:
+        E = ((C - want).abs() / want.abs().max())[:, :M]          # (N, M): E[n, m]
+        nt, mt = (N + 63) // 64, (M + 63) // 64
+        bad = [(mi, ni) for ni in range(nt) for mi in range(mt) if float(E[ni * 64:(ni + 1) * 64, mi * 64:(mi + 1) * 64].max()) >= 1e-12]
+        print(f"   bad 64x64 tiles (m-tile, n-tile): {len(bad)} of {nt * mt}; first {bad[:12]} last {bad[-6:]}")
+        mi, ni = bad[0]
+        sub = E[ni * 64:(ni + 1) * 64, mi * 64:(mi + 1) * 64]
+        print("   inside the first bad tile: bad rows(n)", sorted(set(torch.nonzero(sub >= 1e-12)[:, 0].tolist()))[:20],
+              "bad cols(m)", sorted(set(torch.nonzero(sub >= 1e-12)[:, 1].tolist()))[:20])
     ok = ok and err < 1e-12
 print("correctness:", "OK" if ok else "FAILED")
 print()

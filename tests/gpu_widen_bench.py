@@ -42,7 +42,16 @@ out["N4_fit_marginal_fused"] = {"n": n, "p": p, "m": m, "seconds": t_fused, "row
                                 "selected_at_q0.1": len(sel), "true_positives": len(sel & set(idx)),
                                 "cpu_oracle_scores_seconds_extrapolated": t_cpu * n / rows_cpu,
                                 "cpu_sample": f"numpy z-score + X'y on {rows_cpu} of {n} rows (x n/rows), all BLAS threads"}
-del X, y
+# the same call with X in PAGE-LOCKED host memory (what bench.py's e2e uses); the default above is pageable numpy memory
+import torch
+Xp_t = torch.empty((p, n), dtype=torch.float64, pin_memory=True)
+Xp = Xp_t.numpy().T                                   # (n, p) Fortran-ordered view of the pinned buffer
+Xp[:] = X
+timed(lambda: kb.fit_marginal(y, Xp, mu, Sigma, method="mvr", m=m, keep_knockoffs=False, seed=1, ctx=ctx))
+t_pin, r2 = timed(lambda: kb.fit_marginal(y, Xp, mu, Sigma, method="mvr", m=m, keep_knockoffs=False, seed=1, ctx=ctx))
+out["N4_fit_marginal_fused"].update({"host_memory": "pageable (numpy)", "seconds_pinned_X": t_pin, "rows_per_s_pinned_X": n / t_pin,
+                                      "same_selection_pinned": bool(np.array_equal(r2.selected[2], r.selected[2]))})
+del X, y, Xp, Xp_t
 
 # ---- N2: approx_modelX_gaussian_knockoffs, p = 5000 in windows of 500 --------------------------------------
 n2, p2, m2 = 20000, 5000, 1
