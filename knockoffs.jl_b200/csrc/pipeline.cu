@@ -574,6 +574,12 @@ int sample_plan_create(kb_ctx* ctx, Scope& sc, int p, int m, const double* dmu, 
             factor_upper_part_kernel<<<ew_grid2(ctx, (long)p * p * (m - 1)), 256, 0, ctx->stream>>>(dLb, ldo, (long)bstride, p, m,
                                                                                                   plan->band, plan->N, plan->ld);
             ctx->launches++;
+            // operand tiles of the batched launch staged by TMA (cp.async.bulk.tensor + mbarrier ring) when the buffers
+            // qualify (16-byte aligned, even strides); KB_SAMPLE_TMA=0 keeps the LDGSTS kernel
+            const long tstride = (long)plan->chunk * p;
+            if (sample_tma_usable(plan->T, plan->chunk, tstride, dLb, ldo, 2 * (long)bstride, plan->N, plan->ld, plan->ld * (long)p) &&
+                sample_tma_maps(ctx, &plan->maps, plan->T, plan->chunk, p, m, tstride, dLb, ldo, (long)bstride, plan->N, plan->ld) == KB_OK)
+                plan->tma = true;
         }
     }
     if (need_zbuf) KB_TRY(sc.alloc(&plan->Zbuf, (size_t)plan->chunk * p * m));
@@ -624,6 +630,7 @@ int sample_chunk(kb_ctx* ctx, const SamplePlan& pl, const double* Xc, long rows,
         suffix_sum_incl_kernel<<<ew_grid2(ctx, rows * p), 256, 0, ctx->stream>>>(pl.T, pl.chunk, (long)tstride, Zc, ldzc,
                                                                                  (long)p * ldzc, rows, p, m);
         ctx->launches++;
+        if (pl.tma) return sample_tma_launch(ctx, pl.maps, (int)rows, p, m, pl.band, pl.Mu, pl.chunk, Xko, ldxko);
         GemmParams P{};
         P.M = (int)rows; P.N = p;
         P.seg[0] = GemmSeg{pl.T, pl.chunk, pl.dLb, pl.ldo, p, SEG_KLO_N};                       // S_k L_kk

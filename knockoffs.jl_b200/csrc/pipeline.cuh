@@ -21,6 +21,17 @@ int eigmin_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, double* lambd
 int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const double* dS, long ldS, int s_is_diag,
                     int m, double* dSiS, double* dLb, long ldo);
 
+// TMA tensor maps of the structured sampling launch (dgemm_tma.cu); opaque here (4 CUtensorMap objects)
+struct alignas(64) SampleTmaMaps {
+    unsigned char raw[4 * 128];
+};
+bool sample_tma_usable(const double* T, long ldt, long tstride, const double* L, long ldl, long lstride, const double* Nn, long ldn,
+                       long nstride);
+int sample_tma_maps(kb_ctx* ctx, SampleTmaMaps* out, const double* T, long chunk, int p, int m, long tstride, const double* Lb, long ldo,
+                    long bstride, const double* Nn, long ldn);
+int sample_tma_launch(kb_ctx* ctx, const SampleTmaMaps& mp, int rows, int p, int m, int band, const double* Mu, long ldmu, double* Xko,
+                      long ldxko);
+
 // Row-chunk sampling plan: the per-call constants (−ΣinvS, μ'ΣinvS) and the chunk work buffers.
 struct SamplePlan {
     int p = 0, m = 1;
@@ -37,6 +48,8 @@ struct SamplePlan {
     double* Zbuf = nullptr;    // device-generated Z of the current chunk (chunk x m p)
     const double* dLb = nullptr;
     long ldo = 0;
+    bool tma = false;          // structured launch through the TMA / mbarrier kernel (sample_tma_kernel)
+    SampleTmaMaps maps;
 };
 int sample_plan_create(kb_ctx* ctx, Scope& sc, int p, int m, const double* dmu, const double* dSiS, const double* dLb,
                        long ldo, long chunk, bool need_zbuf, SamplePlan* plan);

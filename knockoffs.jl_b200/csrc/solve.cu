@@ -611,7 +611,9 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
             sweeps_done += hsweeps;
             lam = hcount[2];
             if (info) {
-                for (int l = 0; l < sweeps_done && l < KB_MAX_TRACE; ++l) info->trace[l] = htrace[l];
+                // MVR / maxent: the device trace holds max|δ| per sweep; sdp_ccd: sum(s) per sweep is filled in below
+                if (method != KB_METHOD_SDP_CCD)
+                    for (int l = 0; l < sweeps_done && l < KB_MAX_TRACE; ++l) info->trace[l] = htrace[l];
                 info->updates = hcount[1];
                 info->touched_bytes = (mode == KB_MODE_STREAM) ? 16.0 * CCD_SLOT_ROWS * hcount[0] : block_touched;
                 if (getenv("KB_CCD_PHASES"))
@@ -624,7 +626,9 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
                 if (info && last >= 0 && last < KB_MAX_TRACE) {   // what verbose prints: sum(s) (utilities.jl:313-316)
                     double t = 0.0;
                     for (int i = 0; i < p; ++i) t += hs[i];
-                    info->trace[last] = t;
+                    // a launch of the streaming kernel may cover several sweeps: only its last sweep's s is visible here
+                    for (int l = last - hsweeps + 1; l <= last; ++l)
+                        if (l >= 0) info->trace[l] = t;
                 }
                 if (lam < opts.tol) converged = true;              // utilities.jl:339-340
             } else if (hcount[3] < opts.tol) {
