@@ -144,7 +144,26 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
             G[a][b] = 0.0;
         }
     if (MVR) {
-        for (int sl = 0; sl < nslab; ++sl) {
+        // partial Grams of the 128-row slabs, summed in slab order (deterministic).  Four slabs per round: 64 independent
+        // loads in flight per thread -- one L2 round trip per four slabs instead of one per slab (ncu r01b: this loop was
+        // the kernel's long-scoreboard stall, ~18 % of its 67 us at p = 5000).
+        int sl = 0;
+        for (; sl + 4 <= nslab; sl += 4) {
+            double t[4][16];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double* gp = Gpart + (size_t)(sl + u) * (BW * BW);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) t[u][e] = gp[e * BLK_THREADS + tid];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) G[a][b] += t[u][a * 4 + b];
+        }
+        for (; sl < nslab; ++sl) {
             const double* gp = Gpart + (size_t)sl * (BW * BW);
 #pragma unroll
             for (int a = 0; a < 4; ++a)

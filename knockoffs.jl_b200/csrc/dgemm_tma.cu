@@ -364,7 +364,11 @@ static int make_map3(kb_ctx* ctx, CUtensorMap* map, const double* base, long row
 
 bool sample_tma_usable(const double* T, long ldt, long tstride, const double* L, long ldl, long lstride, const double* Nn, long ldn,
                        long nstride) {
-    static const bool on = [] { const char* e = getenv("KB_SAMPLE_TMA"); return !(e && e[0] == '0'); }();
+    // OFF by default: measured in the sampling stage at p = 5000, m = 5 (r02j) the TMA kernel is 0.6 % slower than the LDGSTS
+    // kernel (1685.4 vs 1675.6 ms per step) although it is 1.4-2.2 % faster on plain GEMM shapes (profiles/r02_gemm_variants.md).
+    // KB_SAMPLE_TMA=1 switches it on (read at every plan creation, so a test can toggle it).
+    const char* e = getenv("KB_SAMPLE_TMA");
+    const bool on = e && e[0] == '1';
     auto ok = [](const void* p_, long ld, long zs) { return !((uintptr_t)p_ & 15) && !(ld & 1) && !(zs & 1); };
     return on && get_encode() && ok(T, ldt, tstride) && ok(L, ldl, lstride) && (Nn == nullptr || ok(Nn, ldn, nstride));
 }

@@ -630,3 +630,25 @@ def test_pinned_and_pageable_host_buffers_give_identical_results(kb, ctx):
         assert np.max(np.abs(outs[0] - want)) < XKO_TOL
     finally:
         ctx.set_sample_chunk_rows(0)
+
+
+def test_tma_staged_sampling_kernel_matches_ldgsts_kernel(kb, ctx):
+    """The batched structured sampling launch exists in two forms: LDGSTS / padded rows (default) and TMA
+    (cp.async.bulk.tensor + mbarrier ring, 128-byte swizzle, csrc/dgemm_tma.cu; KB_SAMPLE_TMA=1).  Same X-tilde."""
+    import os
+    rng = np.random.default_rng(41)
+    n, p, m = 700, 192, 3
+    Sigma = toeplitz(p, 0.5)
+    X = np.asfortranarray(rng.standard_normal((n, p)) @ np.linalg.cholesky(Sigma).T)
+    Z = np.asfortranarray(rng.standard_normal((n, m * p)))
+    mu = rng.standard_normal(p) * 0.1
+    s = kb.solve_s(Sigma, "mvr", m=m, ctx=ctx)
+    a = kb.condition(X, mu, Sigma, s, m=m, Z=Z, ctx=ctx)
+    os.environ["KB_SAMPLE_TMA"] = "1"
+    try:
+        b = kb.condition(X, mu, Sigma, s, m=m, Z=Z, ctx=ctx)
+    finally:
+        del os.environ["KB_SAMPLE_TMA"]
+    want = ko.condition(X, mu, Sigma, s, m=m, Z=Z)
+    assert np.max(np.abs(b - want)) < XKO_TOL and np.max(np.abs(a - want)) < XKO_TOL
+    assert np.max(np.abs(a - b)) < 1e-12
