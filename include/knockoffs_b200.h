@@ -112,6 +112,12 @@ typedef struct {
 
 /* ---- context ----------------------------------------------------------------------------- */
 int kb_create(kb_ctx** ctx, int device);
+/* A context for THROUGHPUT work that is to run beside another context's latency-bound solve on the same GPU (e.g. sampling
+ * the :mvr knockoffs while the :sdp_ccd solve of configs[2] is sweeping): all of its kernels -- main stream included -- are
+ * confined to the SM partition that leaves KB_GREEN_SMS (default 16) SMs free and run at the lowest stream priority, so the
+ * single-CTA chain kernels of the foreground context always find a free SM.  Falls back to an ordinary low-priority context
+ * when the driver has no green contexts.  Same API as a kb_create context. */
+int kb_create_background(kb_ctx** ctx, int device);
 void kb_destroy(kb_ctx* ctx);
 const char* kb_last_error(const kb_ctx* ctx);
 const char* kb_version(void);

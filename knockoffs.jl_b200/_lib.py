@@ -48,6 +48,7 @@ class GroupInfo(C.Structure):
 _vp, _i32, _i64, _u64, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
 SIGNATURES = {
     "kb_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "kb_create_background": (C.c_int, [C.POINTER(_vp), C.c_int]),
     "kb_destroy": (None, [_vp]),
     "kb_last_error": (C.c_char_p, [_vp]),
     "kb_version": (C.c_char_p, []),

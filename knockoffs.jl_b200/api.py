@@ -33,10 +33,12 @@ def _ptr(a):
 class Context:
     """One per host thread / device (include/knockoffs_b200.h: kb_create)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, background: bool = False):
+        """``background=True``: kb_create_background -- every kernel of this context is confined to the SM partition that
+        leaves a few SMs free, for throughput work (sampling) that runs beside another context's solve on the same GPU."""
         self._lib = _lib.load()
         h = C.c_void_p()
-        rc = self._lib.kb_create(C.byref(h), int(device))
+        rc = (self._lib.kb_create_background if background else self._lib.kb_create)(C.byref(h), int(device))
         if rc != 0:
             raise _lib.KnockoffsError(rc, f"kb_create(device={device}) failed: no usable CUDA device "
                                           "(knockoffs_b200 has no CPU fallback)")

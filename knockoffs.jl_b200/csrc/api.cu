@@ -255,7 +255,7 @@ int bad_ctx() { return KB_ERR_INVALID; }
 // kernel) always find a free SM while a rank-256 pass / trailing update runs beside them.  Without the partition the block
 // scheduler back-fills every freed slot with GEMM CTAs and the chain kernel waits for the GEMM grid to drain.
 // Returns false (and leaves ctx untouched) if the driver refuses any step; the caller then creates an ordinary stream.
-bool make_green_aux_stream(kb_ctx* ctx, int reserve, int priority) {
+bool make_green_aux_stream(kb_ctx* ctx, int reserve, int priority, bool also_main = false) {
     auto get = [](const char* name) -> void* {
         void* f = nullptr;
         cudaDriverEntryPointQueryResult st;
@@ -307,6 +307,17 @@ bool make_green_aux_stream(kb_ctx* ctx, int reserve, int priority) {
         cudaStreamDestroy((cudaStream_t)st);
         gdestroy(g);
         return false;
+    }
+    if (also_main) {
+        // background context: the MAIN stream lives in the partition too (a second stream of the same green context)
+        CUstream st2;
+        if (gstream(&st2, g, CU_STREAM_NON_BLOCKING, priority) != CUDA_SUCCESS) {
+            cudaStreamDestroy((cudaStream_t)st);
+            gdestroy(g);
+            return false;
+        }
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        ctx->stream = (cudaStream_t)st2;
     }
     ctx->stream_aux = (cudaStream_t)st;
     ctx->green_ctx = (void*)g;
@@ -455,7 +466,11 @@ extern "C" {
 
 const char* kb_version(void) { return "knockoffs_b200 0.1.0 (sm_100a)"; }
 
-int kb_create(kb_ctx** out, int device) {
+static int create_ctx(kb_ctx** out, int device, bool background);
+int kb_create(kb_ctx** out, int device) { return create_ctx(out, device, false); }
+int kb_create_background(kb_ctx** out, int device) { return create_ctx(out, device, true); }
+
+static int create_ctx(kb_ctx** out, int device, bool background) {
     if (!out) return KB_ERR_INVALID;
     *out = nullptr;
     int ndev = 0;
@@ -486,14 +501,15 @@ int kb_create(kb_ctx** out, int device) {
     // Highest priority for the main stream, lowest for the auxiliary one: a freed SM slot goes to the chain first.
     int prio_least = 0, prio_greatest = 0;
     if (ok) cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
-    ok = ok && cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, background ? prio_least : prio_greatest) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_h2d, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream_d2h, cudaStreamNonBlocking) == cudaSuccess;
     if (ok) {
         // KB_GREEN_SMS = SMs kept free of auxiliary-stream work (default 16; 0 = no partition)
         const char* e = getenv("KB_GREEN_SMS");
         const int reserve = e ? atoi(e) : 16;
-        if (!(reserve > 0 && make_green_aux_stream(ctx, reserve, prio_least)))
+        ctx->background = background ? 1 : 0;
+        if (!(reserve > 0 && make_green_aux_stream(ctx, reserve, prio_least, background)))
             ok = cudaStreamCreateWithPriority(&ctx->stream_aux, cudaStreamNonBlocking, prio_least) == cudaSuccess;
     }
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming) == cudaSuccess;

@@ -1000,10 +1000,10 @@ int group_solve_contiguous(kb_ctx* ctx, const std::vector<double>& Scor, int p, 
     // Delayed updates per group (group_run_* kernels) whenever every group fits; KB_GROUP_MODE=step forces the per-step kernels.
     // Group :sdp stays on the per-step kernels by default: its PCA line search is Brent on a piecewise-LINEAR objective whose
     // minimum is often a flat interval, so which minimiser is returned -- and with it the whole iterate path and, through the
-    // loose relative stopping rule, even the final objective -- depends on rounding-level details (the oracle, a host build
+    // loose relative stopping rule, even the final objective -- depends on rounding-level details (the CPU restatement, a host build
     // of this very Brent and the GPU already pick three different points on the first step of the runtests.jl:546-625
     // problem).  The delayed-update recurrences change rounding, hence the path; MVR / ME have smooth line searches and
-    // agree with the oracle at 1e-8 either way.  KB_GROUP_MODE=runs forces the delayed updates for :sdp as well.
+    // agree with the CPU restatement at 1e-8 either way.  KB_GROUP_MODE=runs forces the delayed updates for :sdp as well.
     static const int mode_env = [] { const char* e = getenv("KB_GROUP_MODE"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'r' ? 2 : 0)); }();
     const bool use_runs = mode_env != 1 && gmax <= GB_MAX && (method != KB_METHOD_SDP_CCD || mode_env == 2);
     double *dWp = nullptr, *dEpart = nullptr, *dQ = nullptr;

@@ -30,6 +30,7 @@ struct kb_ctx {
     cudaStream_t stream_aux = nullptr;   // look-ahead stream of the blocked Cholesky (trailing update || next panel)
     void* green_ctx = nullptr;           // CUgreenCtx that stream_aux belongs to (SM partition), or NULL
     int aux_sms = 0;                     // SMs stream_aux may use (0 = all: no partition)
+    int background = 0;                  // kb_create_background: the main stream is confined to the partition as well
     cudaEvent_t aux_ev[2] = {nullptr, nullptr};
     cudaEvent_t ccd_ev[3] = {nullptr, nullptr, nullptr};   // blocked CCD: panel ready / gather done / rank-256 update done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
