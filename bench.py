@@ -64,8 +64,9 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0, help="rows per sampling chunk (0 = library default)")
     ap.add_argument("--refresh-every", type=int, default=-1)
     ap.add_argument("--c5-rows", type=int, default=500000)
-    ap.add_argument("--no-pipeline", action="store_true",
-                    help="1 GPU: run the two methods strictly one after the other instead of sampling :mvr beside the :sdp_ccd solve")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="1 GPU experiment: sample :mvr on a background (SM-partitioned) context beside the :sdp_ccd solve instead of "
+                         "running the stages one after the other (measured SLOWER on B200, profiles/r02_pipeline_experiment.md)")
     return ap.parse_args()
 
 
@@ -395,12 +396,14 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
             st["sample_ms"] += e0.elapsed_time(e1)
             st["steps"] += 1
 
-    # ---- 1 GPU, two methods: software pipeline over two contexts.  The :sdp_ccd solve is a latency-bound chain of small
-    #      kernels that leaves most SMs idle, the :mvr sampling is pure tensor-core throughput.  A BACKGROUND context
+    # ---- 1 GPU, two methods, OPT-IN (--pipeline): software pipeline over two contexts.  The :sdp_ccd solve is a chain of small
+    #      kernels, the :mvr sampling is pure tensor-core throughput.  A BACKGROUND context
     #      (kb_create_background: every kernel confined to the SM partition that keeps 16 SMs free, lowest priority) samples
     #      the first method's knockoffs on a second host thread WHILE the foreground context solves the second method;
     #      the second method is sampled on the foreground context (whole GPU).  Same work, same outputs, same seeds.
-    pipelined = (world == 1 and len(methods) == 2 and not a.no_pipeline)
+    #      Measured on B200 (r02k): 2476 ms per step against 2397 ms for the plain order -- the solve's own GEMM phases need
+    #      about half of the machine, and beside 0.5 ms-long sampling CTAs it slows from 0.53 to 1.44 s.  Hence off by default.
+    pipelined = (world == 1 and len(methods) == 2 and a.pipeline)
     ctx_bg = ext_bg = Xko_t2 = None
     if pipelined:
         try:
