@@ -33,6 +33,10 @@ constexpr int MAX_NIN = 8;             // inner blocks per outer block: at most 
 constexpr int SLAB = 128;              // rows per gather / Gram CTA
 constexpr int GPITCH = SLAB + 1;       // shared-memory pitch of one panel column
 constexpr int BLK_THREADS = 256;
+#ifndef KB_CHAIN_FAST_MATH
+#define KB_CHAIN_FAST_MATH 1
+#endif
+constexpr bool CHAIN_FAST_MATH = KB_CHAIN_FAST_MATH != 0;   // MUFU-seeded reciprocal / sqrt on the sequential kernel's chain (ccd_device.cuh)
 constexpr int GRAM_SLOTS = 5;                    // double2 rows per thread and pass of the direct column-norm recompute
 constexpr double GRAM_RECOMPUTE_RATIO = 2e-6;    // recompute G_jj when it is below this fraction of its error scale
 static_assert(BW == 64 && SLOT_ROWS == 64, "ownership maps below assume 64-wide blocks");
@@ -236,7 +240,7 @@ ccd_block_seq_kernel(const CcdParams P, int j0, int bw, const double* __restrict
             const double sj = s_s[j], ajj = s_a[j];
             double delta, s_new, cfac;
             bool skip;
-            ccd_line_search(METHOD, m, lam, lambda_min, sj, ajj, s_k[j], ss, Mjj, delta, s_new, skip, cfac, status);
+            ccd_line_search<CHAIN_FAST_MATH>(METHOD, m, lam, lambda_min, sj, ajj, s_k[j], ss, Mjj, delta, s_new, skip, cfac, status);
             const bool upd = !skip && status == 0;
             if (upd) {
                 if (fabs(delta) > max_delta) max_delta = fabs(delta);
