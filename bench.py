@@ -40,9 +40,10 @@ UNIT = "rows/s"
 NCU_TRAFFIC_BYTES = {
     # profiles/r01_ccd_stream_kernel_ncu_raw.csv: 375.47 GB read + 494.29 GB written per sweep launch (p = 5000)
     "ccd_stream_kernel": 869.76e9,
-    # profiles/r01g_dgemm_dmma_kernel_batched_sampling_ncu_raw.csv: ONE batched launch = all m = 5 copies of one 4096-row
-    # chunk (gridDim.z = 5; per copy a lower- and an upper-triangular K = 5000 segment): 6.633 GB read + 0.802 GB written
-    "dgemm_dmma_kernel": 7.434e9,
+    # profiles/r02_dgemm_dmma_kernel_batched_sampling_ncu_raw.csv: ONE batched launch = all m = 5 copies of one 4096-row
+    # chunk (gridDim.z = 5, 25 280 CTAs; per copy a lower- and an upper-triangular K = 5000 segment): 7.347 GB read +
+    # 0.801 GB written in 27.19 ms, DMMA pipe 93.4 % active (algorithmic: ~3.4 GB of operands + 0.82 GB of C)
+    "dgemm_dmma_kernel": 8.149e9,
 }
 
 
