@@ -281,6 +281,7 @@ class Env:
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group("nccl", device_id=self.d)
+        self.early_groups = {}
         self.ctx = self.kb.Context(self.local)
         if a.chunk:
             self.ctx.set_sample_chunk_rows(a.chunk)
@@ -310,6 +311,13 @@ class Env:
     def ev(self):
         return self.torch.cuda.Event(enable_timing=True)
 
+    def group_without(self, rank_out):
+        """NCCL group of every rank but `rank_out` (created once; every rank must call this)."""
+        if rank_out not in self.early_groups:
+            ranks = [r for r in range(self.world) if r != rank_out]
+            self.early_groups[rank_out] = (self.dist.new_group(ranks=ranks), ranks)
+        return self.early_groups[rank_out]
+
 
 def gen_gaussian_Xt(E, dSigma, p, n, seed):
     """X = Z0 chol(Sigma)' generated on the device (data generation only), stored column-major as Xt[j, i] = X[i, j]."""
@@ -337,17 +345,36 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
         lo, hi = rank * a.n, (rank + 1) * a.n
         n_total = a.n * world
     n_loc = hi - lo
+    # Rows per method.  With two methods on N >= 2 ranks the rank that solves the LONG method (:sdp_ccd, 0.52 s, sequential)
+    # would keep everyone waiting: instead the other ranks receive the first method's factor early (broadcast inside the group
+    # that excludes the long solver) and sample ALL of its rows among themselves while the long solve is still running; the
+    # second method's rows are then shared by all ranks.
+    owner = [i % world for i in range(len(methods))]
+    staggered = (world > 1 and len(methods) == 2)
+    rows = [(lo, hi) for _ in methods]
+    early = None
+    if staggered:
+        grp, early_ranks = E.group_without(owner[1])
+        early = (grp, early_ranks)
+        if rank in early_ranks:
+            l0, h0 = kb.dist.shard_rows(n_total, len(early_ranks), early_ranks.index(rank))
+            rows[0] = (l0, h0)
+        else:
+            rows[0] = (lo, lo)                                   # the long solver samples none of the first method
+    x_lo = min(r[0] for r in rows if r[1] > r[0])
+    x_hi = max(r[1] for r in rows if r[1] > r[0])
+    n_x = x_hi - x_lo
+    n_loc = max(r[1] - r[0] for r in rows)
     Sigma_h = kb.harness.block_sigma(p, 10, 0.5, 0.25)
     dSigma = torch.from_numpy(np.ascontiguousarray(Sigma_h)).to(E.d)          # symmetric: row/col-major coincide
-    Xt = gen_gaussian_Xt(E, dSigma, p, n_loc, 20260003 + rank)
+    Xt = gen_gaussian_Xt(E, dSigma, p, n_x, 20260003 + rank)              # this rank's rows [x_lo, x_hi) of X
     dmu = torch.zeros(p, dtype=f64, device=E.d)
     ds = [torch.empty(p, dtype=f64, device=E.d) for _ in methods]
     dSiS = [torch.empty((p, p), dtype=f64, device=E.d) for _ in methods]
     dLb = [torch.empty((2 * m - 1, p, p), dtype=f64, device=E.d) for _ in methods]
     Xko_t = torch.empty((m * p, n_loc), dtype=f64, device=E.d)
     torch.cuda.synchronize()
-    owner = [i % world for i in range(len(methods))]
-    st = {"steps": 0, "bcast_ms": 0.0, "sample_ms": 0.0}
+    st = {"steps": 0, "bcast_ms": 0.0, "sample_ms": 0.0, "staggered": staggered}
     per = {mth: {"solve_ms": 0.0, "ccd_ms": 0.0, "init_ms": 0.0, "factor_ms": 0.0, "ref_bytes": 0.0, "touched_bytes": 0.0,
                  "sweeps": 0, "flops": 0.0, "objective": None} for mth in methods}
 
@@ -373,28 +400,52 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
                 q["ccd_ms"] += info["solve_ms"]; q["init_ms"] += info["init_ms"]; q["ref_bytes"] += info["ref_bytes"]
                 q["touched_bytes"] += info["touched_bytes"]; q["sweeps"] = info["sweeps"]; q["mode"] = info["mode"]
                 q["flops"] += info["flops"]; q["objective"] = info["objective"]
-        if world > 1:
-            # the step's collectives: s (p doubles) and the factor blocks ((2m) p^2 doubles = 2 GB per method) from the
-            # rank that solved to everyone, NCCL broadcast over NVLink
+        def sample(i):
+            r0, r1 = rows[i]
+            if r1 <= r0:
+                return
+            dev.sample_dev(ctx, Xt.data_ptr() + 8 * (r0 - x_lo), r1 - r0, n_x, p, dmu.data_ptr(), dSiS[i].data_ptr(), dLb[i].data_ptr(), m,
+                           Xko_t.data_ptr(), n_loc, seed=20260003 + i, row_offset=r0)
+
+        def bcast_method(i, group=None):
+            # s (p doubles) and the factor blocks ((2m) p^2 doubles = 2 GB) from the rank that solved, NCCL over NVLink
             b0, b1 = E.ev(), E.ev()
             b0.record()
-            for i in range(len(methods)):
-                E.bcast(ds[i], owner[i]); E.bcast(dSiS[i], owner[i]); E.bcast(dLb[i], owner[i])
+            for t in (ds[i], dSiS[i], dLb[i]):
+                E.dist.broadcast(t, src=owner[i], group=group)
             b1.record()
             torch.cuda.current_stream().synchronize()
-            if record:
-                st["bcast_ms"] += b0.elapsed_time(b1)
+            return b0.elapsed_time(b1)
+
         e0, e1 = E.ev(), E.ev()
-        e0.record(ext)
-        for i, mth in enumerate(methods):
-            nvtx.range_push(f"sample:{mth}")
-            dev.sample_dev(ctx, Xt.data_ptr(), n_loc, n_loc, p, dmu.data_ptr(), dSiS[i].data_ptr(), dLb[i].data_ptr(), m,
-                           Xko_t.data_ptr(), n_loc, seed=20260003 + i, row_offset=lo)
-            nvtx.range_pop()
-        e1.record(ext)
-        if record:
+        samp = 0.0
+        bc = 0.0
+        if staggered:
+            grp, early_ranks = early
+            if rank in early_ranks:
+                bc += bcast_method(0, grp)
+                e0.record(ext); sample(0); e1.record(ext); ext.synchronize()
+                samp += e0.elapsed_time(e1)
+            bc_all = bcast_method(1)
+            e2, e3 = E.ev(), E.ev()
+            e2.record(ext); sample(1); e3.record(ext); ext.synchronize()
+            samp += e2.elapsed_time(e3)
+            if record:
+                st["bcast_ms"] += bc_all if rank == owner[1] else bc       # the waiting inside a collective is not transfer time
+        else:
+            if world > 1:
+                for i in range(len(methods)):
+                    bc += bcast_method(i)
+                if record:
+                    st["bcast_ms"] += bc
+            e0.record(ext)
+            for i in range(len(methods)):
+                sample(i)
+            e1.record(ext)
             ext.synchronize()
-            st["sample_ms"] += e0.elapsed_time(e1)
+            samp = e0.elapsed_time(e1)
+        if record:
+            st["sample_ms"] += samp
             st["steps"] += 1
 
     # ---- 1 GPU, two methods, OPT-IN (--pipeline): software pipeline over two contexts.  The :sdp_ccd solve is a chain of small
@@ -495,7 +546,8 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     ms_per_step = total_ms / steps
     out = {"ms_per_step": ms_per_step, "value": len(methods) * n_total / (ms_per_step * 1e-3), "launches": int(launches),
            "clocks": clocks, "n_total": n_total, "rows_per_gpu": n_loc, "st": st, "per": per, "owner": owner,
-           "handles": (dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo), "ctx_bg": ctx_bg}
+           "handles": (dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo), "ctx_bg": ctx_bg,
+           "shard": (lo, hi, x_lo)}
     del Xko_t2
     # per-method timings live on their owner: gather them on rank 0
     if world > 1:
@@ -519,14 +571,15 @@ def run_e2e(E, a, res, steps):
     ctx, world, rank = E.ctx, E.world, E.rank
     p, m, methods = a.p, a.m, methods_of(a)
     dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo = res["handles"]
-    n_loc = Xt.shape[1]
+    lo, hi, x_lo = res["shard"]                   # the plain row shard of this rank; Xt holds rows [x_lo, ...) of X
+    n_loc = hi - lo
     need = (p * n_loc + m * p * n_loc) * 8
     avail = psutil.virtual_memory().available / max(1, world)
     n_e = n_loc
     if need > 0.6 * avail:
         n_e = max(1024, int(n_loc * 0.6 * avail / need) // 1024 * 1024)
     Xh_t = torch.empty((p, n_e), dtype=torch.float64, pin_memory=True)
-    Xh_t.copy_(Xt[:, :n_e])
+    Xh_t.copy_(Xt[:, lo - x_lo:lo - x_lo + n_e])
     Xko_h_t = torch.empty((m * p, n_e), dtype=torch.float64, pin_memory=True)
     mu_h = np.zeros(p)
     Sig_f = np.asfortranarray(Sigma_h)
@@ -852,7 +905,7 @@ def run_ours(a):
         for _ in range(2):
             e0, e1 = E.ev(), E.ev()
             e0.record(E.ext)
-            dev.sample_dev(ctx, Xt.data_ptr(), n_loc, n_loc, p, dmu.data_ptr(), dSiS[0].data_ptr(), dLb[0].data_ptr(), m,
+            dev.sample_dev(ctx, Xt.data_ptr(), n_loc, Xt.shape[1], p, dmu.data_ptr(), dSiS[0].data_ptr(), dLb[0].data_ptr(), m,
                            Xko_t.data_ptr(), n_loc, seed=20260003, row_offset=lo)
             e1.record(E.ext)
             E.ext.synchronize()
@@ -934,7 +987,7 @@ def run_ours(a):
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
                 "parallelism": (f"rows sharded x{world} ({n_loc} per GPU), solves of the {len(methods)} methods on different ranks, "
-                                f"s + factor blocks NCCL-broadcast" if world > 1 else
+                                f"s + factor blocks NCCL-broadcast; the ranks that do not run the long :sdp_ccd solve sample ALL :mvr rows meanwhile" if world > 1 else
                                 ("single GPU, two contexts: :mvr sampled on the background (SM-partitioned) context beside the :sdp_ccd solve"
                                  if st.get("pipelined") else "single GPU, stages strictly one after the other")),
                 "clocks": res["clocks"], "gpu_launches": res["launches"],
