@@ -350,21 +350,24 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     # that excludes the long solver) and sample ALL of its rows among themselves while the long solve is still running; the
     # second method's rows are then shared by all ranks.
     owner = [i % world for i in range(len(methods))]
-    staggered = (world > 1 and len(methods) == 2)
-    rows = [(lo, hi) for _ in methods]
+    can_stagger = (world > 1 and len(methods) == 2)
+    rows_plain = [(lo, hi) for _ in methods]
+    rows_stag = list(rows_plain)
     early = None
-    if staggered:
+    if can_stagger:
         grp, early_ranks = E.group_without(owner[1])
         early = (grp, early_ranks)
         if rank in early_ranks:
-            l0, h0 = kb.dist.shard_rows(n_total, len(early_ranks), early_ranks.index(rank))
-            rows[0] = (l0, h0)
+            rows_stag[0] = kb.dist.shard_rows(n_total, len(early_ranks), early_ranks.index(rank))
         else:
-            rows[0] = (lo, lo)                                   # the long solver samples none of the first method
-    x_lo = min(r[0] for r in rows if r[1] > r[0])
-    x_hi = max(r[1] for r in rows if r[1] > r[0])
+            rows_stag[0] = (lo, lo)                              # the long solver samples none of the first method
+    mode = {"staggered": False}                                  # decided after the first (plain) warm-up step, see below
+    rows = rows_plain
+    both = [r for r in rows_plain + rows_stag if r[1] > r[0]]
+    x_lo = min(r[0] for r in both)
+    x_hi = max(r[1] for r in both)
     n_x = x_hi - x_lo
-    n_loc = max(r[1] - r[0] for r in rows)
+    n_loc = max(r[1] - r[0] for r in rows_plain + rows_stag)
     Sigma_h = kb.harness.block_sigma(p, 10, 0.5, 0.25)
     dSigma = torch.from_numpy(np.ascontiguousarray(Sigma_h)).to(E.d)          # symmetric: row/col-major coincide
     Xt = gen_gaussian_Xt(E, dSigma, p, n_x, 20260003 + rank)              # this rank's rows [x_lo, x_hi) of X
@@ -374,7 +377,8 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     dLb = [torch.empty((2 * m - 1, p, p), dtype=f64, device=E.d) for _ in methods]
     Xko_t = torch.empty((m * p, n_loc), dtype=f64, device=E.d)
     torch.cuda.synchronize()
-    st = {"steps": 0, "bcast_ms": 0.0, "sample_ms": 0.0, "staggered": staggered}
+    st = {"steps": 0, "bcast_ms": 0.0, "sample_ms": 0.0, "staggered": False}
+    last = {"solve_factor_ms": 0.0, "sample_ms": 0.0}            # stage times of the most recent step on this rank
     per = {mth: {"solve_ms": 0.0, "ccd_ms": 0.0, "init_ms": 0.0, "factor_ms": 0.0, "ref_bytes": 0.0, "touched_bytes": 0.0,
                  "sweeps": 0, "flops": 0.0, "objective": None} for mth in methods}
 
@@ -393,13 +397,17 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
             dev.cond_factor_dev(ctx, dSigma.data_ptr(), p, ds[i].data_ptr(), True, m, dSiS[i].data_ptr(), dLb[i].data_ptr())
             nvtx.range_pop()
             e[2].record(ext)
+            ext.synchronize()
+            last["solve_factor_ms"] = e[0].elapsed_time(e[2])
             if record:
-                ext.synchronize()
                 q = per[mth]
                 q["solve_ms"] += e[0].elapsed_time(e[1]); q["factor_ms"] += e[1].elapsed_time(e[2])
                 q["ccd_ms"] += info["solve_ms"]; q["init_ms"] += info["init_ms"]; q["ref_bytes"] += info["ref_bytes"]
                 q["touched_bytes"] += info["touched_bytes"]; q["sweeps"] = info["sweeps"]; q["mode"] = info["mode"]
                 q["flops"] += info["flops"]; q["objective"] = info["objective"]
+        rows = rows_stag if mode["staggered"] else rows_plain
+        staggered = mode["staggered"]
+
         def sample(i):
             r0, r1 = rows[i]
             if r1 <= r0:
@@ -444,6 +452,7 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
             e1.record(ext)
             ext.synchronize()
             samp = e0.elapsed_time(e1)
+        last["sample_ms"] = samp
         if record:
             st["sample_ms"] += samp
             st["steps"] += 1
@@ -525,8 +534,25 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
 
     if pipelined:
         step = step_pipelined            # noqa: F811
-    for _ in range(warmup):
+    for w in range(warmup):
         step()
+        if w == 0 and can_stagger:
+            # One plain step has been timed on every rank: A / B = solve + factor of the short / long method on their owners,
+            # t = this rank's sampling of its plain shard of both methods.  Sampling all rows of one method on one GPU then
+            # takes Ts = t N / 2.  plain: B + 2 Ts / N;  staggered: max(A + Ts / (N - 1), B) + Ts / N.  Every rank evaluates the
+            # same gathered numbers, so all take the same decision.
+            gathered = [None] * world
+            E.dist.all_gather_object(gathered, (last["solve_factor_ms"], last["sample_ms"]))
+            A_ms, B_ms = gathered[owner[0]][0], gathered[owner[1]][0]
+            Ts = max(g[1] for g in gathered) * world / 2.0
+            plain_ms = B_ms + 2.0 * Ts / world
+            stag_ms = max(A_ms + Ts / (world - 1), B_ms) + Ts / world
+            mode["staggered"] = stag_ms < 0.98 * plain_ms
+            st["staggered"] = mode["staggered"]
+            st["stagger_model_ms"] = {"plain": plain_ms, "staggered": stag_ms}
+    if warmup == 0 and can_stagger:
+        mode["staggered"] = scaling == "strong" and world >= 3
+        st["staggered"] = mode["staggered"]
     sampler = ClockSampler(E.local) if (sample_clocks and rank == 0) else None
     E.barrier()
     if sampler:
@@ -987,7 +1013,8 @@ def run_ours(a):
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
                 "parallelism": (f"rows sharded x{world} ({n_loc} per GPU), solves of the {len(methods)} methods on different ranks, "
-                                f"s + factor blocks NCCL-broadcast; the ranks that do not run the long :sdp_ccd solve sample ALL :mvr rows meanwhile" if world > 1 else
+                                f"s + factor blocks NCCL-broadcast" + ("; the ranks that do not run the long :sdp_ccd solve sample ALL :mvr rows meanwhile"
+                                                                       if st.get("staggered") else "") if world > 1 else
                                 ("single GPU, two contexts: :mvr sampled on the background (SM-partitioned) context beside the :sdp_ccd solve"
                                  if st.get("pipelined") else "single GPU, stages strictly one after the other")),
                 "clocks": res["clocks"], "gpu_launches": res["launches"],

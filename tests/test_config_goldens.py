@@ -53,8 +53,12 @@ def test_fixture_is_consistent(job):
     if meta["method"] == "sdp_ccd":
         assert meta["sweeps"] == 59                                  # utilities.jl:339-340 with the default λ, μ, tol
         assert abs(meta["trace"][-1] - meta["obj_sdp"]) < 1e-9 * meta["obj_sdp"]
-    else:
+    elif meta["sweeps"] < 100:
         assert meta["trace"][-1] < 1e-6 and (meta["sweeps"] == 1 or meta["trace"][-2] >= 1e-6)
+    else:
+        # c5_maxent: Σ̂ of 20000 dosage rows at p = 5000 is badly conditioned; max|δ| stalls around 2e-6 and the loop ends
+        # on niter = 100 (utilities.jl:339-340 defaults), never on tol.  The GPU path has to reproduce exactly that.
+        assert min(meta["trace"]) >= 1e-6
 
 
 def test_small_fixture_regenerates_on_cpu():
