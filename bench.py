@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--methods", default="mvr,sdp_ccd")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory leg of the end-to-end measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true", help="skip the separately timed streaming-kernel sweep")
     ap.add_argument("--no-extra", action="store_true", help="skip the config4 / config5 / weak-scaling sections")
@@ -689,6 +690,34 @@ def run_e2e(E, a, res, steps):
            "rows_per_gpu": n_e, "ms_per_step": 1000.0 * dt / steps,
            "api": "kb_solve_s + kb_condition (host pointers, pinned); bytes are per rank",
            "pipelined": Xko_h_t2 is not None}
+    # the same call sequence from PAGEABLE host memory (plain numpy arrays, what a Julia Matrix{Float64} is): the library
+    # stages through its pinned bounce buffers with host copy threads (api.cu host_is_pageable / parallel_copy2d)
+    if world == 1 and not a.no_pageable:
+        try:
+            Xp = np.empty((p, n_e))
+            Xp[...] = Xh_t.numpy()
+            Xkop = np.empty((m * p, n_e))
+
+            def pageable_step():
+                for i, mth in enumerate(methods):
+                    rc = ctx._lib.kb_solve_s(ctx.h, Sig_f.ctypes.data, p, kb.api.METHODS[mth], float(m), C.byref(opts), None,
+                                             s_h[i].ctypes.data, C.byref(info))
+                    kb.api.check(ctx.h, rc)
+                    rc = ctx._lib.kb_condition(ctx.h, Xp.ctypes.data, n_e, p, mu_h.ctypes.data, Sig_f.ctypes.data, s_h[i].ctypes.data,
+                                               1, m, None, 20260003 + i, lo, Xkop.ctypes.data)
+                    kb.api.check(ctx.h, rc)
+
+            pageable_step()            # first touch of the output pages
+            t0 = time.perf_counter()
+            pageable_step()
+            dtp = time.perf_counter() - t0
+            same = bool(np.array_equal(Xkop[:, :256], Xko_h_t.numpy()[:, :256]))
+            out["pageable"] = {"value": nm * n_e / dtp, "unit": UNIT, "ms_per_step": 1000.0 * dtp, "steps": 1,
+                               "host_buffers": "numpy (pageable) X and X-tilde; staged through the library's pinned bounce buffers",
+                               "same_bits_as_pinned_run": same}
+            del Xp, Xkop
+        except MemoryError as ex:
+            out["pageable"] = {"unavailable": str(ex)}
     del Xh_t, Xko_h_t, Xko_h_t2
     return out
 

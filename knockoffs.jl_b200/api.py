@@ -30,6 +30,18 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+def _need(cond, what):
+    """The reference raises DimensionMismatch / ArgumentError before touching data; here every array shape is checked
+    before a raw pointer crosses the C ABI (the library trusts the sizes it is given)."""
+    if not cond:
+        raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, what)
+
+
+def _square(A, name="Sigma"):
+    _need(A.ndim == 2 and A.shape[0] == A.shape[1], f"{name} must be square but was {A.shape}")
+    return A.shape[0]
+
+
 class Context:
     """One per host thread / device (include/knockoffs_b200.h: kb_create)."""
 
@@ -154,6 +166,8 @@ def solve_s(Sigma, method, m=1, s_init=None, ctx: Optional[Context] = None, retu
     info = SolveInfo()
     s = np.empty(p)
     si = None if s_init is None else np.ascontiguousarray(s_init, dtype=np.float64)
+    _need(si is None or si.shape == (p,), f"s_init must have length {p}")
+    _need(float(m) >= 1, f"m should be 1 or larger but was {m}.")
     rc = ctx._lib.kb_solve_s(ctx.h, _ptr(Sigma), p, mid, float(m), C.byref(opts), _ptr(si), _ptr(s), C.byref(info))
     check(ctx.h, rc)
     d = _info_dict(info, str(method).lstrip(":"))
@@ -165,8 +179,9 @@ def solve_s(Sigma, method, m=1, s_init=None, ctx: Optional[Context] = None, retu
 def eigmin(Sigma, ctx: Optional[Context] = None) -> float:
     ctx = ctx or default_context()
     Sigma = _f(Sigma)
+    p = _square(Sigma)
     out = C.c_double()
-    check(ctx.h, ctx._lib.kb_eigmin(ctx.h, _ptr(Sigma), Sigma.shape[0], C.byref(out)))
+    check(ctx.h, ctx._lib.kb_eigmin(ctx.h, _ptr(Sigma), p, C.byref(out)))
     return out.value
 
 
@@ -180,6 +195,7 @@ def gram(X, center=True, denom=None, ctx: Optional[Context] = None):
     ``mean(X, dims=1)`` of the 2-argument entry (src/modelX.jl:47-49)."""
     ctx = ctx or default_context()
     X = _f(X)
+    _need(X.ndim == 2, "X must be a matrix")
     n, p = X.shape
     G = np.empty((p, p), order="F")
     mu = np.empty(p)
@@ -192,6 +208,7 @@ def cov_shrink_lw(X, ctx: Optional[Context] = None):
     covariance_approximator of the 2-argument entry (src/modelX.jl:43-50).  Returns (Sigma, mu, lambda)."""
     ctx = ctx or default_context()
     X = _f(X)
+    _need(X.ndim == 2, "X must be a matrix")
     n, p = X.shape
     Sig = np.empty((p, p), order="F")
     mu = np.empty(p)
@@ -206,10 +223,11 @@ def cond_factor(Sigma, S, m=1, ctx: Optional[Context] = None):
     [L_11, M_1, L_22, M_2, ..., L_mm] (block (i,k) of the pm x pm lower factor is L_kk if i == k, M_k if i > k)."""
     ctx = ctx or default_context()
     Sigma = _f(Sigma)
-    p = Sigma.shape[0]
+    p = _square(Sigma)
     S = np.asarray(S, dtype=np.float64)
     is_diag = S.ndim == 1
     S = np.ascontiguousarray(S) if is_diag else _f(S)
+    _need(S.shape == ((p,) if is_diag else (p, p)), f"S must have length {p} or be {p} x {p}")
     m = int(m)
     if m < 1:
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"m should be 1 or larger but was {m}.")
@@ -236,10 +254,18 @@ def sample(X, mu, SigmaInvS, Lblocks, m=1, Z=None, seed=0, row_offset=0, ctx: Op
     injected ``randn(n, mp)``; ``Z=None`` draws it on the device (Philox4x32-10, keyed by seed/row/column)."""
     ctx = ctx or default_context()
     X = _f(X)
+    _need(X.ndim == 2, "X must be a matrix")
     n, p = X.shape
+    m = int(m)
+    _need(m >= 1, f"m should be 1 or larger but was {m}.")
     mu = np.ascontiguousarray(mu, dtype=np.float64)
     SiS = _f(SigmaInvS)
     Lb = _f(Lblocks)
+    if Lb.ndim == 2 and m == 1:
+        Lb = Lb.reshape(Lb.shape[0], Lb.shape[1], 1, order="F")
+    _need(mu.shape == (p,), f"mu must have length {p}")
+    _need(SiS.shape == (p, p), f"SigmaInvS must be {p} x {p}")
+    _need(Lb.shape == (p, p, 2 * m - 1), f"Lblocks must be {p} x {p} x {2 * m - 1} ([L_11, M_1, ..., L_mm])")
     Zf = None if Z is None else _f(Z)
     if Zf is not None and Zf.shape != (n, m * p):
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
@@ -314,6 +340,7 @@ def modelX_gaussian_knockoffs(X, method, mu=None, Sigma=None, m=1, Z=None, seed=
     if Zf is not None and Zf.shape != (n, m * p):
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
     si = None if s_init is None else np.ascontiguousarray(s_init, dtype=np.float64)
+    _need(si is None or si.shape == (p,), f"s_init must have length {p}")
     Xko = np.empty((n, m * p), order="F")
     s = np.empty(p)
     rc = ctx._lib.kb_modelx_gaussian_knockoffs(ctx.h, _ptr(X), n, p, _ptr(mu), _ptr(Sigma), mid, m, C.byref(opts),
@@ -375,7 +402,7 @@ def solve_s_group(Sigma, groups, method, m=1, V=None, ctx: Optional[Context] = N
     ``V`` (p x nv, caller's variable order) replaces get_PCA_vectors' direction set."""
     ctx = ctx or default_context()
     Sigma = _f(Sigma)
-    p = Sigma.shape[0]
+    p = _square(Sigma)
     groups = np.ascontiguousarray(groups, dtype=np.int64)
     if groups.shape != (p,):
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Length of groups should be equal to dimension of Σ")
@@ -383,6 +410,8 @@ def solve_s_group(Sigma, groups, method, m=1, V=None, ctx: Optional[Context] = N
     opts = make_group_opts(**kwargs)
     info = GroupInfo()
     Vf = None if V is None else _f(V)
+    _need(Vf is None or (Vf.ndim == 2 and Vf.shape[0] == p), f"V must have {p} rows")
+    _need(float(m) >= 1, f"m should be 1 or larger but was {m}.")
     nv = 0 if Vf is None else Vf.shape[1]
     S = np.empty((p, p), order="F")
     obj = C.c_double()
@@ -454,12 +483,15 @@ def modelX_gaussian_group_knockoffs(X, method, groups, mu, Sigma, m=1, V=None, Z
     if groups.shape != (p,):                                         # group.jl:119-120
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, "Length of groups should be equal to number of variables")
     m = int(m)
+    _need(m >= 1, f"m should be 1 or larger but was {m}.")
     Sigma = _f(Sigma)
     mu = np.ascontiguousarray(mu, dtype=np.float64)
+    _need(Sigma.shape == (p, p) and mu.shape == (p,), "dimension mismatch between X, mu and Sigma")
     mid = _group_method_id(method)
     opts = make_group_opts(**kwargs)
     info = GroupInfo()
     Vf = None if V is None else _f(V)
+    _need(Vf is None or (Vf.ndim == 2 and Vf.shape[0] == p), f"V must have {p} rows")
     Zf = None if Z is None else _f(Z)
     if Zf is not None and Zf.shape != (n, m * p):
         raise _lib.KnockoffsError(_lib.KB_ERR_INVALID, f"Z must be {n} x {m * p}")
@@ -729,8 +761,10 @@ def feasible_gamma(Sigma, s, m=1, ctx: Optional[Context] = None) -> float:
     ctx = ctx or default_context()
     Sigma = _f(Sigma)
     s = np.ascontiguousarray(s, dtype=np.float64)
+    p = _square(Sigma)
+    _need(s.shape == (p,), f"s must have length {p}")
     out = C.c_double()
-    check(ctx.h, ctx._lib.kb_feasible_gamma(ctx.h, _ptr(Sigma), Sigma.shape[0], _ptr(s), float(m), C.byref(out)))
+    check(ctx.h, ctx._lib.kb_feasible_gamma(ctx.h, _ptr(Sigma), p, _ptr(s), float(m), C.byref(out)))
     return out.value
 
 
@@ -741,8 +775,9 @@ def choose_group_reps(Sigma, groups, threshold=0.5, prioritize_idx=None, ctx: Op
     Indices (result and ``prioritize_idx``) are 1-based like the reference's."""
     ctx = ctx or default_context()
     Sigma = _f(Sigma)
-    p = Sigma.shape[0]
+    p = _square(Sigma)
     groups = np.ascontiguousarray(groups, dtype=np.int64)
+    _need(groups.shape == (p,), "Length of groups should be equal to dimension of Σ")
     pr = None if prioritize_idx is None else np.ascontiguousarray(prioritize_idx, dtype=np.int64)
     out = np.zeros(p, dtype=np.int64)
     nr = C.c_int64()
@@ -755,9 +790,11 @@ def cond_indep_corr(Sigma, groups, group_reps, ctx: Optional[Context] = None) ->
     """``cond_indep_corr(Σ, groups, group_reps)`` -- src/group.jl:205-240 (1-based ``group_reps``)."""
     ctx = ctx or default_context()
     Sigma = _f(Sigma)
-    p = Sigma.shape[0]
+    p = _square(Sigma)
     groups = np.ascontiguousarray(groups, dtype=np.int64)
     reps = np.ascontiguousarray(group_reps, dtype=np.int64)
+    _need(groups.shape == (p,), "Length of groups should be equal to dimension of Σ")
+    _need(reps.ndim == 1 and (reps.size == 0 or (reps.min() >= 1 and reps.max() <= p)), f"group_reps must be indices in 1:{p}")
     out = np.empty((p, p), order="F")
     check(ctx.h, ctx._lib.kb_cond_indep_corr(ctx.h, _ptr(Sigma), p, _ptr(groups), _ptr(reps), reps.size, _ptr(out)))
     return out
@@ -769,9 +806,11 @@ def solve_s_graphical_group(Sigma, groups, group_reps, method, m=1, V=None, ctx:
     Returns (S, D, obj)."""
     ctx = ctx or default_context()
     Sigma = _f(Sigma)
-    p = Sigma.shape[0]
+    p = _square(Sigma)
     groups = np.ascontiguousarray(groups, dtype=np.int64)
     reps = np.ascontiguousarray(group_reps, dtype=np.int64)
+    _need(groups.shape == (p,), "Length of groups should be equal to dimension of Σ")
+    _need(reps.ndim == 1 and reps.size >= 1 and reps.min() >= 1 and reps.max() <= p, f"group_reps must be indices in 1:{p}")
     r = reps.size
     opts = make_group_opts(**kwargs)
     info = GroupInfo()

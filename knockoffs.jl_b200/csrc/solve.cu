@@ -524,9 +524,13 @@ int solve_s_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, int method, 
         // passes per sweep); for the blocked one (p/64 rank-64 passes per sweep) after the FIRST sweep -- the equi
         // starting point makes the initial A nearly singular (λmin(A) = λmin option), the inverse built there is the
         // least accurate one of the whole solve -- and then every 8th sweep (measured at p = 5000: same objective to 1e-15
-        // as every 4th, and runs with no refresh at all still meet the 1e-8 parity tests).
-        const bool auto_block = (opts.refresh_every < 0 && mode == KB_MODE_BLOCK);
-        const int refresh_every = opts.refresh_every < 0 ? (mode == KB_MODE_STREAM ? 1 : 8) : opts.refresh_every;
+        // as every 4th, and runs with no refresh at all still meet the 1e-8 parity tests).  :sdp_ccd starts from s = 0
+        // with no shift, i.e. from a well conditioned A = κΣ: its 59-sweep solve at p = 5000 ends 1.76e-12 from the
+        // golden s whether the inverse is rebuilt every 8 sweeps or never (profiles/r02_refresh_sweep.json), so the
+        // blocked kernel rebuilds it every 32nd sweep only (8.5 ms per rebuild).
+        const bool sdp = (method == KB_METHOD_SDP_CCD);
+        const bool auto_block = (opts.refresh_every < 0 && mode == KB_MODE_BLOCK && !sdp);
+        const int refresh_every = opts.refresh_every < 0 ? (mode == KB_MODE_STREAM ? 1 : (sdp ? 32 : 8)) : opts.refresh_every;
         double lam = opts.sdp_lambda;
         double init_ms = 0.0, solve_ms = 0.0;
         int sweeps_done = 0;

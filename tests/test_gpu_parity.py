@@ -146,6 +146,37 @@ def test_error_behaviour(kb, ctx):
         kb.condition(np.zeros((4, 50)), np.zeros(50), Sigma, np.full(50, 0.3), m=0, ctx=ctx)
 
 
+def test_shapes_are_validated_before_the_c_call(kb, ctx):
+    """DimensionMismatch-style errors instead of an out-of-bounds host read behind the raw pointers."""
+    p, n = 40, 8
+    Sigma = toeplitz(p, 0.4)
+    X = np.zeros((n, p))
+    s = np.full(p, 0.3)
+    SiS, Lb = kb.cond_factor(Sigma, s, m=2, ctx=ctx)
+    bad_calls = [
+        lambda: kb.solve_s(Sigma, "mvr", s_init=np.full(p - 1, 0.5), ctx=ctx),
+        lambda: kb.solve_s(Sigma[:, :-1], "mvr", ctx=ctx),
+        lambda: kb.eigmin(Sigma[:-1], ctx=ctx),
+        lambda: kb.cond_factor(Sigma, s[:-1], m=1, ctx=ctx),
+        lambda: kb.cond_factor(Sigma, np.eye(p - 1), m=1, ctx=ctx),
+        lambda: kb.sample(X, np.zeros(p), SiS, Lb, m=3, ctx=ctx),              # 3 blocks given, 5 needed
+        lambda: kb.sample(X, np.zeros(p - 1), SiS, Lb, m=2, ctx=ctx),
+        lambda: kb.sample(X, np.zeros(p), SiS[:-1, :-1], Lb, m=2, ctx=ctx),
+        lambda: kb.modelX_gaussian_knockoffs(X, "mvr", np.zeros(p), Sigma, s_init=np.ones(p + 1), ctx=ctx),
+        lambda: kb.modelX_gaussian_group_knockoffs(X, "maxent", np.arange(p) // 2 + 1, np.zeros(p - 1), Sigma, ctx=ctx),
+        lambda: kb.modelX_gaussian_group_knockoffs(X, "maxent", np.arange(p) // 2 + 1, np.zeros(p), Sigma[:-1, :-1], ctx=ctx),
+        lambda: kb.solve_s_group(Sigma, np.arange(p) // 2 + 1, "maxent", V=np.zeros((p - 1, 3)), ctx=ctx),
+        lambda: kb.feasible_gamma(Sigma, s[:-1], ctx=ctx),
+        lambda: kb.choose_group_reps(Sigma, np.ones(p - 1, dtype=int), ctx=ctx),
+        lambda: kb.cond_indep_corr(Sigma, np.ones(p, dtype=int), [0], ctx=ctx),
+        lambda: kb.solve_s_graphical_group(Sigma, np.ones(p, dtype=int), [p + 1], "maxent", ctx=ctx),
+    ]
+    for i, call in enumerate(bad_calls):
+        with pytest.raises(kb.KnockoffsError):
+            call()
+            pytest.fail(f"bad call {i} was accepted")
+
+
 # ---- conditional factor + sampling ---------------------------------------------------------------------
 @pytest.mark.parametrize("p,m", [(200, 1), (130, 3), (257, 2)])
 def test_cond_factor_matches_oracle(kb, ctx, p, m):
