@@ -1045,7 +1045,7 @@ def run_ours(a):
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
-                "parallelism": (f"rows sharded x{world} ({n_loc} per GPU), solves of the {len(methods)} methods on different ranks, "
+                "parallelism": (f"rows sharded x{world} ({res['shard'][1] - res['shard'][0]} per GPU), solves of the {len(methods)} methods on different ranks, "
                                 f"s + factor blocks NCCL-broadcast" + ("; the ranks that do not run the long :sdp_ccd solve sample ALL :mvr rows meanwhile"
                                                                        if st.get("staggered") else "") if world > 1 else
                                 ("single GPU, two contexts: :mvr sampled on the background (SM-partitioned) context beside the :sdp_ccd solve"
