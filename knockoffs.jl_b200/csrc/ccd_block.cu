@@ -25,6 +25,7 @@
 #include "linalg.cuh"
 #include <cstdlib>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>     // header-only; ranges are emitted only with KB_NVTX=1 (ncu --nvtx --nvtx-include "ccd_big/")
 
 namespace kb {
 
@@ -425,7 +426,11 @@ int ccd_block_run(kb_ctx* ctx, const CcdParams& P, double* work) {
         }
         if (!overlap) {
             // M (lower tiles) += Uc_all · U_allᵀ   (K = 64 nin)
-            KB_TRY(gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, nin * BW, 1.0, Ucall, ld, Uall, ld, 1.0, P.M, ld, 0, 1, 0));
+            static const bool nvtx_on = getenv("KB_NVTX") != nullptr;
+            if (nvtx_on) nvtxRangePushA("ccd_big");
+            const int rc_big = gemm1(ctx, A_MCONTIG, B_NCONTIG, p, p, nin * BW, 1.0, Ucall, ld, Uall, ld, 1.0, P.M, ld, 0, 1, 0);
+            if (nvtx_on) nvtxRangePop();
+            KB_TRY(rc_big);
             mark(PH_BIG);
             continue;
         }

@@ -9,7 +9,9 @@ KEEP = ("dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.p
         "sm__cycles_elapsed.max", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active")
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__ops_path_tensor_src_fp64.avg.pct_of_peak_sustained_elapsed", "sm__ops_path_tensor_src_fp64.min", "sm__ops_path_tensor_src_fp64.max",
+        "sm__ops_path_tensor_src_fp64.avg", "sm__cycles_active.avg")
 rows = list(csv.reader(sys.stdin))
 hdr, units = rows[0], rows[1]
 ki = hdr.index("Kernel Name")

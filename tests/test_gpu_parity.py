@@ -146,6 +146,31 @@ def test_error_behaviour(kb, ctx):
         kb.condition(np.zeros((4, 50)), np.zeros(50), Sigma, np.full(50, 0.3), m=0, ctx=ctx)
 
 
+def test_context_is_reusable_after_errors(kb):
+    """An error return must leave no work in flight and no workspace checked out: the same context then reproduces a
+    fresh context's results bit for bit."""
+    rng = np.random.default_rng(11)
+    p, n, m = 120, 300, 2
+    Sigma = toeplitz(p, 0.5)
+    X = np.asfortranarray(rng.standard_normal((n, p)))
+    want_s = kb.solve_s(Sigma, "maxent", m=m, ctx=kb.Context(0))
+    want_X = kb.condition(X, np.zeros(p), Sigma, want_s, m=m, seed=5, ctx=kb.Context(0))
+    c = kb.Context(0)
+    notpd = np.asfortranarray(np.full((p, p), 0.999) + 0.001 * np.eye(p))
+    for _ in range(2):
+        with pytest.raises(kb.PosDefException):                       # CCD: first Cholesky fails
+            kb.solve_s(notpd, "mvr", ctx=c, s_init=np.full(p, 1.0))
+        with pytest.raises(kb.PosDefException):                       # condition: 2S - S inv(Sigma) S indefinite for s = 2 diag
+            kb.condition(X, np.zeros(p), Sigma, np.full(p, 2.0), m=m, seed=5, ctx=c)
+        with pytest.raises(kb.KnockoffsError):
+            kb.modelX_gaussian_knockoffs(X, "nonsense", np.zeros(p), Sigma, m=m, ctx=c)
+        with pytest.raises(kb.PosDefException):                       # one-shot entry, error in the middle of the pipeline
+            kb.modelX_gaussian_knockoffs(X, "mvr", np.zeros(p), notpd, m=m, ctx=c, s_init=np.full(p, 1.0))
+        got_s = kb.solve_s(Sigma, "maxent", m=m, ctx=c)
+        got_X = kb.condition(X, np.zeros(p), Sigma, got_s, m=m, seed=5, ctx=c)
+        assert np.array_equal(got_s, want_s) and np.array_equal(got_X, want_X)
+
+
 def test_shapes_are_validated_before_the_c_call(kb, ctx):
     """DimensionMismatch-style errors instead of an out-of-bounds host read behind the raw pointers."""
     p, n = 40, 8
