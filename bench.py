@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--methods", default="mvr,sdp_ccd")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-split-factor", action="store_true", help="N >= 4: factor on the solver rank and broadcast all blocks (round-2 first form)")
     ap.add_argument("--c4-cold", action="store_true", help="config 4: time the first full-size solve (workspace allocation included)")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory leg of the end-to-end measurement")
     ap.add_argument("--no-cpu", action="store_true")
@@ -384,6 +385,13 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     per = {mth: {"solve_ms": 0.0, "ccd_ms": 0.0, "init_ms": 0.0, "factor_ms": 0.0, "ref_bytes": 0.0, "touched_bytes": 0.0,
                  "sweeps": 0, "flops": 0.0, "objective": None} for mth in methods}
 
+    # Factor split (>= 4 ranks, m >= 2): the m block columns of the factor are independent (closed form of the recursion,
+    # kb_cond_factor_block_dev), so after the solve only s is broadcast and the ranks build the columns side by side:
+    # ~5/3 p^3 flops per rank instead of 5.3 p^3 on the solver, then each column is broadcast from where it was built.
+    split_factor = (world >= 4 and m >= 2 and not a.no_split_factor)
+    split_model_ms = 16.0            # what the split factor adds after the solve (for the staggering decision only)
+    st["split_factor"] = split_factor
+
     def step(record=False):
         nvtx = torch.cuda.nvtx
         for i, mth in enumerate(methods):
@@ -395,12 +403,13 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
             info = dev.solve_s_dev(ctx, dSigma.data_ptr(), p, mth, m, ds[i].data_ptr(), refresh_every=a.refresh_every)
             nvtx.range_pop()
             e[1].record(ext)
-            nvtx.range_push(f"cond_factor:{mth}")
-            dev.cond_factor_dev(ctx, dSigma.data_ptr(), p, ds[i].data_ptr(), True, m, dSiS[i].data_ptr(), dLb[i].data_ptr())
-            nvtx.range_pop()
+            if not split_factor:
+                nvtx.range_push(f"cond_factor:{mth}")
+                dev.cond_factor_dev(ctx, dSigma.data_ptr(), p, ds[i].data_ptr(), True, m, dSiS[i].data_ptr(), dLb[i].data_ptr())
+                nvtx.range_pop()
             e[2].record(ext)
             ext.synchronize()
-            last["solve_factor_ms"] = e[0].elapsed_time(e[2])
+            last["solve_factor_ms"] = e[0].elapsed_time(e[2]) + (split_model_ms if split_factor else 0.0)
             if record:
                 q = per[mth]
                 q["solve_ms"] += e[0].elapsed_time(e[1]); q["factor_ms"] += e[1].elapsed_time(e[2])
@@ -417,12 +426,40 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
             dev.sample_dev(ctx, Xt.data_ptr() + 8 * (r0 - x_lo), r1 - r0, n_x, p, dmu.data_ptr(), dSiS[i].data_ptr(), dLb[i].data_ptr(), m,
                            Xko_t.data_ptr(), n_loc, seed=20260003 + i, row_offset=r0)
 
-        def bcast_method(i, group=None):
+        def bcast_method(i, group=None, ranks=None):
             # s (p doubles) and the factor blocks ((2m) p^2 doubles = 2 GB) from the rank that solved, NCCL over NVLink
             b0, b1 = E.ev(), E.ev()
             b0.record()
-            for t in (ds[i], dSiS[i], dLb[i]):
-                E.dist.broadcast(t, src=owner[i], group=group)
+            if not split_factor:
+                for t in (ds[i], dSiS[i], dLb[i]):
+                    E.dist.broadcast(t, src=owner[i], group=group)
+                b1.record()
+                torch.cuda.current_stream().synchronize()
+                return b0.elapsed_time(b1)
+            # split factor: only s travels from the solver; block column k of the factor (closed form, independent of the
+            # other columns: kb_cond_factor_block_dev) is built by rank ranks[(k - 1) % G] and broadcast from there
+            ranks = ranks if ranks is not None else list(range(world))
+            G = len(ranks)
+            E.dist.broadcast(ds[i], src=owner[i], group=group)
+            torch.cuda.current_stream().synchronize()
+            f0, f1 = E.ev(), E.ev()
+            f0.record(ext)
+            for k in range(1, m + 1):
+                if ranks[(k - 1) % G] == rank:
+                    dev.cond_factor_block_dev(ctx, dSigma.data_ptr(), p, ds[i].data_ptr(), k, m, dSiS[i].data_ptr() if k == 1 else 0,
+                                              dLb[i][2 * (k - 1)].data_ptr(), dLb[i][2 * (k - 1) + 1].data_ptr() if k < m else 0)
+            f1.record(ext)
+            ext.synchronize()
+            if record and rank == owner[i]:
+                per[methods[i]]["factor_ms"] += f0.elapsed_time(f1)
+            b0.record()
+            for k in range(1, m + 1):
+                src = ranks[(k - 1) % G]
+                if k == 1:
+                    E.dist.broadcast(dSiS[i], src=src, group=group)
+                E.dist.broadcast(dLb[i][2 * (k - 1)], src=src, group=group)
+                if k < m:
+                    E.dist.broadcast(dLb[i][2 * (k - 1) + 1], src=src, group=group)
             b1.record()
             torch.cuda.current_stream().synchronize()
             return b0.elapsed_time(b1)
@@ -433,7 +470,7 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
         if staggered:
             grp, early_ranks = early
             if rank in early_ranks:
-                bc += bcast_method(0, grp)
+                bc += bcast_method(0, grp, early_ranks)
                 e0.record(ext); sample(0); e1.record(ext); ext.synchronize()
                 samp += e0.elapsed_time(e1)
             bc_all = bcast_method(1)
@@ -1045,8 +1082,9 @@ def run_ours(a):
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg,
-                "parallelism": (f"rows sharded x{world} ({res['shard'][1] - res['shard'][0]} per GPU), solves of the {len(methods)} methods on different ranks, "
-                                f"s + factor blocks NCCL-broadcast" + ("; the ranks that do not run the long :sdp_ccd solve sample ALL :mvr rows meanwhile"
+                "parallelism": (f"rows sharded x{world} ({res['shard'][1] - res['shard'][0]} per GPU), solves of the {len(methods)} methods on different ranks, " +
+                                ("s NCCL-broadcast, the m block columns of the factor built side by side on different ranks (closed form) and broadcast from there"
+                                 if st.get("split_factor") else "s + factor blocks NCCL-broadcast") + ("; the ranks that do not run the long :sdp_ccd solve sample ALL :mvr rows meanwhile"
                                                                        if st.get("staggered") else "") if world > 1 else
                                 ("single GPU, two contexts: :mvr sampled on the background (SM-partitioned) context beside the :sdp_ccd solve"
                                  if st.get("pipelined") else "single GPU, stages strictly one after the other")),

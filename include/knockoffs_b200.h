@@ -257,6 +257,12 @@ int kb_modelx_gaussian_knockoffs(kb_ctx* ctx, const double* X, int64_t n, int64_
 /* device-resident pieces of the same pipeline (used by the multi-GPU driver and bench.py) */
 int kb_cond_factor_dev(kb_ctx* ctx, const double* dSigma, int64_t p, const double* dS, int32_t s_is_diag,
                        int32_t m, double* dSigmaInvS, double* dLblocks);
+/* One block column k (1-based) of the factor for Diagonal(s), independent of the others: the recursion of
+ * modelX.jl:116-120 has the closed form A_k = ((k+1)/k) S - (1/k) S (k Sigma - (k-1) S)^-1 S, L_kk = chol(A_k),
+ * M_k = L_kk - S inv(L_kk)'.  Lets several devices / ranks build the m block columns side by side.
+ * dSigmaInvS: written for k == 1 only (may be NULL); dMk: NULL allowed, not written for k == m. */
+int kb_cond_factor_block_dev(kb_ctx* ctx, const double* dSigma, int64_t p, const double* ds, int32_t k, int32_t m,
+                             double* dSigmaInvS, double* dLkk, double* dMk);
 int kb_sample_dev(kb_ctx* ctx, const double* dX, int64_t n, int64_t ldx, int64_t p, const double* dmu,
                   const double* dSigmaInvS, const double* dLblocks, int32_t m, const double* dZ, int64_t ldz,
                   uint64_t seed, int64_t row_offset, double* dXko, int64_t ldxko);

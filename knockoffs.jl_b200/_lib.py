@@ -78,6 +78,7 @@ SIGNATURES = {
     "kb_cov_shrink_lw": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, c_double_p]),
     "kb_cond_factor": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "kb_cond_factor_dev": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "kb_cond_factor_block_dev": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _vp, _vp, _vp]),
     "kb_sample": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _u64, _i64, _vp]),
     "kb_condition": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _vp, _u64, _i64, _vp]),
     "kb_sample_dev": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i64, _u64, _i64, _vp, _i64]),

@@ -782,6 +782,16 @@ int kb_cond_factor_dev(kb_ctx* ctx, const double* dSigma, int64_t p, const doubl
     return KB_OK;
 }
 
+int kb_cond_factor_block_dev(kb_ctx* ctx, const double* dSigma, int64_t p, const double* ds, int32_t k, int32_t m,
+                             double* dSigmaInvS, double* dLkk, double* dMk) {
+    if (!ctx) return bad_ctx();
+    if (!dSigma || !ds || !dLkk || p < 1) return set_error(ctx, KB_ERR_INVALID, "cond_factor_block: bad arguments");
+    DeviceGuard g(ctx->device);
+    KB_TRY(cond_factor_block_dev(ctx, dSigma, (long)p, (int)p, ds, k, m, dSigmaInvS, dLkk, dMk, (long)p));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KB_OK;
+}
+
 int kb_cond_factor(kb_ctx* ctx, const double* Sigma, int64_t p, const double* S, int32_t s_is_diag, int32_t m,
                    double* SigmaInvS_out, double* Lblocks_out) {
     if (!ctx) return bad_ctx();

@@ -18,6 +18,8 @@ int eigmin_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, double* lambd
 
 // dSigma: upper triangle trusted, leading dim lds.  dS: p-vector (diag) or p x p (ld = ldS).
 // Outputs: dSiS (p x p, ld ldo) and dLb (2m-1 blocks of p x p, each ld ldo, block stride ldo*p).
+int cond_factor_block_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const double* ds, int k, int m,
+                          double* dSiS, double* dLkk, double* dMk, long ldo);
 int cond_factor_dev(kb_ctx* ctx, const double* dSigma, long lds, int p, const double* dS, long ldS, int s_is_diag,
                     int m, double* dSiS, double* dLb, long ldo);
 

@@ -19,6 +19,11 @@ def solve_s_dev(ctx: Context, dSigma: int, p: int, method, m, d_s_out: int, d_s_
     return _info_dict(info, str(method).lstrip(":"))
 
 
+def cond_factor_block_dev(ctx: Context, dSigma: int, p: int, ds: int, k: int, m: int, dSiS: int, dLkk: int, dMk: int):
+    """Block column k (1-based) of the factor for Diagonal(s) from the closed form of the recursion (pointers; 0 = NULL)."""
+    check(ctx.h, ctx._lib.kb_cond_factor_block_dev(ctx.h, dSigma, p, ds, int(k), int(m), dSiS or None, dLkk, dMk or None))
+
+
 def cond_factor_dev(ctx: Context, dSigma: int, p: int, dS: int, s_is_diag: bool, m: int, dSiS: int, dLb: int):
     check(ctx.h, ctx._lib.kb_cond_factor_dev(ctx.h, dSigma, p, dS, int(s_is_diag), int(m), dSiS, dLb))
 

@@ -203,6 +203,38 @@ def test_shapes_are_validated_before_the_c_call(kb, ctx):
 
 
 # ---- conditional factor + sampling ---------------------------------------------------------------------
+@pytest.mark.parametrize("p,m,method", [(200, 1, "maxent"), (130, 3, "mvr"), (257, 5, "sdp_ccd"), (192, 4, "equi09")])
+def test_cond_factor_block_columns_equal_the_recursion(kb, ctx, p, m, method):
+    """kb_cond_factor_block_dev: block column k from the closed form A_k = ((k+1)/k) S - (1/k) S (k Sigma - (k-1) S)^-1 S
+    against the recursion of modelX.jl:116-120 (kb_cond_factor) and against the oracle's dense pm x pm Cholesky factor."""
+    import torch
+    Sigma = toeplitz(p, 0.5)
+    if method == "equi09":
+        s = 0.9 * kb.solve_s(Sigma, "equi", m=m, ctx=ctx)
+    else:
+        s = kb.solve_s(Sigma, method, m=m, ctx=ctx)
+    SiS_w, Lb_w = kb.cond_factor(Sigma, s, m=m, ctx=ctx)
+    _, L_oracle = ko.cond_factor(Sigma, s, m)
+    d = torch.device("cuda", 0)
+    dSig = torch.from_numpy(np.ascontiguousarray(Sigma)).to(d)
+    ds = torch.from_numpy(s).to(d)
+    dSiS = torch.zeros((p, p), dtype=torch.float64, device=d)
+    dLb = torch.zeros((2 * m - 1, p, p), dtype=torch.float64, device=d)
+    torch.cuda.synchronize()
+    for k in range(m, 0, -1):                              # any order: the columns are independent
+        kb.dev.cond_factor_block_dev(ctx, dSig.data_ptr(), p, ds.data_ptr(), k, m, dSiS.data_ptr() if k == 1 else 0,
+                                     dLb[2 * (k - 1)].data_ptr(), dLb[2 * (k - 1) + 1].data_ptr() if k < m else 0)
+    got = np.transpose(dLb.cpu().numpy(), (2, 1, 0))       # device blocks are column-major p x p
+    tol = 1e-6 if method == "sdp_ccd" else 1e-9            # :sdp_ccd ends on the feasibility boundary (cond ~ 1e9)
+    scale = np.max(np.abs(Lb_w))
+    assert np.max(np.abs(got - Lb_w)) / scale < tol
+    assert np.max(np.abs(dSiS.cpu().numpy().T - SiS_w)) < 1e-11
+    L = kb.dense_factor_from_blocks(np.asfortranarray(got))
+    assert np.max(np.abs(L - L_oracle)) / np.max(np.abs(L_oracle)) < (1e-6 if method == "sdp_ccd" else 1e-8)
+    with pytest.raises(kb.KnockoffsError):
+        kb.dev.cond_factor_block_dev(ctx, dSig.data_ptr(), p, ds.data_ptr(), m + 1, m, 0, dLb[0].data_ptr(), 0)
+
+
 @pytest.mark.parametrize("p,m", [(200, 1), (130, 3), (257, 2)])
 def test_cond_factor_matches_oracle(kb, ctx, p, m):
     Sigma = toeplitz(p, 0.5)
