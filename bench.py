@@ -612,7 +612,7 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     out = {"ms_per_step": ms_per_step, "value": len(methods) * n_total / (ms_per_step * 1e-3), "launches": int(launches),
            "clocks": clocks, "n_total": n_total, "rows_per_gpu": n_loc, "st": st, "per": per, "owner": owner,
            "handles": (dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo), "ctx_bg": ctx_bg,
-           "shard": (lo, hi, x_lo)}
+           "shard": (lo, hi, x_lo), "stag": {"on": bool(mode["staggered"]), "rows0": rows_stag[0], "early": early}}
     del Xko_t2
     # per-method timings live on their owner: gather them on rank 0
     if world > 1:
@@ -645,7 +645,18 @@ def run_e2e(E, a, res, steps):
         n_e = max(1024, int(n_loc * 0.6 * avail / need) // 1024 * 1024)
     Xh_t = torch.empty((p, n_e), dtype=torch.float64, pin_memory=True)
     Xh_t.copy_(Xt[:, lo - x_lo:lo - x_lo + n_e])
-    Xko_h_t = torch.empty((m * p, n_e), dtype=torch.float64, pin_memory=True)
+    # staggered (N >= 3): like the device-resident step, the ranks that do not run the long solve condition ALL rows of the
+    # first method among themselves meanwhile; this rank's share of those rows gets its own pinned X buffer
+    stag = res.get("stag") or {"on": False}
+    stag_on = bool(stag["on"]) and n_e == n_loc
+    r0 = r1 = 0
+    Xh0_t = None
+    if stag_on:
+        r0, r1 = stag["rows0"]
+        if r1 > r0:
+            Xh0_t = torch.empty((p, r1 - r0), dtype=torch.float64, pin_memory=True)
+            Xh0_t.copy_(Xt[:, r0 - x_lo:r1 - x_lo])
+    Xko_h_t = torch.empty((m * p, max(n_e, r1 - r0)), dtype=torch.float64, pin_memory=True)
     mu_h = np.zeros(p)
     Sig_f = np.asfortranarray(Sigma_h)
     s_h = [np.empty(p) for _ in methods]
@@ -668,6 +679,31 @@ def run_e2e(E, a, res, steps):
             rc = ctx._lib.kb_condition(ctx.h, Xh_t.data_ptr(), n_e, p, mu_h.ctypes.data, Sig_f.ctypes.data, s_h[i].ctypes.data, 1, m,
                                        None, 20260003 + i, lo, Xko_h_t.data_ptr())
             kb.api.check(ctx.h, rc)
+
+    def e2e_step_staggered():
+        grp, early_ranks = stag["early"]
+        if owner[0] == rank:
+            rc = ctx._lib.kb_solve_s(ctx.h, Sig_f.ctypes.data, p, kb.api.METHODS[methods[0]], float(m), C.byref(opts), None,
+                                     s_h[0].ctypes.data, C.byref(info))
+            kb.api.check(ctx.h, rc)
+        if rank in early_ranks:
+            t = torch.from_numpy(s_h[0]).to(E.d)
+            E.dist.broadcast(t, src=owner[0], group=grp)
+            s_h[0][:] = t.cpu().numpy()
+            if r1 > r0:
+                rc = ctx._lib.kb_condition(ctx.h, Xh0_t.data_ptr(), r1 - r0, p, mu_h.ctypes.data, Sig_f.ctypes.data, s_h[0].ctypes.data,
+                                           1, m, None, 20260003, r0, Xko_h_t.data_ptr())
+                kb.api.check(ctx.h, rc)
+        if owner[1] == rank:
+            rc = ctx._lib.kb_solve_s(ctx.h, Sig_f.ctypes.data, p, kb.api.METHODS[methods[1]], float(m), C.byref(opts), None,
+                                     s_h[1].ctypes.data, C.byref(info))
+            kb.api.check(ctx.h, rc)
+        t = torch.from_numpy(s_h[1]).to(E.d)
+        E.bcast(t, owner[1])
+        s_h[1][:] = t.cpu().numpy()
+        rc = ctx._lib.kb_condition(ctx.h, Xh_t.data_ptr(), n_e, p, mu_h.ctypes.data, Sig_f.ctypes.data, s_h[1].ctypes.data, 1, m,
+                                   None, 20260003 + 1, lo, Xko_h_t.data_ptr())
+        kb.api.check(ctx.h, rc)
 
     # 1 GPU: the same software pipeline as the device-resident step -- kb_condition(:mvr) runs on the background context
     # (second host thread, its own pinned output buffer) while the foreground context solves :sdp_ccd
@@ -713,6 +749,8 @@ def run_e2e(E, a, res, steps):
 
     if Xko_h_t2 is not None:
         e2e_step = e2e_step_pipelined    # noqa: F811
+    if stag_on and world > 2 and len(methods) == 2:
+        e2e_step = e2e_step_staggered    # noqa: F811
     e2e_step()                     # warm-up
     E.barrier()
     t0 = time.perf_counter()
@@ -722,9 +760,11 @@ def run_e2e(E, a, res, steps):
     dt = E.max_over_ranks(time.perf_counter() - t0)
     rows = n_e * world if res["n_total"] != a.n or world == 1 else int(round(a.n * n_e / n_loc))
     nm = len(methods)
+    rows_in = (n_e + (r1 - r0)) if e2e_step is e2e_step_staggered else nm * n_e          # rows this rank conditions per step
     out = {"value": nm * rows * steps / dt, "unit": UNIT,
-           "h2d_bytes_per_step": int(nm * (p * n_e + p * p + 2 * p) * 8 + sum(p * p * 8 for i in range(nm) if owner[i] == rank)),
-           "d2h_bytes_per_step": int(nm * (m * p * n_e) * 8 + sum(p * 8 for i in range(nm) if owner[i] == rank)),
+           "h2d_bytes_per_step": int((p * rows_in + nm * (p * p + 2 * p)) * 8 + sum(p * p * 8 for i in range(nm) if owner[i] == rank)),
+           "d2h_bytes_per_step": int((m * p * rows_in) * 8 + sum(p * 8 for i in range(nm) if owner[i] == rank)),
+           "staggered": e2e_step is e2e_step_staggered,
            "rows_per_gpu": n_e, "ms_per_step": 1000.0 * dt / steps,
            "api": "kb_solve_s + kb_condition (host pointers, pinned); bytes are per rank",
            "pipelined": Xko_h_t2 is not None}
@@ -756,7 +796,7 @@ def run_e2e(E, a, res, steps):
             del Xp, Xkop
         except MemoryError as ex:
             out["pageable"] = {"unavailable": str(ex)}
-    del Xh_t, Xko_h_t, Xko_h_t2
+    del Xh_t, Xko_h_t, Xko_h_t2, Xh0_t
     return out
 
 
