@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--methods", default="mvr,sdp_ccd")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stagger", action="store_true", help="N > 1: plain order (both solves, then all sampling)")
     ap.add_argument("--no-split-factor", action="store_true", help="N >= 4: factor on the solver rank and broadcast all blocks (round-2 first form)")
     ap.add_argument("--c4-cold", action="store_true", help="config 4: time the first full-size solve (workspace allocation included)")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory leg of the end-to-end measurement")
@@ -354,31 +355,64 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     # second method's rows are then shared by all ranks.
     owner = [i % world for i in range(len(methods))]
     can_stagger = (world > 1 and len(methods) == 2)
-    rows_plain = [(lo, hi) for _ in methods]
-    rows_stag = list(rows_plain)
     early = None
+    early_ranks = []
     if can_stagger:
         grp, early_ranks = E.group_without(owner[1])
         early = (grp, early_ranks)
-        if rank in early_ranks:
-            rows_stag[0] = kb.dist.shard_rows(n_total, len(early_ranks), early_ranks.index(rank))
+    # f = the fraction of the FIRST method's rows that the early ranks (everyone but the long solver) sample while the long
+    # solve is still running: as many as fit into that gap (f = 1 from 3-4 ranks on for n = 1e5; ~0.4 on 2 ranks or in the weak
+    # run).  The remaining (1 - f) n rows of the first method and all rows of the second are then shared by all ranks.
+    # f = 0 is the plain order.  Decided after the first (plain) warm-up step from its measured stage times, see below.
+    frac = {"f": 0.0}
+
+    def layout(f):
+        n_early = int(round(f * n_total)) if can_stagger else 0
+        if n_early > 0 and rank in early_ranks:
+            e_rng = kb.dist.shard_rows(n_early, len(early_ranks), early_ranks.index(rank))
         else:
-            rows_stag[0] = (lo, lo)                              # the long solver samples none of the first method
-    mode = {"staggered": False}                                  # decided after the first (plain) warm-up step, see below
-    rows = rows_plain
-    both = [r for r in rows_plain + rows_stag if r[1] > r[0]]
-    x_lo = min(r[0] for r in both)
-    x_hi = max(r[1] for r in both)
-    n_x = x_hi - x_lo
-    n_loc = max(r[1] - r[0] for r in rows_plain + rows_stag)
+            e_rng = (0, 0)
+        l0, l1 = kb.dist.shard_rows(n_total - n_early, world, rank)
+        return e_rng, (l0 + n_early, l1 + n_early)
+
     Sigma_h = kb.harness.block_sigma(p, 10, 0.5, 0.25)
     dSigma = torch.from_numpy(np.ascontiguousarray(Sigma_h)).to(E.d)          # symmetric: row/col-major coincide
-    Xt = gen_gaussian_Xt(E, dSigma, p, n_x, 20260003 + rank)              # this rank's rows [x_lo, x_hi) of X
+    buf = {"X": {}, "Xko_t": None, "n_loc": 0}
+
+    def ensure_buffers(f):
+        """This rank's rows of X under layout(f) -- one device matrix per row range (plain shard, early share, late share) --
+        and an output buffer for its longest range."""
+        e_rng, l_rng = layout(f)
+        want = {"plain": (lo, hi), "early": e_rng, "late": l_rng}
+        for k, (r0, r1) in want.items():
+            have = buf["X"].get(k)
+            if r1 <= r0:
+                buf["X"].pop(k, None)
+            elif have is None or have[0] != r0 or have[1] != r1:
+                buf["X"].pop(k, None)
+                if k != "plain" and (r0, r1) == (lo, hi):
+                    buf["X"][k] = buf["X"]["plain"]
+                else:
+                    buf["X"][k] = (r0, r1, gen_gaussian_Xt(E, dSigma, p, r1 - r0, 20260003 + rank + 1000 * len(k)))
+        need = max(r[1] - r[0] for r in want.values())
+        if buf["Xko_t"] is None or need > buf["n_loc"]:
+            buf["Xko_t"] = None
+            buf["Xko_t"] = torch.empty((m * p, need), dtype=f64, device=E.d)
+            buf["n_loc"] = need
+
+    def x_rows(r0, r1):
+        """(device pointer of row r0, leading dimension) in the piece of X that holds rows [r0, r1)"""
+        for q0, q1, t in buf["X"].values():
+            if q0 <= r0 and r1 <= q1:
+                return t.data_ptr() + 8 * (r0 - q0), q1 - q0
+        raise RuntimeError(f"rows [{r0}, {r1}) of X are not resident on rank {rank}")
+
+    ensure_buffers(0.0)
+    Xt, x_lo, n_x, Xko_t, n_loc = buf["X"]["plain"][2], lo, hi - lo, buf["Xko_t"], buf["n_loc"]     # 1-GPU paths below
     dmu = torch.zeros(p, dtype=f64, device=E.d)
     ds = [torch.empty(p, dtype=f64, device=E.d) for _ in methods]
     dSiS = [torch.empty((p, p), dtype=f64, device=E.d) for _ in methods]
     dLb = [torch.empty((2 * m - 1, p, p), dtype=f64, device=E.d) for _ in methods]
-    Xko_t = torch.empty((m * p, n_loc), dtype=f64, device=E.d)
     torch.cuda.synchronize()
     st = {"steps": 0, "bcast_ms": 0.0, "sample_ms": 0.0, "staggered": False}
     last = {"solve_factor_ms": 0.0, "sample_ms": 0.0}            # stage times of the most recent step on this rank
@@ -416,15 +450,16 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
                 q["ccd_ms"] += info["solve_ms"]; q["init_ms"] += info["init_ms"]; q["ref_bytes"] += info["ref_bytes"]
                 q["touched_bytes"] += info["touched_bytes"]; q["sweeps"] = info["sweeps"]; q["mode"] = info["mode"]
                 q["flops"] += info["flops"]; q["objective"] = info["objective"]
-        rows = rows_stag if mode["staggered"] else rows_plain
-        staggered = mode["staggered"]
+        f = frac["f"]
+        staggered = f > 0.0
+        e_rng, l_rng = layout(f)
 
-        def sample(i):
-            r0, r1 = rows[i]
+        def sample(i, r0, r1):
             if r1 <= r0:
                 return
-            dev.sample_dev(ctx, Xt.data_ptr() + 8 * (r0 - x_lo), r1 - r0, n_x, p, dmu.data_ptr(), dSiS[i].data_ptr(), dLb[i].data_ptr(), m,
-                           Xko_t.data_ptr(), n_loc, seed=20260003 + i, row_offset=r0)
+            xp, xld = x_rows(r0, r1)
+            dev.sample_dev(ctx, xp, r1 - r0, xld, p, dmu.data_ptr(), dSiS[i].data_ptr(),
+                           dLb[i].data_ptr(), m, buf["Xko_t"].data_ptr(), buf["n_loc"], seed=20260003 + i, row_offset=r0)
 
         def bcast_method(i, group=None, ranks=None):
             # s (p doubles) and the factor blocks ((2m) p^2 doubles = 2 GB) from the rank that solved, NCCL over NVLink
@@ -468,14 +503,23 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
         samp = 0.0
         bc = 0.0
         if staggered:
-            grp, early_ranks = early
+            grp, _ = early
             if rank in early_ranks:
                 bc += bcast_method(0, grp, early_ranks)
-                e0.record(ext); sample(0); e1.record(ext); ext.synchronize()
+                e0.record(ext); sample(0, *e_rng); e1.record(ext); ext.synchronize()
                 samp += e0.elapsed_time(e1)
             bc_all = bcast_method(1)
+            if f < 1.0:
+                # the rest of the first method's rows is shared by ALL ranks: the long solver has not seen its blocks yet
+                b0, b1 = E.ev(), E.ev()
+                b0.record()
+                for t in (dSiS[0], dLb[0]):
+                    E.dist.broadcast(t, src=owner[0])
+                b1.record()
+                torch.cuda.current_stream().synchronize()
+                bc_all += b0.elapsed_time(b1)
             e2, e3 = E.ev(), E.ev()
-            e2.record(ext); sample(1); e3.record(ext); ext.synchronize()
+            e2.record(ext); sample(0, *l_rng); sample(1, lo, hi); e3.record(ext); ext.synchronize()
             samp += e2.elapsed_time(e3)
             if record:
                 st["bcast_ms"] += bc_all if rank == owner[1] else bc       # the waiting inside a collective is not transfer time
@@ -487,7 +531,7 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
                     st["bcast_ms"] += bc
             e0.record(ext)
             for i in range(len(methods)):
-                sample(i)
+                sample(i, lo, hi)
             e1.record(ext)
             ext.synchronize()
             samp = e0.elapsed_time(e1)
@@ -575,23 +619,33 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
         step = step_pipelined            # noqa: F811
     for w in range(warmup):
         step()
-        if w == 0 and can_stagger:
+        if w == 0 and can_stagger and not a.no_stagger:
             # One plain step has been timed on every rank: A / B = solve + factor of the short / long method on their owners,
-            # t = this rank's sampling of its plain shard of both methods.  Sampling all rows of one method on one GPU then
-            # takes Ts = t N / 2.  plain: B + 2 Ts / N;  staggered: max(A + Ts / (N - 1), B) + Ts / N.  Every rank evaluates the
-            # same gathered numbers, so all take the same decision.
+            # t = this rank's sampling of its plain shard of both methods; sampling all rows of one method on one GPU then
+            # takes Ts = t N / 2.  The early ranks can sample  f = (B - A - broadcast) (N - 1) / Ts  of the first method's rows
+            # before the long solve ends (capped at 1).  plain: B + 2 Ts / N;  staggered: max(A + f Ts / (N - 1), B) +
+            # (2 - f) Ts / N.  Every rank evaluates the same gathered numbers, so all take the same decision.
             gathered = [None] * world
             E.dist.all_gather_object(gathered, (last["solve_factor_ms"], last["sample_ms"]))
             A_ms, B_ms = gathered[owner[0]][0], gathered[owner[1]][0]
             Ts = max(g[1] for g in gathered) * world / 2.0
+            gap = B_ms - A_ms - 5.0
+            f = min(1.0, 0.97 * gap * (world - 1) / Ts) if (gap > 0 and Ts > 0) else 0.0
+            f = float(int(f * 64.0)) / 64.0 if f < 1.0 else 1.0
             plain_ms = B_ms + 2.0 * Ts / world
-            stag_ms = max(A_ms + Ts / (world - 1), B_ms) + Ts / world
-            mode["staggered"] = stag_ms < 0.98 * plain_ms
-            st["staggered"] = mode["staggered"]
+            stag_ms = max(A_ms + f * Ts / (world - 1), B_ms) + (2.0 - f) * Ts / world + (4.0 if f < 1.0 else 0.0)
+            if f < 0.1 or stag_ms >= 0.98 * plain_ms:
+                f = 0.0
+            frac["f"] = f
+            st["staggered"] = f > 0.0
+            st["early_fraction"] = f
             st["stagger_model_ms"] = {"plain": plain_ms, "staggered": stag_ms}
-    if warmup == 0 and can_stagger:
-        mode["staggered"] = scaling == "strong" and world >= 3
-        st["staggered"] = mode["staggered"]
+            ensure_buffers(f)
+    if warmup == 0 and can_stagger and not a.no_stagger:
+        frac["f"] = 1.0 if (scaling == "strong" and world >= 3) else 0.0
+        st["staggered"] = frac["f"] > 0.0
+        st["early_fraction"] = frac["f"]
+        ensure_buffers(frac["f"])
     sampler = ClockSampler(E.local) if (sample_clocks and rank == 0) else None
     E.barrier()
     if sampler:
@@ -610,9 +664,11 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     total_ms = E.max_over_ranks(t0.elapsed_time(t1))
     ms_per_step = total_ms / steps
     out = {"ms_per_step": ms_per_step, "value": len(methods) * n_total / (ms_per_step * 1e-3), "launches": int(launches),
-           "clocks": clocks, "n_total": n_total, "rows_per_gpu": n_loc, "st": st, "per": per, "owner": owner,
-           "handles": (dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo), "ctx_bg": ctx_bg,
-           "shard": (lo, hi, x_lo), "stag": {"on": bool(mode["staggered"]), "rows0": rows_stag[0], "early": early}}
+           "clocks": clocks, "n_total": n_total, "rows_per_gpu": buf["n_loc"], "st": st, "per": per, "owner": owner,
+           "handles": (dSigma, buf["X"]["plain"][2], dmu, ds, dSiS, dLb, buf["Xko_t"], Sigma_h, lo), "ctx_bg": ctx_bg,
+           "shard": (lo, hi, lo), "stag": {"on": frac["f"] == 1.0, "rows0": layout(frac["f"])[0], "early": early,
+                                           "X0": buf["X"].get("early", (0, 0, None))[2]}}
+    del Xt, Xko_t
     del Xko_t2
     # per-method timings live on their owner: gather them on rank 0
     if world > 1:
@@ -655,7 +711,7 @@ def run_e2e(E, a, res, steps):
         r0, r1 = stag["rows0"]
         if r1 > r0:
             Xh0_t = torch.empty((p, r1 - r0), dtype=torch.float64, pin_memory=True)
-            Xh0_t.copy_(Xt[:, r0 - x_lo:r1 - x_lo])
+            Xh0_t.copy_(stag["X0"])
     Xko_h_t = torch.empty((m * p, max(n_e, r1 - r0)), dtype=torch.float64, pin_memory=True)
     mu_h = np.zeros(p)
     Sig_f = np.asfortranarray(Sigma_h)
@@ -1015,7 +1071,7 @@ def run_ours(a):
 
     res = run_pipeline(E, a, a.scaling, a.steps, a.warmup, sample_clocks=True)
     dSigma, Xt, dmu, ds, dSiS, dLb, Xko_t, Sigma_h, lo = res["handles"]
-    n_loc = res["rows_per_gpu"]
+    n_loc = min(res["rows_per_gpu"], Xt.shape[1])     # rows of the plain shard: what the stage timed alone below samples
 
     # ---- the memory-bound formulation, timed alone (outside the step): ONE sweep of the rank-1 streaming kernel
     #      (8 p (p+1)^2 algorithmic bytes) -> achieved HBM GB/s of ccd_stream_kernel
@@ -1124,8 +1180,8 @@ def run_ours(a):
                 "dtype": "f64", "data": "synthetic", "config": cfg,
                 "parallelism": (f"rows sharded x{world} ({res['shard'][1] - res['shard'][0]} per GPU), solves of the {len(methods)} methods on different ranks, " +
                                 ("s NCCL-broadcast, the m block columns of the factor built side by side on different ranks (closed form) and broadcast from there"
-                                 if st.get("split_factor") else "s + factor blocks NCCL-broadcast") + ("; the ranks that do not run the long :sdp_ccd solve sample ALL :mvr rows meanwhile"
-                                                                       if st.get("staggered") else "") if world > 1 else
+                                 if st.get("split_factor") else "s + factor blocks NCCL-broadcast") + (f"; the ranks that do not run the long :sdp_ccd solve sample {100.0 * st.get('early_fraction', 1.0):.0f} % of the :mvr rows meanwhile, "
+                                                                        "the rest is shared by all ranks afterwards" if st.get("staggered") else "") if world > 1 else
                                 ("single GPU, two contexts: :mvr sampled on the background (SM-partitioned) context beside the :sdp_ccd solve"
                                  if st.get("pipelined") else "single GPU, stages strictly one after the other")),
                 "clocks": res["clocks"], "gpu_launches": res["launches"],
