@@ -367,13 +367,7 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
     frac = {"f": 0.0}
 
     def layout(f):
-        n_early = int(round(f * n_total)) if can_stagger else 0
-        if n_early > 0 and rank in early_ranks:
-            e_rng = kb.dist.shard_rows(n_early, len(early_ranks), early_ranks.index(rank))
-        else:
-            e_rng = (0, 0)
-        l0, l1 = kb.dist.shard_rows(n_total - n_early, world, rank)
-        return e_rng, (l0 + n_early, l1 + n_early)
+        return kb.dist.stagger_layout(n_total, world, rank, owner[1] if can_stagger else -1, f if can_stagger else 0.0)
 
     Sigma_h = kb.harness.block_sigma(p, 10, 0.5, 0.25)
     dSigma = torch.from_numpy(np.ascontiguousarray(Sigma_h)).to(E.d)          # symmetric: row/col-major coincide
@@ -629,13 +623,7 @@ def run_pipeline(E, a, scaling, steps, warmup, sample_clocks=False):
             E.dist.all_gather_object(gathered, (last["solve_factor_ms"], last["sample_ms"]))
             A_ms, B_ms = gathered[owner[0]][0], gathered[owner[1]][0]
             Ts = max(g[1] for g in gathered) * world / 2.0
-            gap = B_ms - A_ms - 5.0
-            f = min(1.0, 0.97 * gap * (world - 1) / Ts) if (gap > 0 and Ts > 0) else 0.0
-            f = float(int(f * 64.0)) / 64.0 if f < 1.0 else 1.0
-            plain_ms = B_ms + 2.0 * Ts / world
-            stag_ms = max(A_ms + f * Ts / (world - 1), B_ms) + (2.0 - f) * Ts / world + (4.0 if f < 1.0 else 0.0)
-            if f < 0.1 or stag_ms >= 0.98 * plain_ms:
-                f = 0.0
+            f, plain_ms, stag_ms = kb.dist.stagger_fraction(A_ms, B_ms, Ts, world)
             frac["f"] = f
             st["staggered"] = f > 0.0
             st["early_fraction"] = f

@@ -27,6 +27,42 @@ def assign_round_robin(n_items: int, world: int, rank: int) -> List[int]:
     return list(range(rank, n_items, world))
 
 
+# ---- two solves of very different length on different ranks (bench.py: :mvr on rank 0, :sdp_ccd on rank 1) ------------
+# While the long solve is still running, the other ranks ("early" ranks) already hold the short method's factor and sample a
+# fraction f of ITS rows among themselves; afterwards all ranks share the remaining (1 - f) n rows of the short method and the
+# n rows of the long one.  No data-path collective is added: the device RNG is keyed by the global row, so the union of the
+# pieces is the single-GPU result whatever the split.
+def stagger_fraction(A_ms: float, B_ms: float, Ts_ms: float, world: int, bcast_ms: float = 5.0, late_bcast_ms: float = 4.0):
+    """f in [0, 1] and the modelled step times (plain, staggered).  A / B: solve + factor time of the short / long method on
+    their ranks; Ts: time to sample ALL rows of one method on one GPU.  plain = B + 2 Ts / N;  the early ranks can sample
+    f = (B - A - bcast)(N - 1) / Ts of the short method's rows before the long solve ends;  staggered = max(A + f Ts / (N - 1), B)
+    + (2 - f) Ts / N (+ one more broadcast of the short method's blocks to the long solver when f < 1).  f is cut to 1/64ths
+    so that every rank derives the same row counts; 0 when staggering is not worth at least 2 %."""
+    plain = B_ms + 2.0 * Ts_ms / world
+    if world < 2 or Ts_ms <= 0.0:
+        return 0.0, plain, plain
+    gap = B_ms - A_ms - bcast_ms
+    f = min(1.0, 0.97 * gap * (world - 1) / Ts_ms) if gap > 0.0 else 0.0
+    f = float(int(f * 64.0)) / 64.0 if f < 1.0 else 1.0
+    stag = max(A_ms + f * Ts_ms / (world - 1), B_ms) + (2.0 - f) * Ts_ms / world + (late_bcast_ms if f < 1.0 else 0.0)
+    if f < 0.1 or stag >= 0.98 * plain:
+        return 0.0, plain, stag
+    return f, plain, stag
+
+
+def stagger_layout(n_total: int, world: int, rank: int, long_rank: int, f: float):
+    """Row ranges of the SHORT method for `rank`: (early range, late range).  The first round(f n) rows are dealt to the ranks
+    other than `long_rank` (early), the rest to all ranks (late).  The long method's rows are the plain shard_rows()."""
+    n_early = int(round(f * n_total)) if world > 1 else 0
+    early_ranks = [r for r in range(world) if r != long_rank]
+    if n_early > 0 and rank in early_ranks:
+        e_rng = shard_rows(n_early, len(early_ranks), early_ranks.index(rank))
+    else:
+        e_rng = (0, 0)
+    l0, l1 = shard_rows(n_total - n_early, world, rank)
+    return e_rng, (l0 + n_early, l1 + n_early)
+
+
 def allreduce_gram(G, colsum, group=None):
     """The Gram stage's only exchange: sum of the per-rank p x p partial Grams and column sums."""
     import torch.distributed as dist

@@ -92,3 +92,34 @@ def test_shard_rows_properties():
     assert kb.dist.assign_round_robin(5, 2, 1) == [1, 3]
     G, mu = kb.dist.gram_reference_numpy([np.ones((2, 2)), 2 * np.ones((3, 2))])
     assert G.shape == (2, 2) and np.allclose(mu, 1.6)
+
+
+def test_stagger_layout_and_fraction():
+    """bench.py's multi-rank step: every row of the short method is sampled exactly once whatever the early fraction, the early
+    ranks exclude the long solver, and the decision model reproduces the measured B200 regimes."""
+    sys.path.insert(0, ROOT)
+    import knockoffs_b200  # noqa: F401
+    kb = sys.modules["knockoffs_b200"]
+    for world in (1, 2, 3, 4, 8):
+        for n in (1000, 1003, 100000):
+            for f in (0.0, 0.25, 27.0 / 64.0, 1.0):
+                cover = np.zeros(n, dtype=np.int64)
+                for r in range(world):
+                    e, l = kb.dist.stagger_layout(n, world, r, 1, f)
+                    if r == 1 or world == 1:
+                        assert e == (0, 0)                           # the long solver takes no early rows
+                    for a, b in (e, l):
+                        assert 0 <= a <= b <= n
+                        cover[a:b] += 1
+                assert np.all(cover == 1)
+                if world > 1 and f == 1.0:
+                    assert all(kb.dist.stagger_layout(n, world, r, 1, f)[1][0] == n for r in range(world))   # no late rows
+    # measured stage times at p = 5000, n = 1e5, m = 5 (profiles/r02_bench_n*.json): A = 147, B = 510, Ts = 836 ms
+    f2, plain2, stag2 = kb.dist.stagger_fraction(147.0, 510.0, 836.0, 2)
+    assert 0.35 < f2 < 0.45 and stag2 < 0.9 * plain2
+    assert kb.dist.stagger_fraction(115.0, 480.0, 836.0, 4)[0] == 1.0
+    assert kb.dist.stagger_fraction(115.0, 480.0, 836.0, 8)[0] == 1.0
+    fw, _, _ = kb.dist.stagger_fraction(115.0, 480.0, 8 * 836.0, 8)      # weak run: 8e5 rows in total
+    assert 0.3 < fw < 0.4 and fw * 64 == int(fw * 64)
+    assert kb.dist.stagger_fraction(500.0, 510.0, 836.0, 4)[0] == 0.0     # no gap: plain order
+    assert kb.dist.stagger_fraction(147.0, 510.0, 836.0, 1) == (0.0, 510.0 + 2 * 836.0, 510.0 + 2 * 836.0)
