@@ -11,7 +11,10 @@ on block-equicorrelated Sigma (blocks of 10, rho = 0.5, gamma = 0.25), p = 5000,
 Multi-GPU (one process per GPU, NCCL): STRONG scaling by default -- n is fixed, rows are sharded n/N per rank, the
 independent solves (:mvr || :sdp_ccd) run on different ranks (a single CCD solve is sequential: "replicas only"),
 s and the factor blocks are BROADCAST over NVLink (NCCL), sampling needs no collective (counter-based RNG keyed by
-the global row).  `scaling_alt` reports the weak-scaling run (n rows per GPU) next to it.  Three more objects ride
+the global row).  The long :sdp_ccd solve is the Amdahl term, so the step is STAGGERED: the ranks that do not run it sample
+as many of the :mvr rows as fit beside it (knockoffs.jl_b200/dist.py: stagger_fraction / stagger_layout), the rest is shared
+by all ranks afterwards; from 4 ranks on the m block columns of the factor are built on different ranks from the closed form
+of the recursion (kb_cond_factor_block_dev).  `scaling_alt` reports the weak-scaling run (n rows per GPU) next to it.  Three more objects ride
 on the same JSON line: `config5` (row-sharded dosage Gram + ONE NCCL all-reduce of the p x p sums + :maxent +
 sampling), `config4` (group :mvr, LD blocks dealt to ranks, the reduce hook over NCCL) and the CPU baseline.
 
